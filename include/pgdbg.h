@@ -1,0 +1,151 @@
+/*
+ * pgdbg.h - C ABI of libpgdbg.so: the B200 (sm_100a) implementation of the
+ * de Bruijn-graph hot path of Rinoahu/pangenome's kmer_numba.py.
+ *
+ * The reference has no FFI: its hot path is a chain of numba-jitted Python
+ * functions.  Each entry point below names the reference
+ * function(s) it replaces (file:line in /root/reference/kmer_numba.py); the
+ * Python host in pangenome_b200/ binds them with ctypes and re-creates the
+ * reference's stage API (seq2rdbg / dbg2rdbg / seq2graph) on top.
+ *
+ * Conventions
+ *   - every function returns PG_OK (0) or a negative PG_ERR_* code; the text of
+ *     the last error is available from pg_last_error(); nothing throws;
+ *   - all `d_` pointers are CALLER-OWNED DEVICE buffers (e.g. a torch tensor's
+ *     data_ptr()); the library allocates nothing on the device;
+ *   - sizes are int64_t; `stream` is a cudaStream_t passed as void*; work is
+ *     enqueued on it and the call returns without synchronising unless stated;
+ *   - one host thread per GPU (one process per GPU under torchrun).
+ *
+ * Key / value conventions (the compared artefacts)
+ *   key   = base-5 code of the k-mer, little-endian digits A0 G1 C2 T3 other 4
+ *           (kmer_numba.py:763-768, 975-985), k <= 27, as uint64;
+ *   val12 = (lastc[prev] << 6) | lastc[next], bit order A,T,G,C,N,$ (:736-747);
+ *   count = uint8 saturating at 255 (:551).
+ * Internally a table in PG_MODE_CANONICAL stores one slot per {X, rc(X)} pair
+ * holding both orientations' masks; exports expand it back to the reference's
+ * "both orientations are separate keys" form.
+ */
+#ifndef PGDBG_H
+#define PGDBG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_ERR_INVALID (-1)    /* bad argument */
+#define PG_ERR_CUDA (-2)       /* a CUDA runtime call failed */
+#define PG_ERR_WORKSPACE (-3)  /* workspace too small */
+#define PG_ERR_CAPACITY (-4)   /* an output buffer / table is too small */
+
+#define PG_MODE_LITERAL 0      /* one strand, literal keys            (-c 0 / -c 1)       */
+#define PG_MODE_LITERAL_RC 1   /* both strands, two literal inserts per position (-c 2/3) */
+#define PG_MODE_CANONICAL 2    /* both strands, one paired slot per position     (-c 2/3) */
+
+/* indices into the int64 stats block of a table */
+#define PG_STAT_OVERFLOW 0     /* != 0: probing gave up, table too small          */
+#define PG_STAT_SHORT 1        /* insertions of the short-record sentinel key (Q5) */
+#define PG_STAT_USED 2         /* occupied slots (filled by pg_table_count)        */
+#define PG_STAT_ENTRIES 3      /* entries in reference convention (pg_table_count) */
+#define PG_STAT_WORDS 8
+
+typedef void *pg_stream_t;
+
+/* An open-addressing table: `capacity` (power of two) 16-byte slots
+ * {uint64 key, uint32 masks, uint32 count}.  Replaces class oakht
+ * (kmer_numba.py:340-679) and init_dict (:1097-1122). */
+typedef struct pg_table {
+    uint64_t *d_slots;   /* device, 2 * capacity uint64 */
+    int64_t capacity;    /* power of two */
+    int64_t *d_stats;    /* device, PG_STAT_WORDS int64 */
+    int32_t mode;        /* PG_MODE_* */
+    int32_t k;           /* k-mer length, 1..27 */
+} pg_table;
+
+const char *pg_last_error(void);
+int pg_version(void);
+/* number of SMs of the current device (grid sizing); negative on error */
+int pg_device_sms(void);
+
+/* ---- K1: FASTA scan + pack --------------------------------------------------
+ * Replaces seq2bytes/readline_jit_/seqio_jit_ (kmer_numba.py:117-188) and the
+ * alpha / lastc / tab_rev_bytes character tables (:191-195, 736-768).
+ * Input : d_fasta[nbytes], the raw file.
+ * Output: d_pk2  - 2 bits per base, 16 bases per uint32 (base i of the
+ *                  concatenated sequence stream at bits 2*(i%16) of word i/16);
+ *                  ACGT hold the base-5 digit (A0 G1 C2 T3); ambiguous bases
+ *                  hold 0 for N/n and 1 for anything else;
+ *         d_amb  - 1 bit per base, 32 per uint32: set for non-ACGT bytes;
+ *         both must hold pg_pack_words(cap_bases) uint32 (padding included) and
+ *         cap_bases >= nbytes always suffices;
+ *         d_hdr_off[r] - byte offset of record r's '>' in the file;
+ *         d_seq_off[r] - offset of record r's first base in the stream,
+ *                        d_seq_off[n_rec] = end of the last record;
+ *         d_counts[0] = n_rec (may exceed cap_records: then only the first
+ *                       cap_records entries were written - grow and call again),
+ *         d_counts[1] = total bases in the stream, d_counts[2] = '\n' count.
+ * Bases that precede the first header occupy [0, d_seq_off[0]) and belong to no
+ * record (the reference drops them, :150-152).  Quirks kept: the last byte of
+ * every line is dropped even without a final newline (Q8); '\r' is a base (Q9).
+ */
+int64_t pg_pack_words(int64_t cap_bases);
+int64_t pg_fasta_workspace_bytes(int64_t nbytes);
+int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes,
+                       uint32_t *d_pk2, uint32_t *d_amb, int64_t cap_bases,
+                       int64_t *d_hdr_off, int64_t *d_seq_off, int64_t cap_records,
+                       int64_t *d_counts, void *d_ws, int64_t ws_bytes, pg_stream_t stream);
+
+/* ---- K2+K3: k-mer extraction fused with table insertion ---------------------
+ * pg_table_clear  : all slots empty, stats zero       (oakht.__init__ :341-352)
+ * pg_kmer_insert  : for every k-mer occurrence of records [0, n_rec) whose
+ *                   start lies in stream range [g_begin, g_end): key/val as
+ *                   build_dbg + add_kmer (:1036-1093), both strands unless
+ *                   mode == PG_MODE_LITERAL (seq2dbg_jit_ :1202-1230), including
+ *                   Q1 (predecessor of each strand's last k-mer), Q3, Q4, Q5.
+ *                   Records shorter than k only bump PG_STAT_SHORT (counted
+ *                   when their offset lies in the range).
+ */
+int64_t pg_table_bytes(int64_t capacity);
+int pg_table_clear(const pg_table *t, pg_stream_t stream);
+int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb,
+                   const int64_t *d_seq_off, int64_t n_rec, int64_t g_begin, int64_t g_end,
+                   pg_stream_t stream);
+
+/* ---- table read-out ---------------------------------------------------------
+ * pg_table_count   : fills PG_STAT_USED / PG_STAT_ENTRIES in t->d_stats.
+ * pg_table_export  : unsorted (key, val12, count<=255) in the reference's
+ *                    convention (iteritems :623-631): both orientations as
+ *                    separate keys, plus the sentinel key 2^64-1 (val 32) if
+ *                    any short record was inserted.  *d_n = entries produced;
+ *                    entries beyond cap are dropped (compare *d_n with cap).
+ * pg_table_checksum: d_out[0..2] = (entries, sum, xor) of mix64 over the same
+ *                    entries - order independent, equals
+ *                    oracle.table_checksum() of the reference's table.
+ */
+int pg_table_count(const pg_table *t, pg_stream_t stream);
+int pg_table_export(const pg_table *t, uint64_t *d_keys, uint16_t *d_vals, uint8_t *d_cnts,
+                    int64_t cap, int64_t *d_n, pg_stream_t stream);
+int pg_table_checksum(const pg_table *t, uint64_t *d_out, pg_stream_t stream);
+
+/* ---- K4: reduced-dBG selection ---------------------------------------------
+ * Replaces nbit + build_rdbg_jit_ + dbg2rdbg (kmer_numba.py:723-727, 1292-1321):
+ * keep k-mers with popcount(in6) != 1 or popcount(out6) != 1.
+ * pg_rdbg_count : d_out[0] = slots the rdBG table needs, d_out[1] = members.
+ * pg_rdbg_select: inserts the members of `dbg` into the cleared table `rdbg`
+ *                 (same mode/k; capacity >= 2 * d_out[0] recommended).  The
+ *                 rdBG count word holds flags: bit0/bit1 = orientation 0/1 is a
+ *                 member, bit2 = key present only as the phantom key 0 (Q6).
+ * pg_rdbg_export: unsorted member (key, val12), reference convention.
+ */
+int pg_rdbg_count(const pg_table *dbg, int64_t *d_out, pg_stream_t stream);
+int pg_rdbg_select(const pg_table *dbg, const pg_table *rdbg, pg_stream_t stream);
+int pg_rdbg_export(const pg_table *rdbg, uint64_t *d_keys, uint16_t *d_vals,
+                   int64_t cap, int64_t *d_n, pg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGDBG_H */

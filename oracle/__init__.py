@@ -93,6 +93,7 @@ def run(fasta, k, c=2, Ns=2 ** 63, stages=4, edge_offbit=5, image=False):
         nrec = g["n_records"]
         hdr_off = _arr(L, h, "hdr_off", nrec)
         hdr_len = _arr(L, h, "hdr_len", nrec)
+        out["hdr_off"] = hdr_off
         out["seq_off"] = _arr(L, h, "seq_off", nrec + 1)
         out["seq"] = _arr(L, h, "seq", int(out["seq_off"][-1]) if nrec else 0)
         raw = bytes(fasta)

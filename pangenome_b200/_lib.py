@@ -1,0 +1,65 @@
+"""ctypes binding of libpgdbg.so (include/pgdbg.h).  Fails loudly: there is no
+CPU fallback anywhere in this package."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpgdbg.so")
+
+PG_MODE_LITERAL, PG_MODE_LITERAL_RC, PG_MODE_CANONICAL = 0, 1, 2
+PG_STAT_OVERFLOW, PG_STAT_SHORT, PG_STAT_USED, PG_STAT_ENTRIES, PG_STAT_WORDS = 0, 1, 2, 3, 8
+
+c_i64, c_int, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
+
+
+class PgTable(ctypes.Structure):
+    _fields_ = [("d_slots", c_vp), ("capacity", c_i64), ("d_stats", c_vp), ("mode", ctypes.c_int32),
+                ("k", ctypes.c_int32)]
+
+
+PT = ctypes.POINTER(PgTable)
+
+# name -> (restype, argtypes); every symbol include/pgdbg.h declares
+SIGNATURES = {
+    "pg_last_error": (ctypes.c_char_p, []),
+    "pg_version": (c_int, []),
+    "pg_device_sms": (c_int, []),
+    "pg_pack_words": (c_i64, [c_i64]),
+    "pg_fasta_workspace_bytes": (c_i64, [c_i64]),
+    "pg_fasta_scan_pack": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "pg_table_bytes": (c_i64, [c_i64]),
+    "pg_table_clear": (c_int, [PT, c_vp]),
+    "pg_kmer_insert": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "pg_table_count": (c_int, [PT, c_vp]),
+    "pg_table_export": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "pg_table_checksum": (c_int, [PT, c_vp, c_vp]),
+    "pg_rdbg_count": (c_int, [PT, c_vp, c_vp]),
+    "pg_rdbg_select": (c_int, [PT, PT, c_vp]),
+    "pg_rdbg_export": (c_int, [PT, c_vp, c_vp, c_i64, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+class PgError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise PgError("libpgdbg.so is missing (%s): build it with `python -m pangenome_b200.build`; "
+                          "pangenome_b200 has no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)      # AttributeError if the library lacks a declared symbol
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise PgError("%s failed (%d): %s" % (what, rc, load().pg_last_error().decode(errors="replace")))

@@ -1,0 +1,33 @@
+// common.cu - error reporting and device queries for libpgdbg.
+#include <stdarg.h>
+#include "common.cuh"
+
+thread_local char pg_err_buf[512] = "";
+
+int pg_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(pg_err_buf, sizeof pg_err_buf, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int pg_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;   // B200
+        sms = n;
+    }
+    return sms;
+}
+
+extern "C" const char *pg_last_error(void) { return pg_err_buf; }
+extern "C" int pg_version(void) { return 100; }
+extern "C" int pg_device_sms(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PG_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return PG_ERR_CUDA;
+    return n;
+}

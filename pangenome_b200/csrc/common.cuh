@@ -1,0 +1,101 @@
+// common.cuh - shared device/host helpers for libpgdbg (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/pgdbg.h"
+
+#define PG_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define PG_HD __host__ __device__ __forceinline__
+
+extern thread_local char pg_err_buf[512];
+int pg_fail(int code, const char *fmt, ...);
+
+#define PG_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return pg_fail(PG_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,       \
+                           cudaGetErrorString(e_));                                        \
+    } while (0)
+
+int pg_num_sms();
+
+// ---- hashing ---------------------------------------------------------------
+PG_HD uint64_t pg_mix64(uint64_t x) {   // murmur3 fmix64: a bijection on u64
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+// ---- base-5 k-mer codes (kmer_numba.py:975-985: code = sum alpha[s[i]] * 5^i) ----
+#define PG_INV5 0xCCCCCCCCCCCCCCCDull   // 5^-1 mod 2^64: exact division of multiples of 5
+PG_HD uint64_t pg_pow5(int e) {
+    uint64_t p = 1;
+    for (int i = 0; i < e; i++) p *= 5;
+    return p;
+}
+// complement digit: A0<->T3, G1<->C2, other 4 -> 4 (reverse_jit_ maps every non-ACGT byte to N)
+PG_HD uint32_t pg_cdig(uint32_t d) { return d == 4 ? 4u : 3u - d; }
+
+// reverse-complement of a base-5 code (the key the rc strand inserts for the same window)
+PG_HD uint64_t pg_rc_code(uint64_t code, int k) {
+    uint64_t r = 0;
+    for (int i = 0; i < k; i++) { r = r * 5 + pg_cdig((uint32_t)(code % 5)); code /= 5; }
+    return r;
+}
+
+// ---- symbols: 0..3 = A G C T (base-5 digit), 4 = N/n, 5 = any other byte ------------
+// lastc on the forward strand (kmer_numba.py:736-743): A1 T2 G4 C8 N16 other 0
+PG_HD uint32_t pg_lastc_f(uint32_t sym) { return (uint32_t)((0x001002080401ull >> (8 * sym)) & 0xff); }
+// lastc of the complemented byte (rc strand; every non-ACGT byte became 'N')
+PG_HD uint32_t pg_lastc_r(uint32_t sym) { return (uint32_t)((0x101001040802ull >> (8 * sym)) & 0xff); }
+
+PG_HD int pg_popc12(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+// rdBG membership of one orientation's 12-bit value (build_rdbg_jit_ :1299-1303)
+PG_HD bool pg_is_rdbg(uint32_t val12) { return !(pg_popc12(val12 >> 6) == 1 && pg_popc12(val12 & 63) == 1); }
+
+// ---- order-independent table checksum (mirrors oracle.table_checksum) ----------------
+PG_HD uint64_t pg_entry_mix(uint64_t key, uint32_t val12, uint32_t cnt) {
+    uint64_t w = ((uint64_t)val12 << 8) | cnt;
+    return pg_mix64(key ^ (w * 0x9E3779B97F4A7C15ull));
+}
+
+// ---- ASCII classification for K1 ---------------------------------------------------
+// returns the 3-bit symbol of a byte
+PG_HD uint32_t pg_sym_of_byte(uint32_t c) {
+    uint32_t u = c & 0xDF;
+    if (u == 'A') return 0;
+    if (u == 'G') return 1;
+    if (u == 'C') return 2;
+    if (u == 'T') return 3;
+    if (u == 'N') return 4;
+    return 5;
+}
+
+#ifdef __CUDACC__
+// 128-bit streaming load (read-once data: do not allocate in L1)
+__device__ __forceinline__ uint4 pg_ld_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+// 16-byte table-slot load at L2 (slots are mutated by atomics, never trust L1)
+__device__ __forceinline__ void pg_ld_slot(const uint64_t *p, uint64_t &key, uint64_t &val) {
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(key), "=l"(val) : "l"(p));
+}
+__device__ __forceinline__ void pg_red_or32(uint32_t *p, uint32_t v) {
+    asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void pg_red_add32(uint32_t *p, uint32_t v) {
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#endif

@@ -1,0 +1,280 @@
+// fasta_pack.cu - K1: FASTA scan + 2-bit pack on the GPU.
+//
+// Replaces the reference's byte-at-a-time reader (readline_jit_ / seqio_jit_,
+// kmer_numba.py:122-188) and the per-base table lookups (alpha / lastc, :736-768)
+// with three launches over 16 KB tiles of the raw file:
+//   A  k1_tile_summaries  every tile -> what it does to the line-state machine for each of the three
+//                         possible entry states (Sum3) + its real '\n' count        [reads 1 B/byte]
+//   B  k1_tile_scan       one CTA composes the tile summaries in file order -> per-tile entry state,
+//                         base rank, record rank; zeroes the few words tiles share   [12 B/tile]
+//   C  k1_tile_pack       every tile again: classify, rank, pack 2-bit digits + 1-bit ambiguity
+//                         mask into shared memory, write whole words coalesced       [reads 1 B/byte,
+//                         writes 0.375 B/base]
+// HBM-bound streaming work: 128-bit coalesced loads, SWAR byte classification (no per-byte loops),
+// shuffle scans, shared-memory staging so global stores are full words.
+#include "fasta_chunk.cuh"
+
+namespace {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_SUB = K1_THREADS * 16;   // bytes per sub-tile
+constexpr int K1_NSUB = 4;
+constexpr int K1_TILE = K1_SUB * K1_NSUB; // 16 KB
+
+struct TileSum { uint32_t v[3]; uint32_t real_nl; };
+struct TileEntry { uint64_t seq; uint64_t hdr; uint32_t state; uint32_t dead; };
+
+__device__ __forceinline__ Sum3 shfl_up_sum3(const Sum3 &x, int o) {
+    Sum3 y;
+#pragma unroll
+    for (int i = 0; i < 3; i++) y.v[i] = __shfl_up_sync(0xffffffffu, x.v[i], o);
+    return y;
+}
+
+// Ordered block scan of Sum3 (non-commutative).  Returns the exclusive prefix of this thread and
+// the block total.  s_warp must hold K1_THREADS/32 Sum3.
+__device__ __forceinline__ void block_scan_sum3(const Sum3 &mine, Sum3 *s_warp, Sum3 &excl, Sum3 &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Sum3 inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Sum3 y = shfl_up_sum3(inc, o);
+        if (lane >= o) inc = sum3_compose(y, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    Sum3 wp = sum3_identity();
+    Sum3 tot = sum3_identity();
+#pragma unroll
+    for (int w = 0; w < K1_THREADS / 32; w++) {
+        Sum3 t = s_warp[w];
+        if (w < warp) wp = sum3_compose(wp, t);
+        tot = sum3_compose(tot, t);
+    }
+    Sum3 prev = shfl_up_sum3(inc, 1);
+    excl = (lane == 0) ? wp : sum3_compose(wp, prev);
+    total = tot;
+    __syncthreads();
+}
+
+__device__ __forceinline__ ChunkCls load_classify(const uint8_t *fasta, int64_t nbytes, int64_t off) {
+    uint32_t w[4] = {0, 0, 0, 0};
+    int64_t left = nbytes - off;
+    if (left >= 16) {
+        uint4 v = pg_ld_stream(reinterpret_cast<const uint4 *>(fasta + off));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else if (left > 0) {   // the single ragged chunk at the end of the file
+        uint64_t lo = 0, hi = 0;
+        for (int i = 0; i < (int)left; i++) {
+            uint64_t b = fasta[off + i];
+            if (i < 8) lo |= b << (8 * i); else hi |= b << (8 * (i - 8));
+        }
+        w[0] = (uint32_t)lo; w[1] = (uint32_t)(lo >> 32); w[2] = (uint32_t)hi; w[3] = (uint32_t)(hi >> 32);
+    }
+    int n_file = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+    return classify16(w, n_file, left <= 16);
+}
+
+__global__ void __launch_bounds__(K1_THREADS)
+k1_tile_summaries(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles, TileSum *__restrict__ sums) {
+    __shared__ Sum3 s_warp[K1_THREADS / 32];
+    __shared__ uint32_t s_nl;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) s_nl = 0;
+        Sum3 carry = sum3_identity();
+        uint32_t my_nl = 0;
+        for (int sub = 0; sub < K1_NSUB; sub++) {
+            int64_t off = tile * K1_TILE + (int64_t)sub * K1_SUB + threadIdx.x * 16;
+            ChunkCls c = load_classify(fasta, nbytes, off);
+            my_nl += c.real_nl;
+            Sum3 excl, total;
+            block_scan_sum3(chunk_sum3(c), s_warp, excl, total);
+            carry = sum3_compose(carry, total);
+        }
+        my_nl = __reduce_add_sync(0xffffffffu, my_nl);
+        if ((threadIdx.x & 31) == 0 && my_nl) atomicAdd(&s_nl, my_nl);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            TileSum t; t.v[0] = carry.v[0]; t.v[1] = carry.v[1]; t.v[2] = carry.v[2]; t.real_nl = s_nl;
+            sums[tile] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// 64-bit running state of the file-order scan
+struct Run { uint64_t seq, hdr; uint32_t state; uint64_t nl; };
+struct Agg3 { uint64_t seq[3], hdr[3]; uint32_t st[3]; uint64_t nl; };
+
+__device__ __forceinline__ void agg3_push(Agg3 &a, const TileSum &t) {
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+        uint32_t st_ = a.st[s]; uint32_t y = st_ == 0 ? t.v[0] : (st_ == 1 ? t.v[1] : t.v[2]);
+        a.seq[s] += SV_SEQ(y); a.hdr[s] += SV_HDR(y); a.st[s] = SV_STATE(y);
+    }
+    a.nl += t.real_nl;
+}
+
+constexpr int K1B_THREADS = 256;
+
+__global__ void __launch_bounds__(K1B_THREADS)
+k1_tile_scan(const TileSum *__restrict__ sums, int64_t ntiles, TileEntry *__restrict__ entries,
+             uint32_t *__restrict__ pk2, uint32_t *__restrict__ amb, int64_t *__restrict__ seq_off,
+             int64_t cap_records, int64_t *__restrict__ counts) {
+    __shared__ Agg3 s_agg[K1B_THREADS];
+    __shared__ Run s_run[K1B_THREADS];
+    const int t = threadIdx.x;
+    int64_t per = (ntiles + K1B_THREADS - 1) / K1B_THREADS;
+    int64_t lo = (int64_t)t * per, hi = lo + per < ntiles ? lo + per : ntiles;
+    Agg3 a;
+#pragma unroll
+    for (int s = 0; s < 3; s++) { a.seq[s] = 0; a.hdr[s] = 0; a.st[s] = s; }
+    a.nl = 0;
+    for (int64_t i = lo; i < hi; i++) agg3_push(a, sums[i]);
+    s_agg[t] = a;
+    __syncthreads();
+    if (t == 0) {   // 256 compositions, serial: a few microseconds
+        Run r; r.seq = 0; r.hdr = 0; r.state = ST_LINE_START; r.nl = 0;
+        for (int i = 0; i < K1B_THREADS; i++) {
+            s_run[i] = r;
+            const Agg3 &g = s_agg[i];
+            uint32_t s = r.state;
+            r.seq += g.seq[s]; r.hdr += g.hdr[s]; r.state = g.st[s]; r.nl += g.nl;
+        }
+        // A file without any real '\n' yields no line at all (readline_jit_ :129-132: `end > start > 0`)
+        bool dead = (r.nl == 0);
+        counts[0] = dead ? 0 : (int64_t)r.hdr;
+        counts[1] = dead ? 0 : (int64_t)r.seq;
+        counts[2] = (int64_t)r.nl;
+        counts[3] = dead ? 1 : 0;
+        if (!dead && (int64_t)r.hdr <= cap_records) seq_off[r.hdr] = (int64_t)r.seq;
+        if (dead) seq_off[0] = 0;
+        // zero the padding the k-mer kernels may read past the last base
+        uint64_t tot = dead ? 0 : r.seq;
+        for (int i = 0; i < 16; i++) { pk2[(tot >> 4) + i] = 0; amb[(tot >> 5) + i] = 0; }
+    }
+    __syncthreads();
+    bool dead = counts[3] != 0;
+    Run r = s_run[t];
+    for (int64_t i = lo; i < hi; i++) {
+        TileEntry e; e.seq = r.seq; e.hdr = r.hdr; e.state = r.state; e.dead = dead ? 1u : 0u;
+        entries[i] = e;
+        if (!dead) { pk2[r.seq >> 4] = 0; amb[r.seq >> 5] = 0; }   // words shared between neighbouring tiles
+        TileSum ts = sums[i];
+        uint32_t y = r.state == 0 ? ts.v[0] : (r.state == 1 ? ts.v[1] : ts.v[2]);
+        r.seq += SV_SEQ(y); r.hdr += SV_HDR(y); r.state = SV_STATE(y);
+    }
+}
+
+constexpr int K1_PKW = (K1_TILE + 32) / 16 + 2;   // staged pk2 words per tile
+constexpr int K1_AMW = (K1_TILE + 32) / 32 + 2;
+
+__global__ void __launch_bounds__(K1_THREADS)
+k1_tile_pack(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles,
+             const TileEntry *__restrict__ entries, uint32_t *__restrict__ pk2, uint32_t *__restrict__ amb,
+             int64_t *__restrict__ hdr_off, int64_t *__restrict__ seq_off, int64_t cap_records) {
+    __shared__ Sum3 s_warp[K1_THREADS / 32];
+    __shared__ uint32_t s_pk[K1_PKW];
+    __shared__ uint32_t s_am[K1_AMW];
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        TileEntry e = entries[tile];
+        if (e.dead) return;
+        for (int i = threadIdx.x; i < K1_PKW; i += K1_THREADS) s_pk[i] = 0;
+        for (int i = threadIdx.x; i < K1_AMW; i += K1_THREADS) s_am[i] = 0;
+        __syncthreads();
+        const uint32_t a0 = (uint32_t)(e.seq & 31);
+        uint32_t cstate = e.state, cseq = 0, chdr = 0;
+        for (int sub = 0; sub < K1_NSUB; sub++) {
+            int64_t off = tile * K1_TILE + (int64_t)sub * K1_SUB + threadIdx.x * 16;
+            ChunkCls c = load_classify(fasta, nbytes, off);
+            Sum3 excl, total;
+            block_scan_sum3(chunk_sum3(c), s_warp, excl, total);
+            uint32_t x = sum3_sel(excl, cstate);
+            ChunkRun r = chunk_run(c, SV_STATE(x));
+            uint32_t rank = cseq + SV_SEQ(x);          // bases of this tile before my chunk
+            uint32_t cnt = pg_popc(r.seqmask);
+            if (cnt) {
+                uint32_t d = pext16_2bit(c.dig, r.seqmask);
+                uint32_t m = pext16_1bit(c.amb, r.seqmask);
+                if (cnt < 16) d &= (1u << (2 * cnt)) - 1u;
+                uint32_t q = a0 + rank;
+                uint32_t sh = 2 * (q & 15);
+                atomicOr(&s_pk[q >> 4], d << sh);
+                if (sh && (d >> (32 - sh))) atomicOr(&s_pk[(q >> 4) + 1], d >> (32 - sh));
+                if (m) {
+                    uint32_t sh1 = q & 31;
+                    atomicOr(&s_am[q >> 5], m << sh1);
+                    if (sh1 > 16 && (m >> (32 - sh1))) atomicOr(&s_am[(q >> 5) + 1], m >> (32 - sh1));
+                }
+            }
+            if (r.hs) {   // rare: this chunk starts record(s)
+                uint32_t hs = r.hs; uint64_t idx = e.hdr + chdr + SV_HDR(x);
+                while (hs) {
+                    int j = pg_ctz(hs); hs &= hs - 1;
+                    if ((int64_t)idx < cap_records) {
+                        hdr_off[idx] = off + j;
+                        seq_off[idx] = (int64_t)(e.seq + rank + pg_popc(r.seqmask & ((1u << j) - 1u)));
+                    }
+                    idx++;
+                }
+            }
+            uint32_t tt = sum3_sel(total, cstate);
+            cstate = SV_STATE(tt); cseq += SV_SEQ(tt); chdr += SV_HDR(tt);
+        }
+        __syncthreads();
+        // write-out: words fully owned by this tile are stored, shared boundary words are OR-ed
+        const uint32_t end = a0 + cseq;
+        uint32_t *gpk = pk2 + ((e.seq >> 5) << 1);
+        uint32_t *gam = amb + (e.seq >> 5);
+        const uint32_t npk = (end + 15) >> 4, nam = (end + 31) >> 5;
+        for (uint32_t w = threadIdx.x; w < npk; w += K1_THREADS) {
+            uint32_t v = s_pk[w];
+            if (16 * w >= a0 && 16 * (w + 1) <= end) gpk[w] = v;
+            else if (v) atomicOr(&gpk[w], v);
+        }
+        for (uint32_t w = threadIdx.x; w < nam; w += K1_THREADS) {
+            uint32_t v = s_am[w];
+            if (32 * w >= a0 && 32 * (w + 1) <= end) gam[w] = v;
+            else if (v) atomicOr(&gam[w], v);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t pg_pack_words(int64_t cap_bases) { return (cap_bases < 0 ? 0 : cap_bases) / 16 + 32; }
+
+extern "C" int64_t pg_fasta_workspace_bytes(int64_t nbytes) {
+    int64_t ntiles = (nbytes + K1_TILE - 1) / K1_TILE;
+    if (ntiles < 1) ntiles = 1;
+    return ntiles * (int64_t)(sizeof(TileSum) + sizeof(TileEntry)) + 256;
+}
+
+extern "C" int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes, uint32_t *d_pk2, uint32_t *d_amb,
+                                  int64_t cap_bases, int64_t *d_hdr_off, int64_t *d_seq_off, int64_t cap_records,
+                                  int64_t *d_counts, void *d_ws, int64_t ws_bytes, pg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (nbytes < 0 || !d_pk2 || !d_amb || !d_hdr_off || !d_seq_off || !d_counts || !d_ws || cap_records < 0)
+        return pg_fail(PG_ERR_INVALID, "pg_fasta_scan_pack: null buffer or negative size");
+    if (nbytes > 0 && !d_fasta) return pg_fail(PG_ERR_INVALID, "pg_fasta_scan_pack: d_fasta is null");
+    if (cap_bases < nbytes) return pg_fail(PG_ERR_CAPACITY, "pg_fasta_scan_pack: cap_bases %lld < nbytes %lld",
+                                           (long long)cap_bases, (long long)nbytes);
+    if (ws_bytes < pg_fasta_workspace_bytes(nbytes))
+        return pg_fail(PG_ERR_WORKSPACE, "pg_fasta_scan_pack: workspace %lld < %lld", (long long)ws_bytes,
+                       (long long)pg_fasta_workspace_bytes(nbytes));
+    if ((reinterpret_cast<uintptr_t>(d_fasta) & 15) != 0)
+        return pg_fail(PG_ERR_INVALID, "pg_fasta_scan_pack: d_fasta must be 16-byte aligned");
+    int64_t ntiles = (nbytes + K1_TILE - 1) / K1_TILE;
+    TileSum *sums = reinterpret_cast<TileSum *>(d_ws);
+    TileEntry *entries = reinterpret_cast<TileEntry *>(reinterpret_cast<char *>(d_ws) + ((ntiles < 1 ? 1 : ntiles) * sizeof(TileSum) + 15) / 16 * 16);
+    int sms = pg_num_sms();
+    int grid = (int)(ntiles < (int64_t)sms * 8 ? (ntiles < 1 ? 1 : ntiles) : (int64_t)sms * 8);
+    if (ntiles > 0) k1_tile_summaries<<<grid, K1_THREADS, 0, stream>>>(d_fasta, nbytes, ntiles, sums);
+    k1_tile_scan<<<1, K1B_THREADS, 0, stream>>>(sums, ntiles, entries, d_pk2, d_amb, d_seq_off, cap_records, d_counts);
+    if (ntiles > 0)
+        k1_tile_pack<<<grid, K1_THREADS, 0, stream>>>(d_fasta, nbytes, ntiles, entries, d_pk2, d_amb, d_hdr_off,
+                                                     d_seq_off, cap_records);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}

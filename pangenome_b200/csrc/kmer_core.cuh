@@ -1,0 +1,104 @@
+// kmer_core.cuh - per-position k-mer arithmetic shared by the insert (K2/K3) and path (K5) kernels.
+// Host+device so tests/host_emul.cu can run the same code on the CPU against the oracle.
+//
+// Restates build_dbg / seq2ns_jit_ (kmer_numba.py:1052-1090, 991-1033) in position-parallel form:
+// for a forward position p of a record of length n (k-mer = s[p..p+k)), the forward strand holds the
+// occurrence (code, prev, next) and the reverse-complement strand holds, at q = n-k-p, the occurrence
+// (rc(code), prev', next') with prev' = comp(s[p+k]), next' = comp(s[p-1]).  Quirks kept:
+//   Q1  the LAST occurrence of each strand takes its predecessor one base too far left (the reference
+//       reuses a loop variable, :1080/:1019)  -> fwd p = n-k uses s[p-2]; rc q = n-k (p = 0) uses s[k+1];
+//   Q3  '#' (no in-bit) at a strand start, '$' (out-bit 32) at a strand end;
+//   Q4  a non-ACGTN byte has lastc 0 on the forward strand but is 'N' (16) on the rc strand;
+//   Q2  n == k+1 is undefined upstream; here the true predecessor is used.
+#pragma once
+#include "common.cuh"
+
+// A 96-base window of the packed stream around a 32-base word: bases [-32, 64) relative to its first.
+struct PgWindow {
+    uint64_t prv, cur, nxt;     // 2-bit digits, 32 bases each
+    uint32_t aprv, acur, anxt;  // ambiguity bits
+    PG_HD uint32_t dig2(int j) const {   // j in [-32, 64)
+        uint64_t w = j < 0 ? prv : (j < 32 ? cur : nxt);
+        return (uint32_t)(w >> (2 * (j & 31))) & 3u;
+    }
+    PG_HD uint32_t ambbit(int j) const {
+        uint32_t w = j < 0 ? aprv : (j < 32 ? acur : anxt);
+        return (w >> (j & 31)) & 1u;
+    }
+    // base-5 digit: A0 G1 C2 T3, anything else 4 (alpha, kmer_numba.py:763-768)
+    PG_HD uint32_t dig5(int j) const { return ambbit(j) ? 4u : dig2(j); }
+    // symbol: 0..3 ACGT digit, 4 = N/n, 5 = other byte
+    PG_HD uint32_t sym(int j) const { return ambbit(j) ? 4u + dig2(j) : dig2(j); }
+    PG_HD bool any_amb() const { return (aprv | acur | anxt) != 0; }
+};
+
+// 12-bit values of the forward-strand occurrence (vf) and of the paired rc-strand occurrence (vr).
+// `j` = window index of the k-mer's first base, p = its position in the record, n = record length.
+PG_HD void pg_occ_vals(const PgWindow &w, int j, int64_t p, int64_t n, int k, uint32_t &vf, uint32_t &vr) {
+    const bool first = (p == 0), last = (p == n - k), q1 = (n >= (int64_t)k + 2);
+    uint32_t lpf = first ? 0u : pg_lastc_f(w.sym(j + ((last && q1) ? -2 : -1)));
+    uint32_t lnf = last ? 32u : pg_lastc_f(w.sym(j + k));
+    uint32_t lpr = last ? 0u : pg_lastc_r(w.sym(j + ((first && q1) ? k + 1 : k)));
+    uint32_t lnr = first ? 32u : pg_lastc_r(w.sym(j - 1));
+    vf = (lpf << 6) | lnf;
+    vr = (lpr << 6) | lnr;
+}
+
+// forward / rc base-5 codes of the window [j, j+k) from scratch
+PG_HD void pg_codes_init(const PgWindow &w, int j, int k, uint64_t &F, uint64_t &R) {
+    F = 0; R = 0;
+    uint64_t p5 = 1;
+    for (int i = 0; i < k; i++) {
+        uint32_t d = w.dig5(j + i);
+        F += (uint64_t)d * p5;            // sum d[i] * 5^i
+        R = R * 5 + pg_cdig(d);           // sum cdig(d[k-1-i]) * 5^i
+        p5 *= 5;
+    }
+}
+// slide both codes one base to the right: window [j, j+k) -> [j+1, j+k+1)
+PG_HD void pg_codes_roll(const PgWindow &w, int j, int k, uint64_t pow5km1, uint64_t &F, uint64_t &R) {
+    uint32_t dout = w.dig5(j), din = w.dig5(j + k);
+    F = (F - dout) * PG_INV5 + (uint64_t)din * pow5km1;       // Nu // 5 + c * 5^(k-1)   (:1070)
+    R = (R - (uint64_t)pg_cdig(dout) * pow5km1) * 5 + pg_cdig(din);
+}
+
+// What one position contributes to a table in each mode.
+struct PgUpdate { uint64_t key; uint32_t masks; uint32_t inc; };
+// canonical pairing: slot key = min(F, R); masks = m(orientation 0) | m(orientation 1) << 16,
+// orientation 0 being the one whose literal code equals the slot key.  Palindromes (F == R, only
+// possible with ambiguity digits or even k) fold both strands into orientation 0 and count twice.
+PG_HD PgUpdate pg_canonical_update(uint64_t F, uint64_t R, uint32_t vf, uint32_t vr) {
+    PgUpdate u;
+    if (F < R) { u.key = F; u.masks = vf | (vr << 16); u.inc = 1; }
+    else if (R < F) { u.key = R; u.masks = vr | (vf << 16); u.inc = 1; }
+    else { u.key = F; u.masks = vf | vr; u.inc = 2; }
+    return u;
+}
+
+// ---- read-out: one occupied slot -> its entries in the reference's convention --------------------
+struct PgEntry { uint64_t key; uint32_t val, cnt; };
+
+// slot value word: low 32 = masks (orientation 0 | orientation 1 << 16), high 32 = count.
+// Returns the number of entries (0..2): both orientations are separate keys upstream (F3).
+PG_HD int pg_slot_entries(uint64_t key, uint64_t v, int mode, int k, PgEntry e[2]) {
+    if (key == PG_EMPTY) return 0;
+    uint32_t masks = (uint32_t)v, cnt = (uint32_t)(v >> 32);
+    uint32_t c255 = cnt < 255u ? cnt : 255u;          // uint8 saturation (kmer_numba.py:551)
+    e[0].key = key; e[0].val = masks & 0xFFFu; e[0].cnt = c255;
+    if (mode != PG_MODE_CANONICAL) return 1;
+    uint64_t rk = pg_rc_code(key, k);
+    if (rk == key) return 1;      // palindrome: both strands were folded into orientation 0 (count += 2 each)
+    e[1].key = rk; e[1].val = (masks >> 16) & 0xFFFu; e[1].cnt = c255;
+    return 2;
+}
+
+// flags of an rdBG slot: bit0/bit1 = orientation 0/1 is a member, bit2 = phantom key 0 (Q6)
+PG_HD uint32_t pg_rdbg_flags(uint64_t key, uint64_t v, int mode, int k) {
+    PgEntry e[2];
+    int n = pg_slot_entries(key, v, mode, k, e);
+    if (n == 0) return 0;
+    uint32_t f = pg_is_rdbg(e[0].val) ? 1u : 0u;
+    if (n == 2 && pg_is_rdbg(e[1].val)) f |= 2u;
+    if (key == 0) f |= 4u;    // has_key(0) is true for every table (equality before occupancy, :532/:599)
+    return f;
+}

@@ -1,0 +1,233 @@
+"""Host side of the B200 dBG path: device buffers (torch), launches through the
+C-ABI (ctypes), and the small amount of host logic the reference keeps in its
+un-jitted stage functions (record prefix for ``-n``, table sizing).
+
+torch is plumbing only (allocation, streams, H2D/D2H); every computation on the
+sequence data is a kernel of libpgdbg.so.  No CPU fallback: constructing any of
+these objects without CUDA raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PgError, PgTable, check
+
+_DEFAULT_LOAD = 0.5
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise PgError("pangenome_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def next_pow2(n):
+    n = max(2, int(n))
+    return 1 << (n - 1).bit_length()
+
+
+def to_device_bytes(data, device="cuda"):
+    """bytes / bytearray / numpy uint8 / torch uint8 -> 16-byte aligned uint8 CUDA tensor."""
+    _require_cuda()
+    if isinstance(data, torch.Tensor):
+        t = data if data.is_cuda else data.to(device, non_blocking=True)
+        return t.contiguous().view(torch.uint8)
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        arr = np.frombuffer(data, dtype=np.uint8)
+    else:
+        arr = np.ascontiguousarray(data, dtype=np.uint8)
+    if arr.size == 0:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.from_numpy(arr.copy() if not arr.flags.writeable else arr).to(device)
+
+
+class PackedSeqs:
+    """Result of K1 (pg_fasta_scan_pack): the 2-bit packed base stream plus the
+    record index.  Replaces what seqio_jit_ (kmer_numba.py:135-168) yields."""
+
+    def __init__(self, d_fasta, cap_records=1 << 12):
+        _require_cuda()
+        L = _lib.load()
+        self.d_fasta = d_fasta
+        nbytes = int(d_fasta.numel())
+        dev = d_fasta.device
+        self.nbytes = nbytes
+        words = int(L.pg_pack_words(nbytes))
+        self.pk2 = torch.empty(words, dtype=torch.int32, device=dev)
+        self.amb = torch.empty(words, dtype=torch.int32, device=dev)
+        ws_bytes = int(L.pg_fasta_workspace_bytes(nbytes))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self.d_counts = torch.zeros(4, dtype=torch.int64, device=dev)
+        while True:
+            self.d_hdr_off = torch.empty(cap_records + 1, dtype=torch.int64, device=dev)
+            self.d_seq_off = torch.empty(cap_records + 2, dtype=torch.int64, device=dev)
+            check(L.pg_fasta_scan_pack(_ptr(d_fasta) if nbytes else None, nbytes, _ptr(self.pk2), _ptr(self.amb),
+                                       nbytes, _ptr(self.d_hdr_off), _ptr(self.d_seq_off), cap_records,
+                                       _ptr(self.d_counts), _ptr(ws), ws_bytes, _stream()), "pg_fasta_scan_pack")
+            counts = self.d_counts.cpu().numpy()     # synchronises: the host needs the record index
+            self.n_rec = int(counts[0])
+            if self.n_rec <= cap_records:
+                break
+            cap_records = next_pow2(self.n_rec + 1)
+        self.n_bases = int(counts[1])
+        self.n_newlines = int(counts[2])
+        self.seq_off = self.d_seq_off[:self.n_rec + 1].cpu().numpy()
+        self.hdr_off = self.d_hdr_off[:self.n_rec].cpu().numpy()
+        self.launches = 3
+
+    @property
+    def seq_lengths(self):
+        return np.diff(self.seq_off)
+
+    def record_prefix(self, Ns, strands):
+        """How many records a stage processes under ``-n``: records are consumed
+        until the running base count exceeds Ns; the record that crosses is
+        still processed (kmer_numba.py:1227, 1820, 1847)."""
+        lens = self.seq_lengths.astype(np.int64) * strands
+        if lens.size == 0:
+            return 0
+        cum = np.cumsum(lens)
+        over = np.nonzero(cum > Ns)[0]
+        return int(over[0]) + 1 if over.size else int(lens.size)
+
+    def n_positions(self, k, n_rec=None):
+        lens = self.seq_lengths[:n_rec]
+        return int(np.maximum(lens - k + 1, 0).sum())
+
+    def n_insertions(self, k, n_rec=None, rc=True):
+        """The metric's unit: sum over record-strands of max(n-k+1, 1)."""
+        lens = self.seq_lengths[:n_rec]
+        return int(np.maximum(lens - k + 1, 1).sum()) * (2 if rc else 1)
+
+
+class DbgTable:
+    """Device hash table behind the C-ABI ``pg_table`` struct (replaces oakht,
+    kmer_numba.py:340-679).  ``mode``: 0 literal one strand, 1 literal both
+    strands, 2 canonical pairs."""
+
+    def __init__(self, capacity, k, mode, device="cuda"):
+        _require_cuda()
+        self.L = _lib.load()
+        self.capacity = next_pow2(capacity)
+        self.k = int(min(max(1, k), 27))
+        self.mode = int(mode)
+        self.slots = torch.empty(2 * self.capacity, dtype=torch.int64, device=device)
+        self.stats = torch.zeros(_lib.PG_STAT_WORDS, dtype=torch.int64, device=device)
+        self.c = PgTable(self.slots.data_ptr(), self.capacity, self.stats.data_ptr(), self.mode, self.k)
+        self.clear()
+
+    def clear(self):
+        check(self.L.pg_table_clear(ctypes.byref(self.c), _stream()), "pg_table_clear")
+
+    def insert(self, packed, n_rec=None, g_begin=None, g_end=None):
+        n_rec = packed.n_rec if n_rec is None else n_rec
+        if n_rec == 0:
+            return
+        g_begin = int(packed.seq_off[0]) if g_begin is None else g_begin
+        g_end = int(packed.seq_off[n_rec]) if g_end is None else g_end
+        check(self.L.pg_kmer_insert(ctypes.byref(self.c), _ptr(packed.pk2), _ptr(packed.amb), _ptr(packed.d_seq_off),
+                                    n_rec, g_begin, g_end, _stream()), "pg_kmer_insert")
+
+    def stats_host(self):
+        return self.stats.cpu().numpy()
+
+    def count(self):
+        check(self.L.pg_table_count(ctypes.byref(self.c), _stream()), "pg_table_count")
+        s = self.stats_host()
+        return int(s[_lib.PG_STAT_USED]), int(s[_lib.PG_STAT_ENTRIES])
+
+    def overflowed(self):
+        return bool(self.stats_host()[_lib.PG_STAT_OVERFLOW])
+
+    def checksum(self):
+        out = torch.zeros(3, dtype=torch.int64, device=self.slots.device)
+        check(self.L.pg_table_checksum(ctypes.byref(self.c), _ptr(out), _stream()), "pg_table_checksum")
+        v = out.cpu().numpy().view(np.uint64)
+        return int(v[0]), int(v[1]), int(v[2])
+
+    def export(self, sort=True):
+        """(keys u64, vals u16, cnts u8) in the reference's convention."""
+        _, n = self.count()
+        dev = self.slots.device
+        keys = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        vals = torch.empty(max(n, 1), dtype=torch.int16, device=dev)
+        cnts = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(self.L.pg_table_export(ctypes.byref(self.c), _ptr(keys), _ptr(vals), _ptr(cnts), n, _ptr(d_n), _stream()),
+              "pg_table_export")
+        got = int(d_n.item())
+        if got != n:
+            raise PgError("pg_table_export produced %d entries, pg_table_count said %d" % (got, n))
+        k = keys[:n].cpu().numpy().view(np.uint64)
+        v = vals[:n].cpu().numpy().view(np.uint16)
+        c = cnts[:n].cpu().numpy()
+        if sort:
+            o = np.argsort(k, kind="stable")
+            k, v, c = k[o], v[o], c[o]
+        return k, v, c
+
+    # ---- K4 ----
+    def rdbg_count(self):
+        out = torch.zeros(2, dtype=torch.int64, device=self.slots.device)
+        check(self.L.pg_rdbg_count(ctypes.byref(self.c), _ptr(out), _stream()), "pg_rdbg_count")
+        o = out.cpu().numpy()
+        return int(o[0]), int(o[1])
+
+    def select_rdbg(self):
+        n_slots, n_members = self.rdbg_count()
+        rd = DbgTable(max(1024, int(n_slots / _DEFAULT_LOAD) + 1), self.k, self.mode, device=self.slots.device)
+        check(self.L.pg_rdbg_select(ctypes.byref(self.c), ctypes.byref(rd.c), _stream()), "pg_rdbg_select")
+        rd.n_members = n_members
+        rd.n_slots_used = n_slots
+        if rd.overflowed():
+            raise PgError("rdBG table overflow")
+        return rd
+
+    def rdbg_export(self, n_members=None, sort=True):
+        """Members (keys u64, vals u16) of an rdBG table, reference convention."""
+        n = self.n_members if n_members is None else n_members
+        dev = self.slots.device
+        keys = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        vals = torch.empty(max(n, 1), dtype=torch.int16, device=dev)
+        d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(self.L.pg_rdbg_export(ctypes.byref(self.c), _ptr(keys), _ptr(vals), n, _ptr(d_n), _stream()), "pg_rdbg_export")
+        got = int(d_n.item())
+        if got != n:
+            raise PgError("pg_rdbg_export produced %d members, expected %d" % (got, n))
+        k = keys[:n].cpu().numpy().view(np.uint64)
+        v = vals[:n].cpu().numpy().view(np.uint16)
+        if sort:
+            o = np.argsort(k, kind="stable")
+            k, v = k[o], v[o]
+        return k, v
+
+
+def build_dbg(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=None, max_grow=6):
+    """K2+K3 over a PackedSeqs: returns (DbgTable, n_rec_used).  Table capacity
+    defaults to next_pow2(positions / 0.5); on overflow it is doubled and the
+    build repeated (the GPU table never rehashes in place)."""
+    k = int(min(max(1, k), 27))
+    if mode is None:
+        mode = _lib.PG_MODE_CANONICAL if rc else _lib.PG_MODE_LITERAL
+    if (mode == _lib.PG_MODE_LITERAL) == bool(rc):
+        raise PgError("mode %d does not match rc=%s" % (mode, rc))
+    n_rec = packed.record_prefix(Ns, 2 if rc else 1)
+    npos = packed.n_positions(k, n_rec)
+    keys_per_pos = 2 if mode == _lib.PG_MODE_LITERAL_RC else 1
+    cap = next_pow2(max(1024, capacity or int(npos * keys_per_pos / _DEFAULT_LOAD) + 1))
+    for _ in range(max_grow):
+        t = DbgTable(cap, k, mode, device=packed.pk2.device)
+        t.insert(packed, n_rec)
+        if not t.overflowed():
+            return t, n_rec
+        cap *= 2
+    raise PgError("dBG table kept overflowing up to capacity %d" % cap)

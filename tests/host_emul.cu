@@ -1,0 +1,139 @@
+// host_emul.cu - CPU emulation of the K1/K2/K4 kernels' per-thread logic, built from the SAME
+// host+device functions the kernels use (fasta_chunk.cuh, kmer_core.cuh).  Test infrastructure for
+// the `-m "not gpu"` suite: it lets the quirk-heavy integer logic be checked against the oracle in a
+// container without a GPU.  It does not emulate warps/CTAs/atomics - the `-m gpu` tests cover those.
+#include <unordered_map>
+#include <vector>
+#include <cstring>
+#include "../pangenome_b200/csrc/fasta_chunk.cuh"
+#include "../pangenome_b200/csrc/kmer_core.cuh"
+
+thread_local char pg_err_buf[512] = "";
+int pg_fail(int code, const char *, ...) { return code; }
+int pg_num_sms() { return 148; }
+
+static const int TILE = 16384;
+
+static ChunkCls load_cls(const uint8_t *f, int64_t n, int64_t off) {
+    uint32_t w[4] = {0, 0, 0, 0};
+    int64_t left = n - off;
+    for (int i = 0; i < 16 && i < left; i++) w[i >> 2] |= (uint32_t)f[off + i] << (8 * (i & 3));
+    int n_file = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+    return classify16(w, n_file, left <= 16);
+}
+
+// mirrors k1_tile_summaries + k1_tile_scan + k1_tile_pack
+extern "C" int64_t emul_pack(const uint8_t *fasta, int64_t nbytes, uint32_t *pk2, uint32_t *amb, int64_t n_words,
+                             int64_t *hdr_off, int64_t *seq_off, int64_t cap_rec, int64_t *counts) {
+    memset(pk2, 0, (size_t)n_words * 4); memset(amb, 0, (size_t)n_words * 4);
+    int64_t ntiles = (nbytes + TILE - 1) / TILE;
+    std::vector<Sum3> sums((size_t)ntiles);
+    uint64_t real_nl = 0;
+    for (int64_t t = 0; t < ntiles; t++) {
+        Sum3 carry = sum3_identity();
+        for (int c = 0; c < TILE / 16; c++) {
+            ChunkCls cls = load_cls(fasta, nbytes, t * TILE + c * 16);
+            real_nl += cls.real_nl;
+            carry = sum3_compose(carry, chunk_sum3(cls));
+        }
+        sums[(size_t)t] = carry;
+    }
+    bool dead = real_nl == 0;
+    uint64_t seq = 0, hdr = 0; uint32_t state = ST_LINE_START;
+    for (int64_t t = 0; t < ntiles && !dead; t++) {
+        uint64_t tseq = seq, thdr = hdr; uint32_t cstate = state, cseq = 0, chdr = 0;
+        Sum3 excl = sum3_identity();
+        for (int c = 0; c < TILE / 16; c++) {
+            int64_t off = t * TILE + c * 16;
+            ChunkCls cls = load_cls(fasta, nbytes, off);
+            uint32_t x = sum3_sel(excl, cstate);
+            ChunkRun r = chunk_run(cls, SV_STATE(x));
+            uint32_t rank = cseq + SV_SEQ(x), cnt = pg_popc(r.seqmask);
+            if (cnt) {
+                uint32_t d = pext16_2bit(cls.dig, r.seqmask), m = pext16_1bit(cls.amb, r.seqmask);
+                if (cnt < 16) d &= (1u << (2 * cnt)) - 1u;
+                uint64_t g = tseq + rank;
+                uint32_t sh = 2 * (g & 15);
+                pk2[g >> 4] |= d << sh;
+                if (sh && (d >> (32 - sh))) pk2[(g >> 4) + 1] |= d >> (32 - sh);
+                uint32_t sh1 = g & 31;
+                amb[g >> 5] |= m << sh1;
+                if (sh1 > 16 && (m >> (32 - sh1))) amb[(g >> 5) + 1] |= m >> (32 - sh1);
+            }
+            uint32_t hs = r.hs; uint64_t idx = thdr + chdr + SV_HDR(x);
+            while (hs) {
+                int j = pg_ctz(hs); hs &= hs - 1;
+                if ((int64_t)idx < cap_rec) { hdr_off[idx] = off + j; seq_off[idx] = (int64_t)(tseq + rank + pg_popc(r.seqmask & ((1u << j) - 1u))); }
+                idx++;
+            }
+            excl = sum3_compose(excl, chunk_sum3(cls));
+        }
+        uint32_t y = sum3_sel(sums[(size_t)t], state);
+        seq += SV_SEQ(y); hdr += SV_HDR(y); state = SV_STATE(y);
+        (void)cseq; (void)chdr;
+    }
+    counts[0] = dead ? 0 : (int64_t)hdr; counts[1] = dead ? 0 : (int64_t)seq; counts[2] = (int64_t)real_nl;
+    if (!dead && (int64_t)hdr <= cap_rec) seq_off[hdr] = (int64_t)seq;
+    if (dead) seq_off[0] = 0;
+    return counts[1];
+}
+
+struct Slot { uint32_t masks; uint64_t cnt; };
+
+// mirrors k2_kmer_insert (one "thread" per 32-base word) + pg_table_export / pg_rdbg_export
+extern "C" int64_t emul_dbg(const uint32_t *pk2_32, const uint32_t *amb, int64_t n_words32, const int64_t *seq_off, int64_t n_rec,
+                            int k, int mode, uint64_t *keys, uint16_t *vals, uint8_t *cnts, int64_t cap,
+                            uint64_t *rkeys, uint16_t *rvals, int64_t rcap, int64_t *n_rdbg) {
+    const uint64_t *pk2 = reinterpret_cast<const uint64_t *>(pk2_32);
+    int64_t n_words = n_words32 / 2;
+    std::unordered_map<uint64_t, Slot> tab;
+    auto upsert = [&](uint64_t key, uint32_t masks, uint32_t inc) { Slot &s = tab[key]; s.masks |= masks; s.cnt += inc; };
+    int64_t g_begin = 0, g_end = seq_off[n_rec];
+    int strands = mode == PG_MODE_LITERAL ? 1 : 2;
+    int64_t n_short = 0;
+    for (int64_t i = 0; i < n_rec; i++) if (seq_off[i + 1] - seq_off[i] < k) n_short += strands;
+    uint64_t p5 = pg_pow5(k - 1);
+    for (int64_t wi = 0; wi * 32 < g_end; wi++) {
+        PgWindow w;
+        auto W = [&](int64_t x) -> uint64_t { return (x >= 0 && x < n_words) ? pk2[x] : 0; };
+        auto A = [&](int64_t x) -> uint32_t { return (x >= 0 && x < n_words32) ? amb[x] : 0; };
+        w.prv = W(wi - 1); w.cur = W(wi); w.nxt = W(wi + 1);
+        w.aprv = A(wi - 1); w.acur = A(wi); w.anxt = A(wi + 1);
+        int64_t g0 = wi * 32;
+        int64_t lo = 0, hi = n_rec;
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= g0) lo = mid + 1; else hi = mid; }
+        int64_t r = lo - 1;
+        int64_t rs = r >= 0 ? seq_off[r] : 0, re = seq_off[r + 1];
+        uint64_t F, R;
+        pg_codes_init(w, 0, k, F, R);
+        for (int j = 0; j < 32; j++) {
+            int64_t g = g0 + j;
+            if (g >= g_end) break;
+            while (r + 1 < n_rec && g >= re) { r++; rs = re; re = seq_off[r + 1]; }
+            if (g >= g_begin && r >= 0 && g + k <= re) {
+                uint32_t vf, vr;
+                pg_occ_vals(w, j, g - rs, re - rs, k, vf, vr);
+                if (mode == PG_MODE_CANONICAL) { PgUpdate u = pg_canonical_update(F, R, vf, vr); upsert(u.key, u.masks, u.inc); }
+                else { upsert(F, vf, 1); if (mode == PG_MODE_LITERAL_RC) upsert(R, vr, 1); }
+            }
+            pg_codes_roll(w, j, k, p5, F, R);
+        }
+    }
+    int64_t n = 0, nr = 0;
+    for (auto &kv : tab) {
+        uint64_t c = kv.second.cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : kv.second.cnt;
+        uint64_t v = (uint64_t)kv.second.masks | (c << 32);
+        PgEntry e[2];
+        int m = pg_slot_entries(kv.first, v, mode, k, e);
+        for (int q = 0; q < m; q++) { if (n < cap) { keys[n] = e[q].key; vals[n] = (uint16_t)e[q].val; cnts[n] = (uint8_t)e[q].cnt; } n++; }
+        uint32_t f = pg_rdbg_flags(kv.first, v, mode, k);
+        if (f & 1u) { if (nr < rcap) { rkeys[nr] = e[0].key; rvals[nr] = (uint16_t)e[0].val; } nr++; }
+        if (f & 2u) { if (nr < rcap) { rkeys[nr] = e[1].key; rvals[nr] = (uint16_t)e[1].val; } nr++; }
+    }
+    if (n_short > 0) {
+        if (n < cap) { keys[n] = PG_EMPTY; vals[n] = 32; cnts[n] = (uint8_t)(n_short < 255 ? n_short : 255); } n++;
+        if (nr < rcap) { rkeys[nr] = PG_EMPTY; rvals[nr] = 32; } nr++;
+    }
+    *n_rdbg = nr;
+    return n;
+}

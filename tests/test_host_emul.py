@@ -1,0 +1,126 @@
+"""CPU check of the kernels' per-thread integer logic (tests/host_emul.cu runs the
+same host+device functions the CUDA kernels call) against the oracle and the
+reference's golden vectors.  No GPU needed."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT, load_small_cases
+from pangenome_b200.synth import survey_4x1m
+
+CASES = load_small_cases()
+_SO = os.path.join(ROOT, "tests", "_host_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(ROOT, "tests", "host_emul.cu")
+    deps = [src] + [os.path.join(ROOT, "pangenome_b200", "csrc", f) for f in
+                    ("fasta_chunk.cuh", "kmer_core.cuh", "common.cuh")]
+    if not os.path.isfile(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-o", _SO, src])
+    L = ctypes.CDLL(_SO)
+    L.emul_pack.restype = ctypes.c_int64
+    L.emul_dbg.restype = ctypes.c_int64
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def run_pack(L, data):
+    n = len(data)
+    buf = np.frombuffer(data, dtype=np.uint8) if n else np.zeros(1, np.uint8)
+    nw = n // 16 + 64
+    pk2 = np.zeros(nw, np.uint32)
+    amb = np.zeros(nw, np.uint32)
+    cap = max(16, data.count(b">") + 1)
+    hdr = np.zeros(cap + 1, np.int64)
+    so = np.zeros(cap + 2, np.int64)
+    counts = np.zeros(4, np.int64)
+    L.emul_pack(_p(buf), ctypes.c_int64(n), _p(pk2), _p(amb), ctypes.c_int64(nw), _p(hdr), _p(so),
+                ctypes.c_int64(cap), _p(counts))
+    nrec = int(counts[0])
+    return pk2, amb, hdr[:nrec], so[:nrec + 1], counts
+
+
+def unpack_syms(pk2, amb, n):
+    i = np.arange(n)
+    d = (pk2[i >> 4] >> (2 * (i & 15)).astype(np.uint32)) & 3
+    a = (amb[i >> 5] >> (i & 31).astype(np.uint32)) & 1
+    return np.where(a == 1, 4 + d, d).astype(np.uint8)
+
+
+def syms_of_bytes(seq):
+    lut = np.full(256, 5, np.uint8)
+    for ch, v in ((b"Aa", 0), (b"Gg", 1), (b"Cc", 2), (b"Tt", 3), (b"Nn", 4)):
+        for c in ch:
+            lut[c] = v
+    return lut[seq]
+
+
+def run_dbg(L, pk2, amb, so, k, mode):
+    nrec = so.size - 1
+    cap = int(2 * max(1, so[-1]) + 8)
+    keys = np.zeros(cap, np.uint64)
+    vals = np.zeros(cap, np.uint16)
+    cnts = np.zeros(cap, np.uint8)
+    rkeys = np.zeros(cap, np.uint64)
+    rvals = np.zeros(cap, np.uint16)
+    nr = np.zeros(1, np.int64)
+    n = L.emul_dbg(_p(pk2), _p(amb), ctypes.c_int64(pk2.size), _p(so), ctypes.c_int64(nrec), ctypes.c_int(k),
+                   ctypes.c_int(mode), _p(keys), _p(vals), _p(cnts), ctypes.c_int64(cap), _p(rkeys), _p(rvals),
+                   ctypes.c_int64(cap), _p(nr))
+    o = np.argsort(keys[:n], kind="stable")
+    ro = np.argsort(rkeys[:int(nr[0])], kind="stable")
+    return (keys[:n][o], vals[:n][o], cnts[:n][o]), rkeys[:int(nr[0])][ro]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_emul_matches_golden(emul, case):
+    if "Ns" in case:
+        pytest.skip("-n prefix selection is host logic, tested with the host module")
+    data = case["input_latin1"].encode("latin-1")
+    ref = oracle.run(data, case["k"], c=case["c"], stages=2)
+    pk2, amb, hdr, so, counts = run_pack(emul, data)
+    assert so.tolist() == ref["seq_off"].tolist()
+    assert hdr.tolist() == ref["hdr_off"].tolist()
+    junk = int(so[0]) if so.size else 0
+    got = unpack_syms(pk2, amb, int(counts[1]))[junk:]
+    assert got.tolist() == syms_of_bytes(ref["seq"]).tolist()
+    rc0 = (case["c"] >> 1) & 1
+    modes = (1, 2) if rc0 else (0,)
+    for mode in modes:
+        (ks, vs, cs), rk = run_dbg(emul, pk2, amb, so, case["k"], mode)
+        got = [[int(a), int(b), int(c)] for a, b, c in zip(ks, vs, cs)]
+        assert got == case["dbg"], "mode %d" % mode
+        assert rk.tolist() == case["rdbg"], "mode %d" % mode
+
+
+def test_emul_header_offsets(emul):
+    data = b"junk\n>s1 desc\nACGT\nAC\n>s2\n\n>s3\nGGGTT"
+    pk2, amb, hdr, so, counts = run_pack(emul, data)
+    assert hdr.tolist() == [5, 22, 27]
+    assert so.tolist() == [4, 10, 10, 14]          # 'junk' occupies [0,4) and belongs to no record
+    assert counts[0] == 3 and counts[1] == 14
+    # a file without any newline yields no line at all
+    pk2, amb, hdr, so, counts = run_pack(emul, b">x ACGT")
+    assert counts[0] == 0 and counts[1] == 0
+
+
+def test_emul_big(emul, big_facts):
+    data = survey_4x1m()
+    pk2, amb, hdr, so, counts = run_pack(emul, data)
+    assert counts[0] == 4 and int(so[-1]) == 4_000_000
+    (ks, vs, cs), rk = run_dbg(emul, pk2, amb, so, 27, 2)
+    assert ks.size == big_facts["dbg_entries"]
+    assert int(cs.astype(np.int64).sum()) == big_facts["dbg_count_sum"]
+    ref = oracle.run(data, 27, stages=2)
+    assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
+    assert np.array_equal(rk, ref["rdbg"])
+    assert oracle.table_checksum(ks, vs, cs) == oracle.table_checksum(*ref["dbg"])
