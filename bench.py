@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py - dBG build throughput (G k-mers/s) of the B200 path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg2|cfg3|small] [--k 27]
+
+One JSON line on stdout (rank 0).  A *step* is one full dBG build of the
+workload: table clear + FASTA scan/pack (K1) + fused k-mer extraction and
+hash-table insertion (K2/K3).  Metric = k-mer insertions / s, an insertion being
+one k-mer occurrence on one strand: 2 * sum max(n_r - k + 1, 1) over records
+(BASELINE.md section 3).
+
+ value   : device-resident input (the FASTA bytes already in HBM), CUDA events
+           around exactly K steps, max over ranks.
+ e2e     : the same build through the public host API with HOST buffers: pinned
+           FASTA bytes -> H2D, build, D2H of the table statistics + checksum.
+ roofline: the dominant kernel (k2_kmer_insert), timed live with CUDA events on
+           the launching stream; algorithmic bytes = 16 B per insertion
+            + 0.25 B per base read.
+ cpu_baseline: the reference's numba code (oracle/_ref, kind "reference") or,
+           if that is unavailable, the C port (oracle/, kind "port"), one core,
+           on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "dbg_build_kmers_per_s"
+UNIT = "G k-mers/s"
+
+
+def workload(name, rank=0):
+    from pangenome_b200 import synth
+    if name == "cfg2":
+        return synth.pangenome(10, 5_000_000), "synthetic 10 x 5 Mbp genomes, 1% SNP (BASELINE configs[1])"
+    if name == "cfg3":
+        return synth.pangenome(200, 5_000_000), "synthetic 200 x 5 Mbp pangenome (BASELINE configs[2])"
+    if name == "small":
+        return synth.pangenome(4, 1_000_000), "synthetic 4 x 1 Mbp genomes, 1% SNP"
+    raise SystemExit("unknown workload %r" % name)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_rate(data, k, sample_bases, prefer="reference"):
+    """Time the CPU dBG stage on the first records of `data` totalling about
+    `sample_bases` bases.  Returns (M inserts/s, kind, cores, sample text)."""
+    import numpy as np
+    # cut the sample at a record boundary
+    pos, acc, cut = 0, 0, len(data)
+    while True:
+        nxt = data.find(b"\n>", pos + 1)
+        if nxt < 0:
+            break
+        acc = nxt
+        pos = nxt
+        if acc >= sample_bases:
+            cut = nxt + 1
+            break
+    sample = data[:cut]
+    if len(sample) > sample_bases * 1.3:      # a single huge record: truncate its body instead
+        sample = data[:int(sample_bases)]
+        sample = sample[:sample.rfind(b"\n") + 1]
+    kind = "port"
+    if prefer == "reference":
+        try:
+            from oracle import refrun
+            if refrun.available():
+                refrun.run(b">w\n" + b"ACGTTGCATG" * 20 + b"\n", k, stages="dbg")      # JIT warm-up, untimed
+                tm = {}
+                res = refrun.run(sample, k, stages="dbg", timings=tm)
+                import oracle
+                n_ins = oracle.run(sample, k, stages=1)["n_inserts"]
+                return n_ins / tm["dbg"] / 1e9, "reference", 1, "%d bytes / %d insertions of the workload, numba steady state (JIT excluded)" % (len(sample), n_ins)
+        except Exception as e:  # numba missing on the box, etc.
+            sys.stderr.write("bench: reference unavailable (%s), using the C port\n" % e)
+    import oracle
+    res = oracle.run(sample, k, stages=1)
+    return res["n_inserts"] / res["times"]["dbg"] / 1e9, kind, 1, "%d bytes / %d insertions of the workload, C port of the reference" % (len(sample), res["n_inserts"])
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    data, wl = workload(args.workload)
+    # bounded sample: every step rebuilds the dBG of the first ~1 Mbp (2 M insertions)
+    sample_bases = 1_000_000
+    rates = []
+    t0 = time.time()
+    kind = cores = text = None
+    for i in range(args.warmup + args.steps):
+        r, kind, cores, text = cpu_reference_rate(data, args.k, sample_bases)
+        if i >= args.warmup:
+            rates.append(r)
+    val = sum(rates) / len(rates)
+    ms = 1e3 * (time.time() - t0) / max(1, args.warmup + args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic", "config": {"workload": wl, "k": args.k, "rc": True},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": text},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--k", type=int, default=27)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pangenome_b200 import engine, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        from pangenome_b200 import multigpu
+        return multigpu.bench(args, world, rank, local)
+
+    data, wl = workload(args.workload)
+    k = args.k
+    host = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+    d_fasta = host.to("cuda", non_blocking=True)
+    torch.cuda.synchronize()
+
+    # one untimed build to size the table and know the unit count
+    packed = engine.PackedSeqs(d_fasta)
+    n_ins = packed.n_insertions(k)
+    table, n_rec = engine.build_dbg(packed, k)
+    cap = table.capacity
+    used, entries = table.count()
+    del table
+    stream = torch.cuda.current_stream()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    ins_events = []
+
+    def step_device(record=False):
+        p = engine.PackedSeqs(d_fasta)                      # K1 (3 launches) + small D2H of the record index
+        t = engine.DbgTable(cap, k, _lib.PG_MODE_CANONICAL)  # clear (1 launch)
+        if record:
+            a, b = ev(), ev()
+            a.record(stream)
+            t.insert(p, n_rec)                              # count_short + k2_kmer_insert
+            b.record(stream)
+            ins_events.append((a, b))
+        else:
+            t.insert(p, n_rec)
+        return t
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    t = None
+    for _ in range(args.steps):
+        t = step_device(record=True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    ms_step = ms_total / args.steps
+    if t.overflowed():
+        raise SystemExit("bench: table overflow inside the timed region")
+    value = n_ins / (ms_step * 1e-3) / 1e9
+    ins_ms = sum(a.elapsed_time(b) for a, b in ins_events) / len(ins_events)
+
+    # end to end through the public API, host buffers
+    def step_e2e():
+        d = host.to("cuda", non_blocking=True)
+        p = engine.PackedSeqs(d)
+        tt = engine.DbgTable(cap, k, _lib.PG_MODE_CANONICAL)
+        tt.insert(p, n_rec)
+        st = tt.stats_host()
+        cs = tt.checksum()
+        return st, cs
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    g0, g1 = ev(), ev()
+    g0.record(stream)
+    for _ in range(args.steps):
+        st, cs = step_e2e()
+    g1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = g0.elapsed_time(g1) / args.steps
+    e2e_val = n_ins / (e2e_ms * 1e-3) / 1e9
+
+    peak, peak_src = peaks()
+    alg_bytes = 16.0 * n_ins + 0.25 * packed.n_bases
+    achieved = alg_bytes / (ins_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "insert_traffic.json")
+    if os.path.isfile(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic",
+        "config": {"workload": wl, "k": k, "rc": True, "insertions_per_step": n_ins, "bases": packed.n_bases,
+                   "table_slots": cap, "table_bytes": cap * 16, "distinct_canonical_keys": used,
+                   "l2": "every step clears and randomly updates the %.1f GB table (> 126 MB L2), which evicts the input" % (cap * 16 / 1e9)},
+        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host.numel()),
+                "d2h_bytes_per_step": int(8 * 8 + 3 * 8 + 4 * 8 + 16 * (packed.n_rec + 1))},
+        "gpu_launches": 6 * args.steps,
+        "clocks": clk,
+        "roofline": {"kernel": "k2_kmer_insert<canonical>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "ms_per_launch": ins_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "convention": "16 B per insertion + 0.25 B per base (SURVEY 8d)",
+                     "frac_64B_sector_convention": (64.0 * n_ins / 2 / (ins_ms * 1e-3) / 1e9) / peak},
+        "checksum": list(cs),
+    }
+    if not args.no_cpu_baseline:
+        r, kind, cores, text = cpu_reference_rate(data, k, 5_000_000)
+        line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": text,
+                                "host_cpus": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
