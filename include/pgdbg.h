@@ -145,6 +145,69 @@ int pg_rdbg_select(const pg_table *dbg, const pg_table *rdbg, pg_stream_t stream
 int pg_rdbg_export(const pg_table *rdbg, uint64_t *d_keys, uint16_t *d_vals,
                    int64_t cap, int64_t *d_n, pg_stream_t stream);
 
+/* ---- K5: compressed-path hits ---------------------------------------------------
+ * Replaces the first half of rdbg_edge_weight (kmer_numba.py:1446-1468) and of
+ * seq2path_jit_ (:1523-1549): walk one strand of records [0, n_rec) and keep the
+ * occurrences whose k-mer is an rdBG member (`has_key`, including the phantom
+ * key 0, Q6).  strand 0 = forward, 1 = reverse complement (hits are still
+ * emitted in ascending forward position).  Outputs, ordered by position:
+ *   d_hit_g    stream offset of the k-mer's first base
+ *   d_hit_node node key = ((rdBG slot << 1 | orientation) << 11) | v5 with
+ *              v5 = (lastc[prev] << 5) | lastc[next]   (offbit 5, F7)
+ *   d_hit_rec  record index,  d_hit_v6 = (lastc[prev] << 6) | lastc[next]
+ * *d_n_hits = hits found; hits beyond cap_hits are dropped (grow and repeat).
+ */
+int64_t pg_path_workspace_bytes(int64_t n_bases);
+int pg_path_hits(const pg_table *rdbg, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                 int64_t n_rec, int64_t g_begin, int64_t g_end, int strand,
+                 int64_t *d_hit_g, uint64_t *d_hit_node, int32_t *d_hit_rec, uint16_t *d_hit_v6, int64_t cap_hits,
+                 int64_t *d_n_hits, void *d_ws, int64_t ws_bytes, pg_stream_t stream);
+
+/* ---- K6/K7: rdBG edge weights and connected components ----------------------------
+ * pg_graph: three single-word open-addressing tables in caller-owned buffers
+ * (capacities: powers of two <= 2^32; size each >= 2x the number of hits).
+ * Replaces the typed-Dict edge map + `visit` dict (:1446-1518) and the label
+ * dict built from the external `mcl` output (:1907-1944).  The reference's
+ * clustering itself is third-party MCL; here components are the connected
+ * components of the edge list restricted to weight >= min_weight (min_weight 1 =
+ * the definition of the reference's other/test_net.py).
+ * d_stats: [0] overflow flag, [1] nodes, [2] edges.
+ */
+typedef struct pg_graph {
+    uint64_t *d_node_keys;    /* node_cap                                  */
+    uint32_t *d_node_parent;  /* node_cap: union-find parent / root         */
+    int32_t *d_node_label;    /* node_cap: region label of the node's component (written by the host) */
+    uint64_t *d_edge_keys;    /* edge_cap: (node slot a << 32) | node slot b */
+    uint32_t *d_edge_w;       /* edge_cap: weight = record-strands containing the edge */
+    uint64_t *d_edge_first;   /* edge_cap: smallest walk ordinal (= .xyz file order)    */
+    uint64_t *d_visit_keys;   /* visit_cap: (edge slot << 32) | record-strand id        */
+    int64_t *d_stats;         /* 8 int64 */
+    int64_t node_cap, edge_cap, visit_cap;
+} pg_graph;
+int pg_graph_clear(const pg_graph *g, pg_stream_t stream);
+int pg_graph_add_hits(const pg_graph *g, const uint64_t *d_hit_node, const int32_t *d_hit_rec, int64_t n_hits,
+                      uint32_t *d_hit_nslot, int strand, int n_strands, pg_stream_t stream);
+int pg_graph_components(const pg_graph *g, uint32_t min_weight, pg_stream_t stream);
+int pg_graph_export_edges(const pg_graph *g, const pg_table *rdbg, uint64_t *d_c0, uint32_t *d_v0, uint64_t *d_c1,
+                          uint32_t *d_v1, uint32_t *d_w, uint64_t *d_first, int64_t cap, int64_t *d_n, pg_stream_t stream);
+int pg_graph_export_nodes(const pg_graph *g, const pg_table *rdbg, uint32_t *d_nslot, uint64_t *d_code, uint32_t *d_v5,
+                          uint32_t *d_root, int64_t cap, int64_t *d_n, pg_stream_t stream);
+
+/* ---- K8: per-record breakpoint labelling -------------------------------------------
+ * Replaces seq2path_jit_ (:1523-1573): a hit matches when (code, v6) equals some
+ * node's (code, v5) (Q7); matched hits are chained greedily ("starts[-1] < idx":
+ * accept iff position > last accepted position + k, first iff position > 0), runs
+ * of equal labels merge, every run yields the row (prev_end, last_pos + k, label).
+ * Outputs one (record, end, label) per row in record/position order; the row's
+ * start is the previous row's end within the record, else 0.  d_n_rows[0] = rows,
+ * d_n_rows[1] = matched hits.  Synchronises the stream once.
+ */
+int64_t pg_label_workspace_bytes(int64_t n_hits);
+int pg_label_regions(const pg_graph *g, const int64_t *d_hit_g, const uint64_t *d_hit_node, const int32_t *d_hit_rec,
+                     const uint16_t *d_hit_v6, int64_t n_hits, const int64_t *d_seq_off, int k, int strand,
+                     int32_t *d_row_rec, int64_t *d_row_end, int32_t *d_row_label, int64_t cap_rows, int64_t *d_n_rows,
+                     void *d_ws, int64_t ws_bytes, pg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,15 @@ class PgTable(ctypes.Structure):
 
 PT = ctypes.POINTER(PgTable)
 
+
+class PgGraph(ctypes.Structure):
+    _fields_ = [("d_node_keys", c_vp), ("d_node_parent", c_vp), ("d_node_label", c_vp), ("d_edge_keys", c_vp),
+                ("d_edge_w", c_vp), ("d_edge_first", c_vp), ("d_visit_keys", c_vp), ("d_stats", c_vp),
+                ("node_cap", c_i64), ("edge_cap", c_i64), ("visit_cap", c_i64)]
+
+
+GT = ctypes.POINTER(PgGraph)
+
 # name -> (restype, argtypes); every symbol include/pgdbg.h declares
 SIGNATURES = {
     "pg_last_error": (ctypes.c_char_p, []),
@@ -36,6 +45,17 @@ SIGNATURES = {
     "pg_rdbg_count": (c_int, [PT, c_vp, c_vp]),
     "pg_rdbg_select": (c_int, [PT, PT, c_vp]),
     "pg_rdbg_export": (c_int, [PT, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "pg_path_workspace_bytes": (c_i64, [c_i64]),
+    "pg_path_hits": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp,
+                             c_i64, c_vp]),
+    "pg_graph_clear": (c_int, [GT, c_vp]),
+    "pg_graph_add_hits": (c_int, [GT, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp]),
+    "pg_graph_components": (c_int, [GT, ctypes.c_uint32, c_vp]),
+    "pg_graph_export_edges": (c_int, [GT, PT, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "pg_graph_export_nodes": (c_int, [GT, PT, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "pg_label_workspace_bytes": (c_i64, [c_i64]),
+    "pg_label_regions": (c_int, [GT, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp,
+                                 c_i64, c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,98 @@
+"""Drop-in command line of kmer_numba.py (entry_point, kmer_numba.py:1971-2144).
+
+    python kmer_b200.py -m -i input.fasta -k 27 > result.tab
+
+Same flags (``-i -k -n -c -r -d -R -D``; ``-k27`` and ``-k 27`` forms; unknown
+flags such as ``-m`` are skipped exactly like upstream, F1), same ``# `` banner
+lines, same table rows, same side-file names.  Extra long options (ignored by
+the reference's parser, so scripts stay portable): ``--min-edge-weight W``,
+``--no-mcl-file``.
+"""
+import sys
+from time import time
+
+
+def manual_print(out=sys.stdout):
+    w = lambda s: print(s, file=out)
+    w('Usage:')
+    w('  pyhton this.py -i qry.fsa -k 10 -n 1000000')
+    w('Parameters:')
+    w('  -i: query sequences in fasta format')
+    w('  -k: kmer length')
+    w('  -d: the de bruijn graph')
+    w('  -r: break point of de bruijn graph')
+    w('  -D: the reduced de bruijn graph')
+    w('  -R: break point of reduced de bruijn graph')
+    w('  -n: length of query sequences for pan-genomic analysis')
+    w('  -c: complementary reverse sequence. 00,01,10,11')
+
+
+def parse_args(argv):
+    args = {'-i': '', '-k': '50', '-n': '2**63', '-r': '', '-d': '', '-R': '', '-D': '', '-c': '2'}
+    extra = {'--min-edge-weight': '1'}
+    flags = set()
+    N = len(argv)
+    for i in range(1, N):
+        k = argv[i]
+        if k in args:
+            args[k] = argv[i + 1] if i + 1 < N else ''
+        elif k in extra:
+            extra[k] = argv[i + 1] if i + 1 < N else extra[k]
+        elif k[:2] in args and len(k) > 2 and not k.startswith('--'):
+            args[k[:2]] = k[2:]
+        elif k.startswith('--'):
+            flags.add(k)
+    return args, extra, flags
+
+
+def _eval_n(text):
+    # the reference eval()s -n ('2**63', '5e8'); accept the same arithmetic without eval
+    import ast
+    import operator as op
+    ops = {ast.Add: op.add, ast.Sub: op.sub, ast.Mult: op.mul, ast.Pow: op.pow, ast.Div: op.truediv, ast.FloorDiv: op.floordiv}
+
+    def ev(n):
+        if isinstance(n, ast.Constant) and isinstance(n.value, (int, float)):
+            return n.value
+        if isinstance(n, ast.BinOp) and type(n.op) in ops:
+            return ops[type(n.op)](ev(n.left), ev(n.right))
+        if isinstance(n, ast.UnaryOp) and isinstance(n.op, ast.USub):
+            return -ev(n.operand)
+        raise ValueError("unsupported -n expression: %r" % text)
+    return int(ev(ast.parse(text, mode="eval").body))
+
+
+def entry_point(argv, out=sys.stdout):
+    args, extra, flags = parse_args(argv)
+    qry, kmer, Ns, rc = args['-i'], int(args['-k']), _eval_n(args['-n']), int(args['-c'])
+    if not qry:
+        manual_print(out)
+        raise SystemExit()
+    if args['-d'] or args['-D'] or args['-r'] or args['-R']:
+        raise SystemExit("pangenome_b200: -d/-D/-r/-R (.npz tables and breakpoints of the CPU reference) are not "
+                         "supported by the GPU path; run without them")
+    from . import stages
+    p = lambda *a: print(*a, file=out)
+    p('# build the dBG')
+    st = time()
+    rc0 = ((rc >> 1) == 1)
+    kmer_dict = stages.seq2rdbg(qry, kmer, 5, Ns, rc=rc0)
+    p('# finished in', time() - st, 'seconds')
+    # the reference dumps the table to <qry>_db.npz and reloads it here (:2116-2126); the result does
+    # not depend on it and the GPU table stays resident instead
+    p('# build the reduced dBG')
+    st = time()
+    rdbg_dict = stages.dbg2rdbg(kmer_dict)
+    del kmer_dict
+    p('# finished in', time() - st, 'seconds')
+    p('# find fr')
+    st = time()
+    rc1 = ((rc & 1) == 1)
+    stages.seq2graph(qry, kmer=kmer, bits=5, Ns=Ns, rdbg_dict=rdbg_dict, rc=rc1, out=out,
+                     min_weight=int(extra['--min-edge-weight']), write_mcl='--no-mcl-file' not in flags)
+    p('# finished in', time() - st, 'seconds')
+    return 0
+
+
+def main():
+    entry_point(sys.argv)

@@ -20,6 +20,7 @@ int pg_fail(int code, const char *fmt, ...);
     } while (0)
 
 int pg_num_sms();
+void pg_tune_once();
 
 // ---- hashing ---------------------------------------------------------------
 PG_HD uint64_t pg_mix64(uint64_t x) {   // murmur3 fmix64: a bijection on u64

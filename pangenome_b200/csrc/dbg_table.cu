@@ -11,69 +11,9 @@
 // Replaces oakht.push/has_key/get (:521-603), add_kmer (:1036-1047), build_dbg (:1052-1093),
 // seq2dbg_jit_ (:1202-1230), build_rdbg_jit_ (:1292-1309).
 #include "kmer_core.cuh"
+#include "table_dev.cuh"
 
 namespace {
-
-constexpr int K2_THREADS = 256;                 // one 32-base word per thread
-constexpr int K2_TILE_WORDS = K2_THREADS;       // 8192 bases per CTA tile
-constexpr uint32_t PG_MAX_PROBE = 1u << 16;
-
-struct TableView { uint64_t *slots; uint64_t capmask; int64_t *stats; };
-
-// returns the slot index the key lives in (claimed if absent), or -1 when probing gives up
-__device__ __forceinline__ int64_t table_upsert(const TableView &t, uint64_t key, uint32_t masks, uint32_t inc) {
-    uint64_t s = pg_mix64(key) & t.capmask;
-    for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
-        uint64_t *p = t.slots + 2 * s;
-        uint64_t ck, cv;
-        pg_ld_slot(p, ck, cv);
-        if (ck == PG_EMPTY) {
-            uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)PG_EMPTY,
-                                     (unsigned long long)key);
-            ck = (old == PG_EMPTY) ? key : old;
-            cv = 0;
-        }
-        if (ck == key) {
-            uint32_t *v = reinterpret_cast<uint32_t *>(p + 1);
-            if (((uint32_t)cv & masks) != masks) pg_red_or32(v, masks);
-            if ((uint32_t)(cv >> 32) < 255u) pg_red_add32(v + 1, inc);
-            return (int64_t)s;
-        }
-        s = (s + 1) & t.capmask;
-    }
-    atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
-    return -1;
-}
-
-// largest r in [-1, n_rec) with seq_off[r] <= g   (r = -1: g precedes the first record)
-__device__ __forceinline__ int64_t find_record(const int64_t *__restrict__ seq_off, int64_t n_rec, int64_t g) {
-    int64_t lo = 0, hi = n_rec;   // first index with seq_off[idx] > g
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (__ldg(seq_off + mid) <= g) lo = mid + 1; else hi = mid;
-    }
-    return lo - 1;
-}
-
-// Stage the packed words [w0-2, w0+K2_TILE_WORDS+2) of a tile in shared memory with 128-bit loads.
-__device__ __forceinline__ void stage_tile(const uint64_t *__restrict__ pk2, const uint32_t *__restrict__ amb,
-                                           int64_t w0, int64_t n_words, uint64_t *s_pk, uint32_t *s_am) {
-    // pk2: (K2_TILE_WORDS + 4) u64 = 130 uint4 ; amb: (K2_TILE_WORDS + 4) u32 = 65 uint4 ; w0 is even -> 16-B aligned
-    const uint4 *gp = reinterpret_cast<const uint4 *>(pk2 + (w0 - 2));
-    const uint4 *ga = reinterpret_cast<const uint4 *>(amb + (w0 - 4));
-    for (int i = threadIdx.x; i < (K2_TILE_WORDS + 4) / 2; i += K2_THREADS) {
-        int64_t w = w0 - 2 + 2 * i;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (w >= 0 && w + 1 < n_words) v = __ldg(gp + i);
-        reinterpret_cast<uint4 *>(s_pk)[i] = v;
-    }
-    for (int i = threadIdx.x; i < (K2_TILE_WORDS + 8) / 4; i += K2_THREADS) {
-        int64_t w = w0 - 4 + 4 * i;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (w >= 0 && w + 3 < n_words) v = __ldg(ga + i);
-        reinterpret_cast<uint4 *>(s_am)[i] = v;
-    }
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(K2_THREADS)
@@ -286,6 +226,7 @@ extern "C" int64_t pg_table_bytes(int64_t capacity) { return capacity * 16; }
 
 extern "C" int pg_table_clear(const pg_table *t, pg_stream_t stream_) {
     int rc = check_table(t, "pg_table_clear"); if (rc) return rc;
+    pg_tune_once();
     cudaStream_t stream = (cudaStream_t)stream_;
     k_table_clear<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(reinterpret_cast<uint4 *>(t->d_slots), t->capacity, t->d_stats);
     PG_CUDA(cudaGetLastError());

@@ -1,0 +1,269 @@
+"""Host side of K5-K8: path hits, rdBG edges/weights, components, region rows.
+
+Mirrors what the reference's ``seq2graph`` (kmer_numba.py:1853-1951) does after
+the rdBG exists, with the external ``mcl`` process replaced by an on-GPU
+union-find (connected components of the edge list, optionally restricted to
+edges of weight >= ``min_weight``).  The host only sizes buffers, orders the
+(small) component list and formats text.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PgError, PgGraph, check
+from .engine import _ptr, _stream, next_pow2
+
+
+class Hits:
+    def __init__(self, g, node, rec, v6, n, strand):
+        self.g, self.node, self.rec, self.v6, self.n, self.strand = g, node, rec, v6, n, strand
+        self.nslot = torch.empty(max(n, 1), dtype=torch.int32, device=g.device)
+
+
+def path_hits(packed, rd, n_rec, strand=0, cap=None):
+    """K5 over records [0, n_rec) of ``packed`` against the rdBG table ``rd``."""
+    L = _lib.load()
+    dev = packed.pk2.device
+    if n_rec == 0:
+        z = torch.empty(1, dtype=torch.int64, device=dev)
+        return Hits(z, z, torch.empty(1, dtype=torch.int32, device=dev), torch.empty(1, dtype=torch.int16, device=dev), 0, strand)
+    g_begin, g_end = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
+    ws_bytes = int(L.pg_path_workspace_bytes(g_end))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cap = cap or max(1024, (g_end - g_begin) // 8)
+    d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+    while True:
+        hg = torch.empty(cap, dtype=torch.int64, device=dev)
+        hn = torch.empty(cap, dtype=torch.int64, device=dev)
+        hr = torch.empty(cap, dtype=torch.int32, device=dev)
+        hv = torch.empty(cap, dtype=torch.int16, device=dev)
+        check(L.pg_path_hits(ctypes.byref(rd.c), _ptr(packed.pk2), _ptr(packed.amb), _ptr(packed.d_seq_off), n_rec,
+                             g_begin, g_end, strand, _ptr(hg), _ptr(hn), _ptr(hr), _ptr(hv), cap, _ptr(d_n), _ptr(ws),
+                             ws_bytes, _stream()), "pg_path_hits")
+        n = int(d_n.item())
+        if n <= cap:
+            return Hits(hg, hn, hr, hv, n, strand)
+        cap = n + 1024
+
+
+class RdbgGraph:
+    """Device node/edge/visit tables (pg_graph) + the host read-outs."""
+
+    def __init__(self, n_hits_total, device):
+        self.L = _lib.load()
+        cap = next_pow2(max(1024, 2 * n_hits_total + 2))
+        if cap > 1 << 32:
+            raise PgError("more than 2^31 hits: shard the input across GPUs")
+        self.cap = cap
+        i64, i32 = torch.int64, torch.int32
+        self.node_keys = torch.empty(cap, dtype=i64, device=device)
+        self.node_parent = torch.empty(cap, dtype=i32, device=device)
+        self.node_label = torch.empty(cap, dtype=i32, device=device)
+        self.edge_keys = torch.empty(cap, dtype=i64, device=device)
+        self.edge_w = torch.empty(cap, dtype=i32, device=device)
+        self.edge_first = torch.empty(cap, dtype=i64, device=device)
+        self.visit_keys = torch.empty(cap, dtype=i64, device=device)
+        self.stats = torch.zeros(8, dtype=i64, device=device)
+        self.c = PgGraph(self.node_keys.data_ptr(), self.node_parent.data_ptr(), self.node_label.data_ptr(),
+                         self.edge_keys.data_ptr(), self.edge_w.data_ptr(), self.edge_first.data_ptr(),
+                         self.visit_keys.data_ptr(), self.stats.data_ptr(), cap, cap, cap)
+        check(self.L.pg_graph_clear(ctypes.byref(self.c), _stream()), "pg_graph_clear")
+
+    def add_hits(self, hits, n_strands):
+        check(self.L.pg_graph_add_hits(ctypes.byref(self.c), _ptr(hits.node), _ptr(hits.rec), hits.n, _ptr(hits.nslot),
+                                       hits.strand, n_strands, _stream()), "pg_graph_add_hits")
+
+    def counts(self):
+        s = self.stats.cpu().numpy()
+        if s[0]:
+            raise PgError("graph table overflow")
+        return int(s[1]), int(s[2])
+
+    def edges(self, rd):
+        """(c0, v0, c1, v1, w) sorted into the reference's .xyz file order
+        (first-insertion order of the edge dict)."""
+        _, ne = self.counts()
+        dev = self.stats.device
+        c0 = torch.empty(max(ne, 1), dtype=torch.int64, device=dev)
+        c1 = torch.empty_like(c0)
+        first = torch.empty_like(c0)
+        v0 = torch.empty(max(ne, 1), dtype=torch.int32, device=dev)
+        v1 = torch.empty_like(v0)
+        w = torch.empty_like(v0)
+        d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(self.L.pg_graph_export_edges(ctypes.byref(self.c), ctypes.byref(rd.c), _ptr(c0), _ptr(v0), _ptr(c1), _ptr(v1),
+                                           _ptr(w), _ptr(first), ne, _ptr(d_n), _stream()), "pg_graph_export_edges")
+        assert int(d_n.item()) == ne
+        order = np.argsort(first[:ne].cpu().numpy().view(np.uint64), kind="stable")
+        f = lambda t, dt: t[:ne].cpu().numpy().view(dt)[order]
+        return f(c0, np.uint64), f(v0, np.uint32), f(c1, np.uint64), f(v1, np.uint32), f(w, np.uint32)
+
+    def components(self, rd, min_weight=1):
+        """K7 + host ordering.  Returns (nslot, code, v5, label) per node; label =
+        rank of the node's component under (size descending, smallest (code, v5))."""
+        check(self.L.pg_graph_components(ctypes.byref(self.c), int(min_weight), _stream()), "pg_graph_components")
+        nn, _ = self.counts()
+        dev = self.stats.device
+        nslot = torch.empty(max(nn, 1), dtype=torch.int32, device=dev)
+        code = torch.empty(max(nn, 1), dtype=torch.int64, device=dev)
+        v5 = torch.empty(max(nn, 1), dtype=torch.int32, device=dev)
+        root = torch.empty(max(nn, 1), dtype=torch.int32, device=dev)
+        d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(self.L.pg_graph_export_nodes(ctypes.byref(self.c), ctypes.byref(rd.c), _ptr(nslot), _ptr(code), _ptr(v5),
+                                           _ptr(root), nn, _ptr(d_n), _stream()), "pg_graph_export_nodes")
+        assert int(d_n.item()) == nn
+        nslot = nslot[:nn].cpu().numpy().view(np.uint32)
+        code = code[:nn].cpu().numpy().view(np.uint64)
+        v5 = v5[:nn].cpu().numpy().view(np.uint32)
+        root = root[:nn].cpu().numpy().view(np.uint32)
+        if nn == 0:
+            return nslot, code, v5, np.zeros(0, np.int64)
+        order = np.lexsort((v5, code))                       # nodes ascending by (code, v5)
+        roots_sorted = root[order]
+        uniq, first_idx, counts = np.unique(roots_sorted, return_index=True, return_counts=True)
+        # first_idx = rank of the component's smallest node; order components by (-size, that rank)
+        comp_order = np.lexsort((first_idx, -counts))
+        label_of_comp = np.empty(uniq.size, np.int64)
+        label_of_comp[comp_order] = np.arange(uniq.size)
+        label = label_of_comp[np.searchsorted(uniq, root)]
+        return nslot, code, v5, label
+
+    def set_labels(self, nslot, label):
+        self.node_label.fill_(-1)
+        if nslot.size:
+            idx = torch.from_numpy(nslot.astype(np.int64)).to(self.node_label.device)
+            val = torch.from_numpy(label.astype(np.int32)).to(self.node_label.device)
+            self.node_label.index_put_((idx,), val)
+
+    def regions(self, hits, packed, k):
+        """K8 for one strand: rows (rec, start, end, label) in walk order."""
+        L = self.L
+        dev = self.stats.device
+        if hits.n == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int32)
+        ws_bytes = int(L.pg_label_workspace_bytes(hits.n))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        cap = hits.n
+        rr = torch.empty(cap, dtype=torch.int32, device=dev)
+        re_ = torch.empty(cap, dtype=torch.int64, device=dev)
+        rl = torch.empty(cap, dtype=torch.int32, device=dev)
+        d_n = torch.zeros(2, dtype=torch.int64, device=dev)
+        check(L.pg_label_regions(ctypes.byref(self.c), _ptr(hits.g), _ptr(hits.node), _ptr(hits.rec), _ptr(hits.v6), hits.n,
+                                 _ptr(packed.d_seq_off), k, hits.strand, _ptr(rr), _ptr(re_), _ptr(rl), cap, _ptr(d_n),
+                                 _ptr(ws), ws_bytes, _stream()), "pg_label_regions")
+        n = int(d_n[0].item())
+        rec = rr[:n].cpu().numpy()
+        end = re_[:n].cpu().numpy()
+        lab = rl[:n].cpu().numpy()
+        start = np.zeros(n, np.int64)
+        if n > 1:
+            same = rec[1:] == rec[:-1]
+            start[1:][same] = end[:-1][same]
+        return rec, start, end, lab
+
+
+class GraphResult:
+    def __init__(self):
+        self.edges = None
+        self.nodes = None
+        self.rows_raw = []          # list of (rec, start, end, strand_sign, label) arrays per strand
+
+    def xyz_lines(self):
+        c0, v0, c1, v1, w = self.edges
+        return ["%d_%d\t%d_%d\t%d" % t for t in zip(c0.tolist(), v0.tolist(), c1.tolist(), v1.tolist(), w.tolist())]
+
+    def mcl_lines(self):
+        """One line per component, like the cluster file the reference reads (:1918-1929)."""
+        nslot, code, v5, label = self.nodes
+        order = np.lexsort((v5, code, label))
+        lines, cur, lab_prev = [], [], None
+        for c, v, l in zip(code[order].tolist(), v5[order].tolist(), label[order].tolist()):
+            if l != lab_prev and cur:
+                lines.append("\t".join(cur))
+                cur = []
+            cur.append("%d_%d" % (c, v))
+            lab_prev = l
+        if cur:
+            lines.append("\t".join(cur))
+        return lines
+
+    def rows(self, packed, data):
+        """[(seqid, start, end, strand, label)] in the reference's print order:
+        per record, forward rows then rc rows mirrored to (n-end, n-start, '-')."""
+        ids = record_ids(packed, data)
+        lens = packed.seq_lengths
+        per_rec = {}
+        for rec, start, end, sign, lab in self.rows_raw:
+            for r, s, e, l in zip(rec.tolist(), start.tolist(), end.tolist(), lab.tolist()):
+                if sign > 0:
+                    per_rec.setdefault((r, 0), []).append((ids[r], s, e, "+", l))
+                else:
+                    n = int(lens[r])
+                    per_rec.setdefault((r, 1), []).append((ids[r], n - e, n - s, "-", l))
+        out = []
+        for key in sorted(per_rec):
+            out.extend(per_rec[key])
+        return out
+
+
+def record_ids(packed, data):
+    """seqid = header line minus '>' and minus its last byte (kmer_numba.py:156, 1947)."""
+    ids = []
+    n = len(data)
+    for off in packed.hdr_off.tolist():
+        e = data.find(b"\n", off)
+        if e < 0:
+            e = n - 1                      # Q8: the final line loses its last byte even without '\n'
+        ids.append(bytes(data[off + 1:e]).decode("utf-8", errors="replace"))
+    return ids
+
+
+def labels_from_mcl(lines, xyz_edges):
+    """label_dct as the reference builds it from a cluster file (:1916-1944): cluster line index,
+    then fresh labels for nodes of the .xyz missing from it, scanning column 1 then column 2."""
+    lab = {}
+    flag = 0
+    for line in lines:
+        for name in line.rstrip("\n").split("\t"):
+            if not name:
+                continue
+            a, b = name.split("_")[:2]
+            lab[(int(a), int(b))] = flag
+        flag += 1
+    c0, v0, c1, v1, _ = xyz_edges
+    for a, b, c, d in zip(c0.tolist(), v0.tolist(), c1.tolist(), v1.tolist()):
+        if (a, b) not in lab:
+            lab[(a, b)] = flag
+            flag += 1
+        if (c, d) not in lab:
+            lab[(c, d)] = flag
+            flag += 1
+    return lab
+
+
+def seq2graph_device(packed, rd, k, Ns=2 ** 63, rc=False, min_weight=1, mcl_lines=None):
+    """Stages 3-5 on the GPU.  ``rd`` = rdBG table from DbgTable.select_rdbg()."""
+    k = int(min(max(1, k), 27))
+    n_rec = packed.record_prefix(Ns, 1)
+    n_strands = 2 if rc else 1
+    hits = [path_hits(packed, rd, n_rec, s) for s in range(n_strands)]
+    total = sum(h.n for h in hits)
+    g = RdbgGraph(total, packed.pk2.device)
+    for h in hits:
+        g.add_hits(h, n_strands)
+    res = GraphResult()
+    res.edges = g.edges(rd)
+    nslot, code, v5, label = g.components(rd, min_weight)
+    if mcl_lines is not None:      # an externally produced cluster file wins (the "# the mcl has been ran" path)
+        lab = labels_from_mcl(mcl_lines, res.edges)
+        label = np.array([lab[(c, v)] for c, v in zip(code.tolist(), v5.tolist())], dtype=np.int64)
+    res.nodes = (nslot, code, v5, label)
+    g.set_labels(nslot, label)
+    for h in hits:
+        rec, start, end, lab_ = g.regions(h, packed, k)
+        res.rows_raw.append((rec, start, end, 1 if h.strand == 0 else -1, lab_))
+    res.n_hits = total
+    res.graph = g
+    return res

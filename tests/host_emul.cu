@@ -11,6 +11,7 @@
 thread_local char pg_err_buf[512] = "";
 int pg_fail(int code, const char *, ...) { return code; }
 int pg_num_sms() { return 148; }
+void pg_tune_once() {}
 
 static const int TILE = 16384;
 

@@ -1,0 +1,38 @@
+"""The CLI end to end on the GPU: same table as the reference printed for test.fsa."""
+import io
+import os
+import shutil
+
+import pytest
+
+from conftest import load_small_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cli_test_fsa(tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pangenome_b200 import cli
+    case = {c["name"]: c for c in load_small_cases()}["test_fsa_k5"]
+    fa = tmp_path / "test.fsa"
+    fa.write_bytes(case["input_latin1"].encode("latin-1"))
+    out = io.StringIO()
+    cli.entry_point(["prog", "-m", "-i", str(fa), "-k5", "-n", "5e8"], out=out)
+    lines = out.getvalue().split("\n")
+    rows = [l for l in lines if l and not l.startswith("#")]
+    assert rows == ["1\t0\t39\t+\t0", "2\t0\t7\t+\t1"]
+    assert [l for l in lines if l.startswith("# ")][0] == "# build the dBG"
+    assert (tmp_path / "test.fsa_rdbg_weight.xyz").read_text().split("\n")[:-1] == case["xyz"]
+    assert sorted((tmp_path / "test.fsa_rdbg_weight.xyz.mcl").read_text().split("\n")[:-1]) == sorted(case["mcl"])
+    # second run: the cluster file exists -> "# the mcl has been ran", same rows
+    out2 = io.StringIO()
+    cli.entry_point(["prog", "-i", str(fa), "-k", "5"], out=out2)
+    assert "# the mcl has been ran" in out2.getvalue()
+    assert [l for l in out2.getvalue().split("\n") if l and not l.startswith("#")] == rows
+    # k = 27: the reference crashes on the empty edge set (F9); defined behaviour: no rows, exit 0
+    os.remove(tmp_path / "test.fsa_rdbg_weight.xyz.mcl")
+    out3 = io.StringIO()
+    cli.entry_point(["prog", "-i", str(fa), "-k", "27"], out=out3)
+    assert [l for l in out3.getvalue().split("\n") if l and not l.startswith("#")] == []

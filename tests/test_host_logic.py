@@ -1,0 +1,70 @@
+"""CPU tests of the host side: CLI parsing, C-ABI symbols, loud failure without CUDA."""
+import ctypes
+import io
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def test_cli_parse_like_reference():
+    from pangenome_b200 import cli
+    a, extra, flags = cli.parse_args(["prog", "-m", "-i", "x.fa", "-k27", "-n", "5e8", "-c", "3", "--min-edge-weight", "2", "-z"])
+    assert a["-i"] == "x.fa" and a["-k"] == "27" and a["-c"] == "3" and a["-n"] == "5e8"
+    assert extra["--min-edge-weight"] == "2"
+    assert cli._eval_n("2**63") == 2 ** 63 and cli._eval_n("5e8") == 500000000
+    out = io.StringIO()
+    with pytest.raises(SystemExit):
+        cli.entry_point(["prog"], out=out)
+    assert out.getvalue().startswith("Usage:") and len(out.getvalue().strip().split("\n")) == 11
+
+
+def test_abi_exports_every_declared_symbol():
+    """libpgdbg.so loads and exports each function include/pgdbg.h declares; the ctypes table
+    covers exactly that set."""
+    from pangenome_b200 import _lib, build
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "pgdbg.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", hdr))
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().pg_version() >= 100
+    assert _lib.load().pg_pack_words(1600) == 132
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pangenome_b200 import engine, _lib
+    with pytest.raises(_lib.PgError):
+        engine.to_device_bytes(b">a\nACGT\n")
+    with pytest.raises(_lib.PgError):
+        engine.DbgTable(1024, 5, 2)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pangenome_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+    src = open(os.path.join(ROOT, "kmer_b200.py")).read()
+    assert "oracle" not in src
+
+
+def test_record_prefix_ns():
+    """-n semantics: records are consumed until the running count exceeds Ns (the crossing record is kept)."""
+    import numpy as np
+    from pangenome_b200.engine import PackedSeqs
+    p = PackedSeqs.__new__(PackedSeqs)
+    p.seq_off = np.array([0, 100, 250, 400, 1000])
+    assert p.record_prefix(2 ** 63, 2) == 4
+    assert p.record_prefix(300, 1) == 3      # 100, 250, 400 > 300
+    assert p.record_prefix(300, 2) == 2      # 200, 500 > 300
+    assert p.record_prefix(0, 1) == 1
