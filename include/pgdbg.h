@@ -110,9 +110,33 @@ int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes,
  */
 int64_t pg_table_bytes(int64_t capacity);
 int pg_table_clear(const pg_table *t, pg_stream_t stream);
+/* adds (strands x records of [0,n_rec) shorter than k whose offset lies in [g_begin, g_end]) to PG_STAT_SHORT;
+ * pg_kmer_insert calls it itself, the two-phase path (pg_kmer_partition) does not */
+int pg_count_short(const pg_table *t, const int64_t *d_seq_off, int64_t n_rec, int64_t g_begin, int64_t g_end,
+                   pg_stream_t stream);
 int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb,
                    const int64_t *d_seq_off, int64_t n_rec, int64_t g_begin, int64_t g_end,
                    pg_stream_t stream);
+
+/* ---- K2a + K3: the two-phase build (single-GPU fast path and the multi-GPU split) ---------
+ * pg_kmer_partition: same occurrences as pg_kmer_insert, but each position emits one
+ *   16-byte update record {uint64 key, uint32 masks, uint32 inc} (mode/k taken from `t`;
+ *   its slots are not touched) into bucket
+ *       (owner << sub_bits) | sub,   owner = low owner_bits of mix64(key)  (which GPU owns the key)
+ *                                    sub   = top sub_bits of mix64(key)    (= which 1/2^sub_bits region
+ *                                            of ANY power-of-two table the key's home slot lies in)
+ *   d_records holds 2^(owner_bits+sub_bits) buckets of part_cap records each; d_part_counts[b]
+ *   = records produced for bucket b (records beyond part_cap are dropped: compare and fall back).
+ * pg_insert_records: upsert the records of n_seg segments [seg_off[i], seg_off[i]+seg_cnt[i]) of
+ *   d_records, segment after segment, so that the table region being updated stays in L2.
+ *   Replaces the same reference lines as pg_kmer_insert; the all-to-all between the two calls is
+ *   the host's (torch.distributed / NCCL).
+ */
+int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                      int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
+                      uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream);
+int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
+                      const int64_t *d_seg_cnt, int n_seg, pg_stream_t stream);
 
 /* ---- table read-out ---------------------------------------------------------
  * pg_table_count   : fills PG_STAT_USED / PG_STAT_ENTRIES in t->d_stats.
@@ -171,7 +195,9 @@ int pg_path_hits(const pg_table *rdbg, const uint32_t *d_pk2, const uint32_t *d_
  * clustering itself is third-party MCL; here components are the connected
  * components of the edge list restricted to weight >= min_weight (min_weight 1 =
  * the definition of the reference's other/test_net.py).
- * d_stats: [0] overflow flag, [1] nodes, [2] edges.
+ * d_stats: [0] overflow flag, [1] node slots used (every hit; only nodes that occur in an
+ * edge are exported / labelled - the reference builds its label dict from the edge list),
+ * [2] edges.
  */
 typedef struct pg_graph {
     uint64_t *d_node_keys;    /* node_cap                                  */

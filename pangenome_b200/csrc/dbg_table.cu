@@ -173,7 +173,7 @@ __global__ void k4_rdbg_select(const uint64_t *__restrict__ slots, int64_t cap, 
         uint32_t f = pg_rdbg_flags(key, v, mode, k);
         if (!f) continue;
         // every key arrives exactly once: claim with CAS, then plain stores of masks + flags
-        uint64_t s = pg_mix64(key) & rd.capmask;
+        uint64_t s = tv_home(rd, key);
         bool done = false;
         for (uint32_t probe = 0; probe < PG_MAX_PROBE && !done; probe++) {
             uint64_t *p = rd.slots + 2 * s;
@@ -233,6 +233,18 @@ extern "C" int pg_table_clear(const pg_table *t, pg_stream_t stream_) {
     return PG_OK;
 }
 
+extern "C" int pg_count_short(const pg_table *t, const int64_t *d_seq_off, int64_t n_rec, int64_t g_begin, int64_t g_end,
+                              pg_stream_t stream_) {
+    int rc = check_table(t, "pg_count_short"); if (rc) return rc;
+    if (!d_seq_off || n_rec < 0) return pg_fail(PG_ERR_INVALID, "pg_count_short: bad arguments");
+    if (n_rec == 0) return PG_OK;
+    int strands = t->mode == PG_MODE_LITERAL ? 1 : 2;
+    // a record is owned by the range holding its offset; the range that ends the stream also owns trailing empty records
+    k2_count_short<<<(unsigned)((n_rec + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(d_seq_off, n_rec, g_begin, g_end, g_end, t->k, strands, t->d_stats);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
 extern "C" int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                               int64_t n_rec, int64_t g_begin, int64_t g_end, pg_stream_t stream_) {
     int rc = check_table(t, "pg_kmer_insert"); if (rc) return rc;
@@ -241,12 +253,10 @@ extern "C" int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const ui
     if ((reinterpret_cast<uintptr_t>(d_pk2) & 15) || (reinterpret_cast<uintptr_t>(d_amb) & 15))
         return pg_fail(PG_ERR_INVALID, "pg_kmer_insert: packed buffers must be 16-byte aligned");
     cudaStream_t stream = (cudaStream_t)stream_;
-    TableView tv{t->d_slots, (uint64_t)t->capacity - 1, t->d_stats};
+    TableView tv = make_view(t);
     int strands = t->mode == PG_MODE_LITERAL ? 1 : 2;
-    if (n_rec > 0) {
-        // g_total is only needed to give trailing empty records an owner; the host passes ranges that end at it
-        k2_count_short<<<(unsigned)((n_rec + 255) / 256), 256, 0, stream>>>(d_seq_off, n_rec, g_begin, g_end, g_end, t->k, strands, t->d_stats);
-    }
+    (void)strands;
+    rc = pg_count_short(t, d_seq_off, n_rec, g_begin, g_end, stream_); if (rc) return rc;
     if (g_end > g_begin && n_rec > 0) {
         int64_t w_first = (g_begin >> 5) & ~(int64_t)3;                 // multiple of 4 words -> 16-byte aligned staging
         int64_t w_last = (g_end + 31) >> 5;
@@ -317,7 +327,7 @@ extern "C" int pg_rdbg_select(const pg_table *dbg, const pg_table *rdbg, pg_stre
     rc = check_table(rdbg, "pg_rdbg_select"); if (rc) return rc;
     if (dbg->mode != rdbg->mode || dbg->k != rdbg->k) return pg_fail(PG_ERR_INVALID, "pg_rdbg_select: mode/k mismatch");
     cudaStream_t stream = (cudaStream_t)stream_;
-    TableView rd{rdbg->d_slots, (uint64_t)rdbg->capacity - 1, rdbg->d_stats};
+    TableView rd = make_view(rdbg);
     k4_rdbg_select<<<scan_grid(dbg->capacity, 256), 256, 0, stream>>>(dbg->d_slots, dbg->capacity, dbg->mode, dbg->k, dbg->d_stats, rd);
     PG_CUDA(cudaGetLastError());
     return PG_OK;

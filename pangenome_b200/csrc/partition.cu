@@ -1,0 +1,213 @@
+// partition.cu - the two-phase dBG build: K2a (k-mer extraction -> hash-partitioned update records)
+// and K3 (record insertion, partition by partition).
+//
+// Why two phases: one fused extract+insert launch (dbg_table.cu) probes a multi-GB table at random -
+// ncu shows it DRAM-activate bound (16 G probes/s, ~3.4 DRAM sectors read + 1 written per probe).
+// Here K2a streams the packed sequence once and emits one 16-byte record {key, masks, inc} per
+// position, bucketed by the high bits of the slot index the key hashes to (and, across GPUs, by the
+// owner rank).  K3 then walks the buckets in order, so at any moment the CTAs of the grid hammer one
+// table region that fits the 126 MB L2: atomicCAS / red.or / red.add resolve in L2 and every table
+// line is written back to HBM once.  The bucketed records are also exactly what the multi-GPU path
+// exchanges with an all-to-all (owner = top hash bits, disjoint from the slot bits).
+//
+// Record emission inside a CTA tile is a counting sort in shared memory (histogram, one global
+// atomicAdd per bucket per tile to reserve space, reorder through an index permutation) so global
+// stores are coalesced 16-byte runs per bucket.
+#include "table_dev.cuh"
+
+namespace {
+
+constexpr int KP_THREADS = 128;
+constexpr int KP_G = 16;                               // positions per thread
+constexpr int KP_TILE = KP_THREADS * KP_G;             // 2048 positions per CTA tile
+constexpr int KP_MAX_REC = 2 * KP_TILE;                // literal-rc mode emits two records per position
+constexpr int KP_MAX_PARTS = 1024;
+
+struct PartArgs {
+    const uint64_t *pk2; const uint32_t *amb; int64_t n_words;
+    const int64_t *seq_off; int64_t n_rec, g_begin, g_end; int k; uint64_t pow5km1;
+    int64_t t_first, n_tiles;
+    int sub_bits, owner_bits; int n_parts;
+    uint4 *records; int64_t part_cap; unsigned long long *part_counts;
+};
+
+__device__ __forceinline__ uint32_t part_of(const PartArgs &a, uint64_t key) {
+    uint64_t h = pg_mix64(key);
+    uint32_t sub = a.sub_bits ? (uint32_t)(h >> (64 - a.sub_bits)) : 0u;      // hash prefix = table region (tv_home)
+    uint32_t owner = a.owner_bits ? (uint32_t)(h & ((1u << a.owner_bits) - 1u)) : 0u;   // low bits: disjoint from the slot bits
+    return (owner << a.sub_bits) | sub;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(KP_THREADS)
+k2a_partition(PartArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int MAXR = (MODE == PG_MODE_LITERAL_RC) ? KP_MAX_REC : KP_TILE;
+    uint4 *s_rec = reinterpret_cast<uint4 *>(smem);                          // MAXR records, natural order
+    uint16_t *s_pid = reinterpret_cast<uint16_t *>(s_rec + MAXR);            // MAXR bucket ids
+    uint16_t *s_perm = s_pid + MAXR;                                         // sorted index -> natural index
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_perm + MAXR);          // n_parts
+    uint32_t *s_off = s_hist + a.n_parts;                                    // n_parts: exclusive offsets
+    uint32_t *s_tick = s_off + a.n_parts;                                    // n_parts: tickets
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_tick + a.n_parts + (a.n_parts & 1));
+    __shared__ uint32_t s_nrec;
+
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.n_parts; i += KP_THREADS) { s_hist[i] = 0; s_tick[i] = 0; }
+        if (threadIdx.x == 0) s_nrec = 0;
+        __syncthreads();
+        // ---- 1. compute this thread's records ------------------------------------------------
+        const int64_t g0 = (a.t_first + tile) * KP_TILE + (int64_t)threadIdx.x * KP_G;
+        if (g0 < a.g_end && g0 + KP_G > a.g_begin) {
+            const int64_t wi = g0 >> 5;
+            const int j0 = (int)(g0 & 31);
+            PgWindow w;
+            w.prv = wi > 0 ? __ldg(a.pk2 + wi - 1) : 0; w.cur = __ldg(a.pk2 + wi); w.nxt = wi + 1 < a.n_words ? __ldg(a.pk2 + wi + 1) : 0;
+            w.aprv = wi > 0 ? __ldg(a.amb + wi - 1) : 0; w.acur = __ldg(a.amb + wi); w.anxt = wi + 1 < a.n_words ? __ldg(a.amb + wi + 1) : 0;
+            int64_t r = find_record(a.seq_off, a.n_rec, g0);
+            int64_t rs = r >= 0 ? __ldg(a.seq_off + r) : 0, re = __ldg(a.seq_off + r + 1);
+            uint64_t F, R;
+            pg_codes_init(w, j0, a.k, F, R);
+#pragma unroll 1
+            for (int q = 0; q < KP_G; q++) {
+                const int64_t g = g0 + q;
+                const int j = j0 + q;
+                if (g >= a.g_end) break;
+                while (r + 1 < a.n_rec && g >= re) { r++; rs = re; re = __ldg(a.seq_off + r + 1); }
+                if (g >= a.g_begin && r >= 0 && g + a.k <= re) {
+                    uint32_t vf, vr;
+                    pg_occ_vals(w, j, g - rs, re - rs, a.k, vf, vr);
+                    if (MODE == PG_MODE_CANONICAL) {
+                        PgUpdate u = pg_canonical_update(F, R, vf, vr);
+                        uint32_t pid = part_of(a, u.key);
+                        uint32_t at = atomicAdd(&s_nrec, 1u);
+                        s_rec[at] = make_uint4((uint32_t)u.key, (uint32_t)(u.key >> 32), u.masks, u.inc);
+                        s_pid[at] = (uint16_t)pid; atomicAdd(&s_hist[pid], 1u);
+                    } else {
+                        uint32_t pid = part_of(a, F);
+                        uint32_t at = atomicAdd(&s_nrec, 1u);
+                        s_rec[at] = make_uint4((uint32_t)F, (uint32_t)(F >> 32), vf, 1u);
+                        s_pid[at] = (uint16_t)pid; atomicAdd(&s_hist[pid], 1u);
+                        if (MODE == PG_MODE_LITERAL_RC) {
+                            pid = part_of(a, R);
+                            at = atomicAdd(&s_nrec, 1u);
+                            s_rec[at] = make_uint4((uint32_t)R, (uint32_t)(R >> 32), vr, 1u);
+                            s_pid[at] = (uint16_t)pid; atomicAdd(&s_hist[pid], 1u);
+                        }
+                    }
+                }
+                pg_codes_roll(w, j, a.k, a.pow5km1, F, R);
+            }
+        }
+        __syncthreads();
+        const uint32_t nrec = s_nrec;
+        if (nrec == 0) continue;
+        // ---- 2. reserve space: one global atomicAdd per bucket per tile; local exclusive offsets ----
+        if (threadIdx.x < 32) {     // warp 0 scans the histogram in chunks of 32
+            uint32_t carry = 0;
+            for (int base = 0; base < a.n_parts; base += 32) {
+                int i = base + threadIdx.x;
+                uint32_t h = i < a.n_parts ? s_hist[i] : 0, inc = h;
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += y; }
+                if (i < a.n_parts) {
+                    s_off[i] = carry + inc - h;
+                    s_base[i] = h ? atomicAdd(a.part_counts + i, (unsigned long long)h) : 0ull;
+                }
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        __syncthreads();
+        // ---- 3. permutation: sorted position -> natural index ------------------------------------
+        for (uint32_t i = threadIdx.x; i < nrec; i += KP_THREADS) {
+            uint32_t pid = s_pid[i];
+            uint32_t o = s_off[pid] + atomicAdd(&s_tick[pid], 1u);
+            s_perm[o] = (uint16_t)i;
+        }
+        __syncthreads();
+        // ---- 4. coalesced write-out: consecutive threads write consecutive records of one bucket ----
+        for (uint32_t o = threadIdx.x; o < nrec; o += KP_THREADS) {
+            uint32_t i = s_perm[o];
+            uint32_t pid = s_pid[i];
+            unsigned long long dst = s_base[pid] + (o - s_off[pid]);
+            if ((int64_t)dst < a.part_cap) a.records[(int64_t)pid * a.part_cap + (int64_t)dst] = s_rec[i];
+        }
+    }
+}
+
+// K3: insert the records of a list of segments, in list order (the grid sweeps the segments together,
+// so the table region under update stays L2-resident).
+__global__ void __launch_bounds__(256)
+k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
+                  const int64_t *__restrict__ seg_cnt, int n_seg) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int s = 0; s < n_seg; s++) {
+        const int64_t off = __ldg(seg_off + s), cnt = __ldg(seg_cnt + s);
+        for (int64_t i = i0; i < cnt; i += stride) {
+            uint4 r = pg_ld_stream(records + off + i);
+            uint64_t key = (uint64_t)r.x | ((uint64_t)r.y << 32);
+            table_upsert(t, key, r.z, r.w);
+        }
+    }
+}
+
+int part_smem_bytes(int mode, int n_parts) {
+    int maxr = mode == PG_MODE_LITERAL_RC ? KP_MAX_REC : KP_TILE;
+    return maxr * 16 + maxr * 2 * 2 + (3 * n_parts + (n_parts & 1)) * 4 + n_parts * 8 + 16;
+}
+
+}  // namespace
+
+extern "C" int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                                 int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
+                                 uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream_) {
+    if (!t || t->k < 1 || t->k > 27 || t->mode < 0 || t->mode > 2)
+        return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: bad table descriptor (only mode and k are used)");
+    if (!d_pk2 || !d_amb || !d_seq_off || !d_records || !d_part_counts || n_rec < 0 || g_begin < 0 || g_end < g_begin || part_cap < 1)
+        return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: bad arguments");
+    if (owner_bits < 0 || owner_bits > 6 || sub_bits < 0 || sub_bits > 10 || (1 << (owner_bits + sub_bits)) > KP_MAX_PARTS)
+        return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: owner_bits/sub_bits out of range");
+    cudaStream_t st = (cudaStream_t)stream_;
+    int n_parts = 1 << (owner_bits + sub_bits);
+    PG_CUDA(cudaMemsetAsync(d_part_counts, 0, (size_t)n_parts * 8, st));
+    if (n_rec == 0 || g_end == g_begin) return PG_OK;
+    PartArgs a;
+    a.pk2 = reinterpret_cast<const uint64_t *>(d_pk2); a.amb = d_amb; a.n_words = ((g_end + 31) >> 5) + 4;
+    a.seq_off = d_seq_off; a.n_rec = n_rec; a.g_begin = g_begin; a.g_end = g_end; a.k = t->k; a.pow5km1 = pg_pow5(t->k - 1);
+    a.t_first = g_begin / KP_TILE; a.n_tiles = (g_end + KP_TILE - 1) / KP_TILE - a.t_first;
+    a.sub_bits = sub_bits; a.owner_bits = owner_bits; a.n_parts = n_parts;
+    a.records = reinterpret_cast<uint4 *>(d_records); a.part_cap = part_cap;
+    a.part_counts = reinterpret_cast<unsigned long long *>(d_part_counts);
+    int smem = part_smem_bytes(t->mode, n_parts);
+    int per_sm = 200 * 1024 / smem; if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
+    int64_t maxg = (int64_t)pg_num_sms() * per_sm;
+    int grid = (int)(a.n_tiles < maxg ? a.n_tiles : maxg);
+    switch (t->mode) {
+    case PG_MODE_LITERAL:
+        PG_CUDA(cudaFuncSetAttribute(k2a_partition<PG_MODE_LITERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k2a_partition<PG_MODE_LITERAL><<<grid, KP_THREADS, smem, st>>>(a); break;
+    case PG_MODE_LITERAL_RC:
+        PG_CUDA(cudaFuncSetAttribute(k2a_partition<PG_MODE_LITERAL_RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k2a_partition<PG_MODE_LITERAL_RC><<<grid, KP_THREADS, smem, st>>>(a); break;
+    default:
+        PG_CUDA(cudaFuncSetAttribute(k2a_partition<PG_MODE_CANONICAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k2a_partition<PG_MODE_CANONICAL><<<grid, KP_THREADS, smem, st>>>(a); break;
+    }
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
+                                 const int64_t *d_seg_cnt, int n_seg, pg_stream_t stream_) {
+    if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)))
+        return pg_fail(PG_ERR_INVALID, "pg_insert_records: bad table");
+    if (n_seg < 0 || (n_seg > 0 && (!d_records || !d_seg_off || !d_seg_cnt))) return pg_fail(PG_ERR_INVALID, "pg_insert_records: bad arguments");
+    if (n_seg == 0) return PG_OK;
+    if (reinterpret_cast<uintptr_t>(d_records) & 15) return pg_fail(PG_ERR_INVALID, "pg_insert_records: records must be 16-byte aligned");
+    TableView tv = make_view(t);
+    int grid = pg_num_sms() * 8;
+    k3_insert_records<<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_seg);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}

@@ -95,7 +95,7 @@ int exclusive_scan(const uint32_t *in, int64_t n, int64_t *out, int64_t *bsum, i
 __device__ __forceinline__ bool rdbg_hit(const TableView &rd, int mode, uint64_t lit, uint64_t other, uint64_t &slot_o) {
     uint64_t key = lit; uint32_t o = 0;
     if (mode == PG_MODE_CANONICAL && other < lit) { key = other; o = 1; }
-    uint64_t s = pg_mix64(key) & rd.capmask;
+    uint64_t s = tv_home(rd, key);
     for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
         uint64_t ck, cv;
         pg_ld_slot(rd.slots + 2 * s, ck, cv);
@@ -271,6 +271,9 @@ __global__ void k6_edges(pg_graph g, const uint32_t *__restrict__ hit_nslot, con
     int64_t v = set_insert(g.d_visit_keys, (uint64_t)g.visit_cap - 1, ((uint64_t)e << 32) | rs_id, &fresh);
     if (v < 0) { atomicExch(reinterpret_cast<unsigned long long *>(g.d_stats), 1ull); return; }
     if (fresh) atomicAdd(g.d_edge_w + e, 1u);
+    // only nodes that appear in an edge exist upstream (label_dct is built from the .xyz, :1918-1944):
+    // -2 = "in the graph, label pending"; hits that never form an edge keep -1 and can never match in K8
+    g.d_node_label[a] = -2; g.d_node_label[b] = -2;
     // walk ordinal: records in order, forward strand before rc strand (rdbg_edge_weight_jit_ :1814-1817), then walk order
     uint64_t ord = (rs_id << 36) | (uint64_t)(strand ? (n - 2 - i) : i);
     atomicMin(reinterpret_cast<unsigned long long *>(g.d_edge_first + e), (unsigned long long)ord);
@@ -332,7 +335,7 @@ __global__ void k_export_nodes(pg_graph g, const uint64_t *__restrict__ rd_slots
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= g.node_cap) return;
     uint64_t nk = g.d_node_keys[i];
-    if (nk == PG_EMPTY) return;
+    if (nk == PG_EMPTY || g.d_node_label[i] == -1) return;     // slot empty / hit that is in no edge
     unsigned long long at = atomicAdd(n_out, 1ull);
     if ((int64_t)at >= cap) return;
     uint64_t c; uint32_t v;
@@ -470,7 +473,7 @@ extern "C" int pg_path_hits(const pg_table *rdbg, const uint32_t *d_pk2, const u
     uint32_t *tile_counts = hitbits + nbits_words;
     int64_t *tile_off = reinterpret_cast<int64_t *>(ws + ((nbits_words + a.n_tiles) * 4 + 15) / 16 * 16);
     int64_t *bsum = tile_off + a.n_tiles;
-    TableView rd{rdbg->d_slots, (uint64_t)rdbg->capacity - 1, rdbg->d_stats};
+    TableView rd = make_view(rdbg);
     int grid = (int)(a.n_tiles < (int64_t)pg_num_sms() * 8 ? a.n_tiles : (int64_t)pg_num_sms() * 8);
     k5_mark<<<grid, K2_THREADS, 0, st>>>(rd, rdbg->mode, a, strand, hitbits, tile_counts);
     exclusive_scan(tile_counts, a.n_tiles, tile_off, bsum, d_n_hits, st);

@@ -7,11 +7,19 @@ constexpr int K2_THREADS = 256;                 // one 32-base word per thread
 constexpr int K2_TILE_WORDS = K2_THREADS;       // 8192 bases per CTA tile
 constexpr uint32_t PG_MAX_PROBE = 1u << 16;
 
-struct TableView { uint64_t *slots; uint64_t capmask; int64_t *stats; };
+// Home slot = TOP bits of the 64-bit mix: the high bits of a slot index are then hash bits too, so
+// "region of the table" == "hash prefix" for every capacity (K2a buckets records by that prefix before
+// the table is even sized); the owner rank of the multi-GPU split comes from the LOW bits instead.
+struct TableView { uint64_t *slots; uint64_t capmask; int64_t *stats; int shift; };
+__host__ __device__ __forceinline__ uint64_t tv_home(const TableView &t, uint64_t key) { return pg_mix64(key) >> t.shift; }
+inline TableView make_view(const pg_table *t) {
+    int bits = 0; while ((1ll << bits) < t->capacity) bits++;
+    return TableView{t->d_slots, (uint64_t)t->capacity - 1, t->d_stats, 64 - bits};
+}
 
 // returns the slot index the key lives in (claimed if absent), or -1 when probing gives up
 __device__ __forceinline__ int64_t table_upsert(const TableView &t, uint64_t key, uint32_t masks, uint32_t inc) {
-    uint64_t s = pg_mix64(key) & t.capmask;
+    uint64_t s = tv_home(t, key);
     for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
         uint64_t *p = t.slots + 2 * s;
         uint64_t ck, cv;

@@ -231,3 +231,76 @@ def build_dbg(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=None, max_grow
             return t, n_rec
         cap *= 2
     raise PgError("dBG table kept overflowing up to capacity %d" % cap)
+
+
+class RecordBuckets:
+    """Output of K2a (pg_kmer_partition): 2^(owner_bits+sub_bits) buckets of 16-byte update
+    records, ``part_cap`` records apart, with the per-bucket counts on the device."""
+
+    def __init__(self, n_parts, part_cap, device):
+        self.n_parts, self.part_cap = n_parts, part_cap
+        self.records = torch.empty(2 * n_parts * part_cap, dtype=torch.int64, device=device)
+        self.counts = torch.zeros(n_parts, dtype=torch.int64, device=device)
+        self.seg_off = torch.arange(n_parts, dtype=torch.int64, device=device) * part_cap
+
+
+def partition_kmers(packed, k, mode, n_rec, owner_bits, sub_bits, g_begin=None, g_end=None, slack=1.25, buckets=None):
+    """K2a over records [0, n_rec): returns RecordBuckets (no synchronisation)."""
+    L = _lib.load()
+    n_parts = 1 << (owner_bits + sub_bits)
+    g_begin = int(packed.seq_off[0]) if g_begin is None else g_begin
+    g_end = int(packed.seq_off[n_rec]) if g_end is None else g_end
+    per_pos = 2 if mode == _lib.PG_MODE_LITERAL_RC else 1
+    part_cap = int((g_end - g_begin) * per_pos / n_parts * slack) + 4096
+    if buckets is None or buckets.n_parts != n_parts or buckets.part_cap < part_cap:
+        buckets = RecordBuckets(n_parts, part_cap, packed.pk2.device)
+    desc = PgTable(None, 2, None, mode, k)          # only mode and k are read by K2a
+    check(L.pg_kmer_partition(ctypes.byref(desc), _ptr(packed.pk2), _ptr(packed.amb), _ptr(packed.d_seq_off), n_rec,
+                              g_begin, g_end, owner_bits, sub_bits, _ptr(buckets.records), buckets.part_cap,
+                              _ptr(buckets.counts), _stream()), "pg_kmer_partition")
+    return buckets
+
+
+def sub_bits_for(capacity, sub_bytes=32 << 20):
+    """Enough hash-prefix buckets that one bucket's table region (capacity*16/2^bits bytes) fits L2."""
+    bits = 0
+    while (capacity * 16) >> bits > sub_bytes and bits < 10:
+        bits += 1
+    return bits
+
+
+def build_dbg_partitioned(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=None, sub_bytes=32 << 20, buckets=None,
+                          table=None):
+    """Two-phase build (K2a + K3).  Falls back to the fused kernel when a bucket overflows
+    (pathological hash skew, e.g. one k-mer making up most of the input)."""
+    k = int(min(max(1, k), 27))
+    if mode is None:
+        mode = _lib.PG_MODE_CANONICAL if rc else _lib.PG_MODE_LITERAL
+    n_rec = packed.record_prefix(Ns, 2 if rc else 1)
+    npos = packed.n_positions(k, n_rec)
+    per_pos = 2 if mode == _lib.PG_MODE_LITERAL_RC else 1
+    cap = next_pow2(max(1024, capacity or int(npos * per_pos / _DEFAULT_LOAD) + 1))
+    L = _lib.load()
+    for _ in range(6):
+        sub_bits = sub_bits_for(cap, sub_bytes)
+        if table is not None and table.capacity == cap and table.mode == mode and table.k == k:
+            t = table
+            t.clear()
+        else:
+            t = DbgTable(cap, k, mode, device=packed.pk2.device)
+        if n_rec == 0:
+            return t, n_rec, buckets
+        g_begin, g_end = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
+        check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
+        buckets = partition_kmers(packed, k, mode, n_rec, 0, sub_bits, buckets=buckets)
+        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(buckets.records), _ptr(buckets.seg_off), _ptr(buckets.counts),
+                                  buckets.n_parts, _stream()), "pg_insert_records")
+        worst = int(buckets.counts.max().item())           # synchronises
+        if worst > buckets.part_cap:
+            t2, n_rec = build_dbg(packed, k, rc=rc, Ns=Ns, mode=mode, capacity=cap)
+            return t2, n_rec, buckets
+        if not t.overflowed():
+            return t, n_rec, buckets
+        cap *= 2
+        table = None
+    raise PgError("dBG table kept overflowing up to capacity %d" % cap)

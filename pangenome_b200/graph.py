@@ -113,7 +113,7 @@ class RdbgGraph:
         d_n = torch.zeros(1, dtype=torch.int64, device=dev)
         check(self.L.pg_graph_export_nodes(ctypes.byref(self.c), ctypes.byref(rd.c), _ptr(nslot), _ptr(code), _ptr(v5),
                                            _ptr(root), nn, _ptr(d_n), _stream()), "pg_graph_export_nodes")
-        assert int(d_n.item()) == nn
+        nn = int(d_n.item())          # nodes that appear in at least one edge (<= inserted node slots)
         nslot = nslot[:nn].cpu().numpy().view(np.uint32)
         code = code[:nn].cpu().numpy().view(np.uint64)
         v5 = v5[:nn].cpu().numpy().view(np.uint32)
@@ -131,6 +131,7 @@ class RdbgGraph:
         return nslot, code, v5, label
 
     def set_labels(self, nslot, label):
+        """Upload one label per graph node; every other node slot gets -1 (never matches in K8)."""
         self.node_label.fill_(-1)
         if nslot.size:
             idx = torch.from_numpy(nslot.astype(np.int64)).to(self.node_label.device)
