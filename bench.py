@@ -5,8 +5,8 @@
                     [--workload cfg2|cfg3|small] [--k 27]
 
 One JSON line on stdout (rank 0).  A *step* is one full dBG build of the
-workload: table clear + FASTA scan/pack (K1) + fused k-mer extraction and
-hash-table insertion (K2/K3).  Metric = k-mer insertions / s, an insertion being
+workload: FASTA scan/pack (K1) + table clear + k-mer extraction into
+hash-partitioned update records (K2a) + record insertion (K3).  Metric = k-mer insertions / s, an insertion being
 one k-mer occurrence on one strand: 2 * sum max(n_r - k + 1, 1) over records
 (BASELINE.md section 3).
 
@@ -14,9 +14,9 @@ one k-mer occurrence on one strand: 2 * sum max(n_r - k + 1, 1) over records
            around exactly K steps, max over ranks.
  e2e     : the same build through the public host API with HOST buffers: pinned
            FASTA bytes -> H2D, build, D2H of the table statistics + checksum.
- roofline: the dominant kernel (k2_kmer_insert), timed live with CUDA events on
+ roofline: the dominant kernel (k3_insert_records), timed live with CUDA events on
            the launching stream; algorithmic bytes = 16 B per insertion
-            + 0.25 B per base read.
+           (SURVEY.md 8d).
  cpu_baseline: the reference's numba code (oracle/_ref, kind "reference") or,
            if that is unavailable, the C port (oracle/, kind "port"), one core,
            on a bounded sample of the same workload.
@@ -201,30 +201,24 @@ def main():
     d_fasta = host.to("cuda", non_blocking=True)
     torch.cuda.synchronize()
 
-    # one untimed build to size the table and know the unit count
+    # one untimed build to know the unit count; buffers (table + record buckets) stay resident across steps
     packed = engine.PackedSeqs(d_fasta)
     n_ins = packed.n_insertions(k)
-    table, n_rec = engine.build_dbg(packed, k)
+    n_rec = packed.record_prefix(2 ** 63, 2)
+    builder = engine.TwoPhaseBuilder(k, _lib.PG_MODE_CANONICAL, packed.n_positions(k))
+    table = builder.build(packed, n_rec)
+    torch.cuda.synchronize()
+    builder.verify()
     cap = table.capacity
     used, entries = table.count()
-    del table
     stream = torch.cuda.current_stream()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    ins_events = []
+    kev = {}
 
     def step_device(record=False):
         p = engine.PackedSeqs(d_fasta)                      # K1 (3 launches) + small D2H of the record index
-        t = engine.DbgTable(cap, k, _lib.PG_MODE_CANONICAL)  # clear (1 launch)
-        if record:
-            a, b = ev(), ev()
-            a.record(stream)
-            t.insert(p, n_rec)                              # count_short + k2_kmer_insert
-            b.record(stream)
-            ins_events.append((a, b))
-        else:
-            t.insert(p, n_rec)
-        return t
+        return builder.build(p, n_rec, ev=kev if record else None)   # clear, count_short, K2a, K3
 
     for _ in range(args.warmup):
         step_device()
@@ -240,37 +234,36 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize()
     clk = clocks.stop()
+    builder.verify()
     ms_total = e0.elapsed_time(e1)
     ms_step = ms_total / args.steps
-    if t.overflowed():
-        raise SystemExit("bench: table overflow inside the timed region")
     value = n_ins / (ms_step * 1e-3) / 1e9
-    ins_ms = sum(a.elapsed_time(b) for a, b in ins_events) / len(ins_events)
+    ins_ms = sum(a.elapsed_time(b) for a, b in kev["insert"]) / len(kev["insert"])
+    part_ms = sum(a.elapsed_time(b) for a, b in kev["partition"]) / len(kev["partition"])
 
-    # end to end through the public API, host buffers
+    # end to end through the public API, host buffers: H2D of the FASTA bytes, build, D2H of the table statistics
     def step_e2e():
         d = host.to("cuda", non_blocking=True)
         p = engine.PackedSeqs(d)
-        tt = engine.DbgTable(cap, k, _lib.PG_MODE_CANONICAL)
-        tt.insert(p, n_rec)
-        st = tt.stats_host()
-        cs = tt.checksum()
-        return st, cs
+        tt = builder.build(p, n_rec)
+        return tt.count()            # (occupied slots, dBG entries) - synchronises
     for _ in range(2):
         step_e2e()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
     g0, g1 = ev(), ev()
     g0.record(stream)
     for _ in range(args.steps):
-        st, cs = step_e2e()
+        st = step_e2e()
     g1.record(stream)
     torch.cuda.synchronize()
+    builder.verify()
     e2e_ms = g0.elapsed_time(g1) / args.steps
     e2e_val = n_ins / (e2e_ms * 1e-3) / 1e9
+    cs = t.checksum()
 
     peak, peak_src = peaks()
-    alg_bytes = 16.0 * n_ins + 0.25 * packed.n_bases
+    alg_bytes = 16.0 * n_ins
+    part_bytes = 0.25 * packed.n_bases + 16.0 * packed.n_positions(k)
     achieved = alg_bytes / (ins_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "insert_traffic.json")
@@ -288,14 +281,17 @@ def main():
                    "table_slots": cap, "table_bytes": cap * 16, "distinct_canonical_keys": used,
                    "l2": "every step clears and randomly updates the %.1f GB table (> 126 MB L2), which evicts the input" % (cap * 16 / 1e9)},
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host.numel()),
-                "d2h_bytes_per_step": int(8 * 8 + 3 * 8 + 4 * 8 + 16 * (packed.n_rec + 1))},
-        "gpu_launches": 6 * args.steps,
+                "d2h_bytes_per_step": int(8 * 8 + 4 * 8 + 16 * (packed.n_rec + 1))},
+        "gpu_launches": (3 + builder.launches_per_build) * args.steps,
         "clocks": clk,
-        "roofline": {"kernel": "k2_kmer_insert<canonical>", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": "k3_insert_records", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "ms_per_launch": ins_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                     "convention": "16 B per insertion + 0.25 B per base (SURVEY 8d)",
-                     "frac_64B_sector_convention": (64.0 * n_ins / 2 / (ins_ms * 1e-3) / 1e9) / peak},
+                     "convention": "insert: 16 B per insertion (SURVEY 8d), 2 insertions per record",
+                     "other_kernels": {"k2a_partition": {"ms_per_launch": part_ms, "algorithmic_bytes_per_launch": part_bytes,
+                                                         "achieved": part_bytes / (part_ms * 1e-3) / 1e9,
+                                                         "frac": part_bytes / (part_ms * 1e-3) / 1e9 / peak,
+                                                         "convention": "0.25 B/base read + 16 B/record written (materialised for the exchange)"}}},
         "checksum": list(cs),
     }
     if not args.no_cpu_baseline:

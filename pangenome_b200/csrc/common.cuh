@@ -93,6 +93,30 @@ __device__ __forceinline__ uint4 pg_ld_stream(const uint4 *p) {
 __device__ __forceinline__ void pg_ld_slot(const uint64_t *p, uint64_t &key, uint64_t &val) {
     asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(key), "=l"(val) : "l"(p));
 }
+// read-once streams (update records): keep them from displacing the table region in L2
+__device__ __forceinline__ uint64_t pg_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 pg_ld_stream_l2first(const uint4 *p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void pg_st_stream_l2first(uint4 *p, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+// 128-bit compare-and-swap of a whole slot {key, value}: claims an empty slot and deposits the first
+// occurrence's masks + count in ONE L2 transaction (instead of CAS + red.or + red.add)
+__device__ __forceinline__ void pg_cas128(uint64_t *p, uint64_t cmp_lo, uint64_t cmp_hi, uint64_t new_lo, uint64_t new_hi,
+                                          uint64_t &old_lo, uint64_t &old_hi) {
+    asm volatile("{\n\t.reg .b128 c, s, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\t"
+                 "atom.global.cas.b128 d, [%6], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                 : "=l"(old_lo), "=l"(old_hi) : "l"(cmp_lo), "l"(cmp_hi), "l"(new_lo), "l"(new_hi), "l"(p) : "memory");
+}
 __device__ __forceinline__ void pg_red_or32(uint32_t *p, uint32_t v) {
     asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

@@ -31,32 +31,6 @@ __device__ __forceinline__ Sum3 shfl_up_sum3(const Sum3 &x, int o) {
     return y;
 }
 
-// Ordered block scan of Sum3 (non-commutative).  Returns the exclusive prefix of this thread and
-// the block total.  s_warp must hold K1_THREADS/32 Sum3.
-__device__ __forceinline__ void block_scan_sum3(const Sum3 &mine, Sum3 *s_warp, Sum3 &excl, Sum3 &total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Sum3 inc = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        Sum3 y = shfl_up_sum3(inc, o);
-        if (lane >= o) inc = sum3_compose(y, inc);
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    Sum3 wp = sum3_identity();
-    Sum3 tot = sum3_identity();
-#pragma unroll
-    for (int w = 0; w < K1_THREADS / 32; w++) {
-        Sum3 t = s_warp[w];
-        if (w < warp) wp = sum3_compose(wp, t);
-        tot = sum3_compose(tot, t);
-    }
-    Sum3 prev = shfl_up_sum3(inc, 1);
-    excl = (lane == 0) ? wp : sum3_compose(wp, prev);
-    total = tot;
-    __syncthreads();
-}
-
 __device__ __forceinline__ ChunkCls load_classify(const uint8_t *fasta, int64_t nbytes, int64_t off) {
     uint32_t w[4] = {0, 0, 0, 0};
     int64_t left = nbytes - off;
@@ -75,27 +49,84 @@ __device__ __forceinline__ ChunkCls load_classify(const uint8_t *fasta, int64_t 
     return classify16(w, n_file, left <= 16);
 }
 
+// Ordered scan of the K1_NSUB x K1_THREADS chunk summaries of one tile (non-commutative compose).
+// Chunk (c, t) covers bytes [(c * K1_THREADS + t) * 16, +16) of the tile, so every load instruction is
+// perfectly coalesced and the four loads of a thread are in flight together.  One warp-shuffle scan per
+// c, then warp 0 scans the 32 (c, warp) aggregates.  excl[c] = everything before chunk (c, t).
+__device__ __forceinline__ void tile_scan4(const Sum3 mine[K1_NSUB], Sum3 *s_agg /* K1_NSUB*8 */, Sum3 excl[K1_NSUB], Sum3 &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Sum3 inc[K1_NSUB];
+#pragma unroll
+    for (int c = 0; c < K1_NSUB; c++) {
+        inc[c] = mine[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            Sum3 y = shfl_up_sum3(inc[c], o);
+            if (lane >= o) inc[c] = sum3_compose(y, inc[c]);
+        }
+        if (lane == 31) s_agg[c * (K1_THREADS / 32) + warp] = inc[c];
+    }
+    __syncthreads();
+    if (warp == 0) {   // 32 aggregates in (c, warp) order -> exclusive prefixes, total in slot 32
+        Sum3 a = s_agg[lane], ainc = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            Sum3 y = shfl_up_sum3(ainc, o);
+            if (lane >= o) ainc = sum3_compose(y, ainc);
+        }
+        Sum3 prev = shfl_up_sum3(ainc, 1);
+        __syncwarp();
+        s_agg[lane] = lane == 0 ? sum3_identity() : prev;
+        if (lane == 31) s_agg[32] = ainc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < K1_NSUB; c++) {
+        Sum3 wp = s_agg[c * (K1_THREADS / 32) + warp];
+        Sum3 prev = shfl_up_sum3(inc[c], 1);
+        excl[c] = (lane == 0) ? wp : sum3_compose(wp, prev);
+    }
+    total = s_agg[32];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void load_classify4(const uint8_t *fasta, int64_t nbytes, int64_t tile_off, ChunkCls c[K1_NSUB]) {
+    uint4 v[K1_NSUB];
+    const bool full = tile_off + K1_TILE <= nbytes;
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++)
+            v[i] = pg_ld_stream(reinterpret_cast<const uint4 *>(fasta + tile_off + ((int64_t)i * K1_THREADS + threadIdx.x) * 16));
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++) {
+            uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            int64_t left = nbytes - (tile_off + ((int64_t)i * K1_THREADS + threadIdx.x) * 16);
+            c[i] = classify16(w, 16, left <= 16);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++) c[i] = load_classify(fasta, nbytes, tile_off + ((int64_t)i * K1_THREADS + threadIdx.x) * 16);
+    }
+}
+
 __global__ void __launch_bounds__(K1_THREADS)
 k1_tile_summaries(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles, TileSum *__restrict__ sums) {
-    __shared__ Sum3 s_warp[K1_THREADS / 32];
+    __shared__ Sum3 s_agg[K1_NSUB * (K1_THREADS / 32) + 1];
     __shared__ uint32_t s_nl;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         if (threadIdx.x == 0) s_nl = 0;
-        Sum3 carry = sum3_identity();
+        ChunkCls c[K1_NSUB];
+        load_classify4(fasta, nbytes, tile * K1_TILE, c);
+        Sum3 mine[K1_NSUB], excl[K1_NSUB], total;
         uint32_t my_nl = 0;
-        for (int sub = 0; sub < K1_NSUB; sub++) {
-            int64_t off = tile * K1_TILE + (int64_t)sub * K1_SUB + threadIdx.x * 16;
-            ChunkCls c = load_classify(fasta, nbytes, off);
-            my_nl += c.real_nl;
-            Sum3 excl, total;
-            block_scan_sum3(chunk_sum3(c), s_warp, excl, total);
-            carry = sum3_compose(carry, total);
-        }
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++) { mine[i] = chunk_sum3(c[i]); my_nl += c[i].real_nl; }
+        tile_scan4(mine, s_agg, excl, total);
         my_nl = __reduce_add_sync(0xffffffffu, my_nl);
         if ((threadIdx.x & 31) == 0 && my_nl) atomicAdd(&s_nl, my_nl);
         __syncthreads();
         if (threadIdx.x == 0) {
-            TileSum t; t.v[0] = carry.v[0]; t.v[1] = carry.v[1]; t.v[2] = carry.v[2]; t.real_nl = s_nl;
+            TileSum t; t.v[0] = total.v[0]; t.v[1] = total.v[1]; t.v[2] = total.v[2]; t.real_nl = s_nl;
             sums[tile] = t;
         }
         __syncthreads();
@@ -173,29 +204,31 @@ __global__ void __launch_bounds__(K1_THREADS)
 k1_tile_pack(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles,
              const TileEntry *__restrict__ entries, uint32_t *__restrict__ pk2, uint32_t *__restrict__ amb,
              int64_t *__restrict__ hdr_off, int64_t *__restrict__ seq_off, int64_t cap_records) {
-    __shared__ Sum3 s_warp[K1_THREADS / 32];
+    __shared__ Sum3 s_agg[K1_NSUB * (K1_THREADS / 32) + 1];
     __shared__ uint32_t s_pk[K1_PKW];
     __shared__ uint32_t s_am[K1_AMW];
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         TileEntry e = entries[tile];
         if (e.dead) return;
+        ChunkCls c[K1_NSUB];
+        load_classify4(fasta, nbytes, tile * K1_TILE, c);          // loads in flight while the staging is cleared
         for (int i = threadIdx.x; i < K1_PKW; i += K1_THREADS) s_pk[i] = 0;
         for (int i = threadIdx.x; i < K1_AMW; i += K1_THREADS) s_am[i] = 0;
-        __syncthreads();
+        Sum3 mine[K1_NSUB], excl[K1_NSUB], total;
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++) mine[i] = chunk_sum3(c[i]);
+        tile_scan4(mine, s_agg, excl, total);                      // contains the barrier that publishes the zeroed staging
         const uint32_t a0 = (uint32_t)(e.seq & 31);
-        uint32_t cstate = e.state, cseq = 0, chdr = 0;
-        for (int sub = 0; sub < K1_NSUB; sub++) {
-            int64_t off = tile * K1_TILE + (int64_t)sub * K1_SUB + threadIdx.x * 16;
-            ChunkCls c = load_classify(fasta, nbytes, off);
-            Sum3 excl, total;
-            block_scan_sum3(chunk_sum3(c), s_warp, excl, total);
-            uint32_t x = sum3_sel(excl, cstate);
-            ChunkRun r = chunk_run(c, SV_STATE(x));
-            uint32_t rank = cseq + SV_SEQ(x);          // bases of this tile before my chunk
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++) {
+            const int64_t off = tile * K1_TILE + ((int64_t)i * K1_THREADS + threadIdx.x) * 16;
+            uint32_t x = sum3_sel(excl[i], e.state);
+            ChunkRun r = chunk_run(c[i], SV_STATE(x));
+            uint32_t rank = SV_SEQ(x);                 // bases of this tile before my chunk
             uint32_t cnt = pg_popc(r.seqmask);
             if (cnt) {
-                uint32_t d = pext16_2bit(c.dig, r.seqmask);
-                uint32_t m = pext16_1bit(c.amb, r.seqmask);
+                uint32_t d = pext16_2bit(c[i].dig, r.seqmask);
+                uint32_t m = pext16_1bit(c[i].amb, r.seqmask);
                 if (cnt < 16) d &= (1u << (2 * cnt)) - 1u;
                 uint32_t q = a0 + rank;
                 uint32_t sh = 2 * (q & 15);
@@ -208,7 +241,7 @@ k1_tile_pack(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles,
                 }
             }
             if (r.hs) {   // rare: this chunk starts record(s)
-                uint32_t hs = r.hs; uint64_t idx = e.hdr + chdr + SV_HDR(x);
+                uint32_t hs = r.hs; uint64_t idx = e.hdr + SV_HDR(x);
                 while (hs) {
                     int j = pg_ctz(hs); hs &= hs - 1;
                     if ((int64_t)idx < cap_records) {
@@ -218,9 +251,8 @@ k1_tile_pack(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles,
                     idx++;
                 }
             }
-            uint32_t tt = sum3_sel(total, cstate);
-            cstate = SV_STATE(tt); cseq += SV_SEQ(tt); chdr += SV_HDR(tt);
         }
+        const uint32_t cseq = SV_SEQ(sum3_sel(total, e.state));
         __syncthreads();
         // write-out: words fully owned by this tile are stored, shared boundary words are OR-ed
         const uint32_t end = a0 + cseq;

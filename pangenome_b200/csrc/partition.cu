@@ -13,6 +13,7 @@
 // Record emission inside a CTA tile is a counting sort in shared memory (histogram, one global
 // atomicAdd per bucket per tile to reserve space, reorder through an index permutation) so global
 // stores are coalesced 16-byte runs per bucket.
+#include <stdlib.h>
 #include "table_dev.cuh"
 
 namespace {
@@ -38,27 +39,51 @@ __device__ __forceinline__ uint32_t part_of(const PartArgs &a, uint64_t key) {
     return (owner << a.sub_bits) | sub;
 }
 
+// 4-entry lastc tables for ACGT digits (A0 G1 C2 T3): forward A1 G4 C8 T2, complemented T2 C8 G4 A1
+__device__ __forceinline__ uint32_t lastc4_f(uint32_t d) { return (0x02080401u >> (8 * d)) & 0xffu; }
+__device__ __forceinline__ uint32_t lastc4_r(uint32_t d) { return (0x01040802u >> (8 * d)) & 0xffu; }
+
 template <int MODE>
 __global__ void __launch_bounds__(KP_THREADS)
 k2a_partition(PartArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int MAXR = (MODE == PG_MODE_LITERAL_RC) ? KP_MAX_REC : KP_TILE;
+    constexpr int RPP = (MODE == PG_MODE_LITERAL_RC) ? 2 : 1;               // records per position
+    constexpr int MAXR = KP_TILE * RPP;
+    constexpr uint16_t NOREC = 0xFFFFu;
     uint4 *s_rec = reinterpret_cast<uint4 *>(smem);                          // MAXR records, natural order
-    uint16_t *s_pid = reinterpret_cast<uint16_t *>(s_rec + MAXR);            // MAXR bucket ids
+    uint16_t *s_pid = reinterpret_cast<uint16_t *>(s_rec + MAXR);            // MAXR bucket ids (NOREC = slot unused)
     uint16_t *s_perm = s_pid + MAXR;                                         // sorted index -> natural index
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_perm + MAXR);          // n_parts
     uint32_t *s_off = s_hist + a.n_parts;                                    // n_parts: exclusive offsets
     uint32_t *s_tick = s_off + a.n_parts;                                    // n_parts: tickets
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_tick + a.n_parts + (a.n_parts & 1));
     __shared__ uint32_t s_nrec;
+    const uint64_t pol = pg_policy_evict_first();
+
+    auto emit = [&](int slot, uint64_t key, uint32_t masks, uint32_t inc) {
+        uint32_t pid = part_of(a, key);
+        s_rec[slot] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), masks, inc);
+        s_pid[slot] = (uint16_t)pid;
+        atomicAdd(&s_hist[pid], 1u);
+    };
+    auto emit_pos = [&](int q, uint64_t F, uint64_t R, uint32_t vf, uint32_t vr) {
+        const int slot = (threadIdx.x * KP_G + q) * RPP;
+        if (MODE == PG_MODE_CANONICAL) {
+            PgUpdate u = pg_canonical_update(F, R, vf, vr);
+            emit(slot, u.key, u.masks, u.inc);
+        } else {
+            emit(slot, F, vf, 1u);
+            if (MODE == PG_MODE_LITERAL_RC) emit(slot + 1, R, vr, 1u);
+        }
+    };
 
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         __syncthreads();
         for (int i = threadIdx.x; i < a.n_parts; i += KP_THREADS) { s_hist[i] = 0; s_tick[i] = 0; }
-        if (threadIdx.x == 0) s_nrec = 0;
         __syncthreads();
         // ---- 1. compute this thread's records ------------------------------------------------
         const int64_t g0 = (a.t_first + tile) * KP_TILE + (int64_t)threadIdx.x * KP_G;
+        bool done = false;
         if (g0 < a.g_end && g0 + KP_G > a.g_begin) {
             const int64_t wi = g0 >> 5;
             const int j0 = (int)(g0 & 31);
@@ -67,42 +92,62 @@ k2a_partition(PartArgs a) {
             w.aprv = wi > 0 ? __ldg(a.amb + wi - 1) : 0; w.acur = __ldg(a.amb + wi); w.anxt = wi + 1 < a.n_words ? __ldg(a.amb + wi + 1) : 0;
             int64_t r = find_record(a.seq_off, a.n_rec, g0);
             int64_t rs = r >= 0 ? __ldg(a.seq_off + r) : 0, re = __ldg(a.seq_off + r + 1);
-            uint64_t F, R;
-            pg_codes_init(w, j0, a.k, F, R);
-#pragma unroll 1
-            for (int q = 0; q < KP_G; q++) {
-                const int64_t g = g0 + q;
-                const int j = j0 + q;
-                if (g >= a.g_end) break;
-                while (r + 1 < a.n_rec && g >= re) { r++; rs = re; re = __ldg(a.seq_off + r + 1); }
-                if (g >= a.g_begin && r >= 0 && g + a.k <= re) {
-                    uint32_t vf, vr;
-                    pg_occ_vals(w, j, g - rs, re - rs, a.k, vf, vr);
-                    if (MODE == PG_MODE_CANONICAL) {
-                        PgUpdate u = pg_canonical_update(F, R, vf, vr);
-                        uint32_t pid = part_of(a, u.key);
-                        uint32_t at = atomicAdd(&s_nrec, 1u);
-                        s_rec[at] = make_uint4((uint32_t)u.key, (uint32_t)(u.key >> 32), u.masks, u.inc);
-                        s_pid[at] = (uint16_t)pid; atomicAdd(&s_hist[pid], 1u);
-                    } else {
-                        uint32_t pid = part_of(a, F);
-                        uint32_t at = atomicAdd(&s_nrec, 1u);
-                        s_rec[at] = make_uint4((uint32_t)F, (uint32_t)(F >> 32), vf, 1u);
-                        s_pid[at] = (uint16_t)pid; atomicAdd(&s_hist[pid], 1u);
-                        if (MODE == PG_MODE_LITERAL_RC) {
-                            pid = part_of(a, R);
-                            at = atomicAdd(&s_nrec, 1u);
-                            s_rec[at] = make_uint4((uint32_t)R, (uint32_t)(R >> 32), vr, 1u);
-                            s_pid[at] = (uint16_t)pid; atomicAdd(&s_hist[pid], 1u);
-                        }
-                    }
+            const int k = a.k;
+            const bool interior = !w.any_amb() && r >= 0 && g0 - 2 >= rs && g0 + KP_G + k + 1 <= re &&
+                                  g0 >= a.g_begin && g0 + KP_G <= a.g_end;
+            if (interior) {
+                // ---- fast path: 16 ACGT positions strictly inside one record.  prev / next are plain
+                // neighbours (no '#', '$', Q1 or ambiguity), every digit is a constant-shift field.
+                // 64-bit views starting at base j0-1, j0 and j0+k (only their low 32 bits are needed)
+                const uint64_t v0 = j0 ? ((w.cur >> (2 * j0)) | (w.nxt << (64 - 2 * j0))) : w.cur;           // bases j0 ..
+                const uint64_t v1 = j0 ? (w.nxt >> (2 * j0)) : w.nxt;                                        // bases j0+32 ..
+                const uint32_t dprev_w = (uint32_t)((v0 << 2) | ((j0 ? (w.cur >> (2 * j0 - 2)) : (w.prv >> 62)) & 3u));   // bases j0-1 ..
+                const uint32_t dout_w = (uint32_t)v0;
+                const uint32_t din_w = (uint32_t)((v0 >> (2 * k)) | (v1 << (64 - 2 * k)));                   // bases j0+k ..
+                uint64_t F = 0, R = 0, p5 = 1;
+                for (int i = 0; i < k; i++) {
+                    uint32_t d = (uint32_t)(v0 >> (2 * i)) & 3u;
+                    F += (uint64_t)d * p5; R = R * 5 + (3u - d); p5 *= 5;
                 }
-                pg_codes_roll(w, j, a.k, a.pow5km1, F, R);
+                p5 = a.pow5km1;
+#pragma unroll
+                for (int q = 0; q < KP_G; q++) {
+                    const uint32_t dp = (dprev_w >> (2 * q)) & 3u, dout = (dout_w >> (2 * q)) & 3u, din = (din_w >> (2 * q)) & 3u;
+                    const uint32_t vf = (lastc4_f(dp) << 6) | lastc4_f(din);
+                    const uint32_t vr = (lastc4_r(din) << 6) | lastc4_r(dp);
+                    emit_pos(q, F, R, vf, vr);
+                    F = (F - dout) * PG_INV5 + (uint64_t)din * p5;
+                    R = (R - (uint64_t)(3u - dout) * p5) * 5 + (3u - din);
+                }
+                done = true;
+            } else {
+                // ---- generic path: record edges, ambiguity codes, range ends (all the quirks) ----
+                uint64_t F, R;
+                pg_codes_init(w, j0, k, F, R);
+#pragma unroll 1
+                for (int q = 0; q < KP_G; q++) {
+                    const int64_t g = g0 + q;
+                    const int j = j0 + q;
+                    bool ok = false;
+                    if (g < a.g_end) {
+                        while (r + 1 < a.n_rec && g >= re) { r++; rs = re; re = __ldg(a.seq_off + r + 1); }
+                        ok = g >= a.g_begin && r >= 0 && g + k <= re;
+                    }
+                    if (ok) {
+                        uint32_t vf, vr;
+                        pg_occ_vals(w, j, g - rs, re - rs, k, vf, vr);
+                        emit_pos(q, F, R, vf, vr);
+                    } else {
+                        for (int e = 0; e < RPP; e++) s_pid[(threadIdx.x * KP_G + q) * RPP + e] = NOREC;
+                    }
+                    pg_codes_roll(w, j, k, a.pow5km1, F, R);
+                }
+                done = true;
             }
         }
+        if (!done)
+            for (int e = 0; e < KP_G * RPP; e++) s_pid[threadIdx.x * KP_G * RPP + e] = NOREC;
         __syncthreads();
-        const uint32_t nrec = s_nrec;
-        if (nrec == 0) continue;
         // ---- 2. reserve space: one global atomicAdd per bucket per tile; local exclusive offsets ----
         if (threadIdx.x < 32) {     // warp 0 scans the histogram in chunks of 32
             uint32_t carry = 0;
@@ -116,11 +161,15 @@ k2a_partition(PartArgs a) {
                 }
                 carry += __shfl_sync(0xffffffffu, inc, 31);
             }
+            if (threadIdx.x == 0) s_nrec = carry;
         }
         __syncthreads();
+        const uint32_t nrec = s_nrec;
+        if (nrec == 0) continue;
         // ---- 3. permutation: sorted position -> natural index ------------------------------------
-        for (uint32_t i = threadIdx.x; i < nrec; i += KP_THREADS) {
+        for (uint32_t i = threadIdx.x; i < (uint32_t)MAXR; i += KP_THREADS) {
             uint32_t pid = s_pid[i];
+            if (pid == NOREC) continue;
             uint32_t o = s_off[pid] + atomicAdd(&s_tick[pid], 1u);
             s_perm[o] = (uint16_t)i;
         }
@@ -130,24 +179,38 @@ k2a_partition(PartArgs a) {
             uint32_t i = s_perm[o];
             uint32_t pid = s_pid[i];
             unsigned long long dst = s_base[pid] + (o - s_off[pid]);
-            if ((int64_t)dst < a.part_cap) a.records[(int64_t)pid * a.part_cap + (int64_t)dst] = s_rec[i];
+            if ((int64_t)dst < a.part_cap) pg_st_stream_l2first(a.records + (int64_t)pid * a.part_cap + (int64_t)dst, s_rec[i], pol);
         }
     }
 }
 
 // K3: insert the records of a list of segments, in list order (the grid sweeps the segments together,
-// so the table region under update stays L2-resident).
+// so the table region under update stays L2-resident).  Four records per thread are in flight at a
+// time: record loads (evict-first in L2), then the four home-slot loads, then the atomics.
+template <int K3_ILP, bool EVICT>
 __global__ void __launch_bounds__(256)
 k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
                   const int64_t *__restrict__ seg_cnt, int n_seg) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const uint64_t pol = pg_policy_evict_first();
     for (int s = 0; s < n_seg; s++) {
         const int64_t off = __ldg(seg_off + s), cnt = __ldg(seg_cnt + s);
-        for (int64_t i = i0; i < cnt; i += stride) {
-            uint4 r = pg_ld_stream(records + off + i);
-            uint64_t key = (uint64_t)r.x | ((uint64_t)r.y << 32);
-            table_upsert(t, key, r.z, r.w);
+        for (int64_t i = i0; i < cnt; i += stride * K3_ILP) {
+            uint4 r[K3_ILP]; uint64_t home[K3_ILP], ck[K3_ILP], cv[K3_ILP];
+#pragma unroll
+            for (int u = 0; u < K3_ILP; u++)
+                if (i + u * stride < cnt) r[u] = EVICT ? pg_ld_stream_l2first(records + off + i + u * stride, pol) : pg_ld_stream(records + off + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < K3_ILP; u++)
+                if (i + u * stride < cnt) {
+                    home[u] = tv_home(t, (uint64_t)r[u].x | ((uint64_t)r[u].y << 32));
+                    pg_ld_slot(t.slots + 2 * home[u], ck[u], cv[u]);
+                }
+#pragma unroll
+            for (int u = 0; u < K3_ILP; u++)
+                if (i + u * stride < cnt)
+                    table_upsert_from(t, home[u], ck[u], cv[u], (uint64_t)r[u].x | ((uint64_t)r[u].y << 32), r[u].z, r[u].w);
         }
     }
 }
@@ -206,8 +269,20 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
     if (n_seg == 0) return PG_OK;
     if (reinterpret_cast<uintptr_t>(d_records) & 15) return pg_fail(PG_ERR_INVALID, "pg_insert_records: records must be 16-byte aligned");
     TableView tv = make_view(t);
-    int grid = pg_num_sms() * 8;
-    k3_insert_records<<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_seg);
+    static int ilp = -1, evict = -1, gmul = -1;
+    if (ilp < 0) {
+        const char *e = getenv("PG_K3_ILP"); ilp = e ? atoi(e) : 4;
+        e = getenv("PG_K3_EVICT"); evict = e ? atoi(e) : 1;
+        e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 8;
+    }
+    int grid = pg_num_sms() * gmul;
+    const uint4 *rec = reinterpret_cast<const uint4 *>(d_records);
+    cudaStream_t st = (cudaStream_t)stream_;
+#define K3_LAUNCH(I, E) k3_insert_records<I, E><<<grid, 256, 0, st>>>(tv, rec, d_seg_off, d_seg_cnt, n_seg)
+    if (ilp == 1) { if (evict) K3_LAUNCH(1, true); else K3_LAUNCH(1, false); }
+    else if (ilp == 2) { if (evict) K3_LAUNCH(2, true); else K3_LAUNCH(2, false); }
+    else { if (evict) K3_LAUNCH(4, true); else K3_LAUNCH(4, false); }
+#undef K3_LAUNCH
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

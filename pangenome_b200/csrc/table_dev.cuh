@@ -17,29 +17,34 @@ inline TableView make_view(const pg_table *t) {
     return TableView{t->d_slots, (uint64_t)t->capacity - 1, t->d_stats, 64 - bits};
 }
 
+// Merge one update into a slot whose key already matches; cv = the value word last seen.
+__device__ __forceinline__ void slot_merge(uint64_t *p, uint64_t cv, uint32_t masks, uint32_t inc) {
+    uint32_t *v = reinterpret_cast<uint32_t *>(p + 1);
+    if (((uint32_t)cv & masks) != masks) pg_red_or32(v, masks);
+    if ((uint32_t)(cv >> 32) < 255u) pg_red_add32(v + 1, inc);       // counts clamp at 255 upstream (:551)
+}
+// Continue an upsert from slot s whose contents (ck, cv) were already loaded.
 // returns the slot index the key lives in (claimed if absent), or -1 when probing gives up
-__device__ __forceinline__ int64_t table_upsert(const TableView &t, uint64_t key, uint32_t masks, uint32_t inc) {
-    uint64_t s = tv_home(t, key);
+__device__ __forceinline__ int64_t table_upsert_from(const TableView &t, uint64_t s, uint64_t ck, uint64_t cv, uint64_t key,
+                                                     uint32_t masks, uint32_t inc) {
     for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
         uint64_t *p = t.slots + 2 * s;
-        uint64_t ck, cv;
-        pg_ld_slot(p, ck, cv);
+        if (probe) pg_ld_slot(p, ck, cv);
         if (ck == PG_EMPTY) {
-            uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)PG_EMPTY,
-                                     (unsigned long long)key);
-            ck = (old == PG_EMPTY) ? key : old;
-            cv = 0;
+            // empty slots always hold {EMPTY, 0}: claim key + first masks + first count at once
+            pg_cas128(p, PG_EMPTY, 0ull, key, (uint64_t)masks | ((uint64_t)inc << 32), ck, cv);
+            if (ck == PG_EMPTY) return (int64_t)s;
         }
-        if (ck == key) {
-            uint32_t *v = reinterpret_cast<uint32_t *>(p + 1);
-            if (((uint32_t)cv & masks) != masks) pg_red_or32(v, masks);
-            if ((uint32_t)(cv >> 32) < 255u) pg_red_add32(v + 1, inc);
-            return (int64_t)s;
-        }
+        if (ck == key) { slot_merge(p, cv, masks, inc); return (int64_t)s; }
         s = (s + 1) & t.capmask;
     }
     atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
     return -1;
+}
+__device__ __forceinline__ int64_t table_upsert(const TableView &t, uint64_t key, uint32_t masks, uint32_t inc) {
+    uint64_t s = tv_home(t, key), ck, cv;
+    pg_ld_slot(t.slots + 2 * s, ck, cv);
+    return table_upsert_from(t, s, ck, cv, key, masks, inc);
 }
 
 // largest r in [-1, n_rec) with seq_off[r] <= g   (r = -1: g precedes the first record)
