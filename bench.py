@@ -193,7 +193,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world > 1:
         from pangenome_b200 import multigpu
-        return multigpu.bench(args, world, rank, local)
+        return multigpu.bench(args, world, rank, local, ClockSampler)
 
     data, wl = workload(args.workload)
     k = args.k
@@ -211,6 +211,11 @@ def main():
     builder.verify()
     cap = table.capacity
     used, entries = table.count()
+    ref_table, _ = engine.build_dbg(packed, k)              # the fused single-launch path must agree
+    ref_sum = ref_table.checksum()
+    if used == 0 or table.checksum() != ref_sum:
+        raise SystemExit("bench: two-phase build disagrees with the fused build")
+    del ref_table
     stream = torch.cuda.current_stream()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -260,6 +265,8 @@ def main():
     e2e_ms = g0.elapsed_time(g1) / args.steps
     e2e_val = n_ins / (e2e_ms * 1e-3) / 1e9
     cs = t.checksum()
+    if cs != ref_sum:
+        raise SystemExit("bench: table built inside the timed region has the wrong checksum")
 
     peak, peak_src = peaks()
     alg_bytes = 16.0 * n_ins

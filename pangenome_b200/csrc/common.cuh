@@ -40,11 +40,30 @@ PG_HD uint64_t pg_pow5(int e) {
 // complement digit: A0<->T3, G1<->C2, other 4 -> 4 (reverse_jit_ maps every non-ACGT byte to N)
 PG_HD uint32_t pg_cdig(uint32_t d) { return d == 4 ? 4u : 3u - d; }
 
-// reverse-complement of a base-5 code (the key the rc strand inserts for the same window)
+// reverse-complement of a base-5 code (the key the rc strand inserts for the same window).
+// The code is split into 9-digit limbs (5^9 < 2^21) so the digit loop runs in 32-bit arithmetic.
 PG_HD uint64_t pg_rc_code(uint64_t code, int k) {
+    const uint32_t P9 = 1953125u;                       // 5^9
+    uint32_t limb[3];
+    limb[0] = (uint32_t)(code % P9); code /= P9;
+    limb[1] = (uint32_t)(code % P9); code /= P9;
+    limb[2] = (uint32_t)code;                            // < 5^9 for k <= 27
     uint64_t r = 0;
-    for (int i = 0; i < k; i++) { r = r * 5 + pg_cdig((uint32_t)(code % 5)); code /= 5; }
+    int left = k;
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+        uint32_t x = limb[l];
+        int n = left < 9 ? left : 9;
+        for (int i = 0; i < n; i++) { uint32_t d = x % 5u; x /= 5u; r = r * 5 + pg_cdig(d); }
+        left -= n;
+    }
     return r;
+}
+// can the code be its own reverse complement?  Only if the middle digit of an odd-k code is the
+// ambiguity digit 4 (cdig(d) == d only for d == 4); for even k any code might be.
+PG_HD bool pg_maybe_palindrome(uint64_t code, int k, uint64_t pow5_mid) {
+    if ((k & 1) == 0) return true;
+    return (code / pow5_mid) % 5 == 4;
 }
 
 // ---- symbols: 0..3 = A G C T (base-5 digit), 4 = N/n, 5 = any other byte ------------

@@ -79,13 +79,14 @@ __global__ void k_table_clear(uint4 *slots, int64_t n_slots, int64_t *stats) {
 }
 
 // ---- read-out ----------------------------------------------------------------------------------
-__global__ void k_table_count(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k, int64_t *stats) {
+__global__ void k_table_count(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k, uint64_t pow5_mid, int64_t *stats) {
     unsigned long long used = 0, ents = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t key, v; pg_ld_slot(slots + 2 * i, key, v);
-        PgEntry e[2];
-        int n = pg_slot_entries(key, v, mode, k, e);
-        used += n > 0; ents += n;
+        uint64_t key = slots[2 * i];                       // streaming 8 of every 16 bytes; the value word is not needed
+        if (key == PG_EMPTY) continue;
+        int n = 1;
+        if (mode == PG_MODE_CANONICAL) n = (pg_maybe_palindrome(key, k, pow5_mid) && pg_rc_code(key, k) == key) ? 1 : 2;
+        used += 1; ents += n;
     }
     for (int o = 16; o; o >>= 1) { used += __shfl_down_sync(0xffffffffu, used, o); ents += __shfl_down_sync(0xffffffffu, ents, o); }
     if ((threadIdx.x & 31) == 0) {
@@ -282,7 +283,7 @@ extern "C" int pg_table_count(const pg_table *t, pg_stream_t stream_) {
     int rc = check_table(t, "pg_table_count"); if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(t->d_stats + PG_STAT_USED, 0, 2 * sizeof(int64_t), stream));
-    k_table_count<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(t->d_slots, t->capacity, t->mode, t->k, t->d_stats);
+    k_table_count<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(t->d_slots, t->capacity, t->mode, t->k, pg_pow5(t->k / 2), t->d_stats);
     k_count_finish<<<1, 1, 0, stream>>>(t->d_stats);
     PG_CUDA(cudaGetLastError());
     return PG_OK;

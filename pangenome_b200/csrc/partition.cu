@@ -271,8 +271,8 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
     TableView tv = make_view(t);
     static int ilp = -1, evict = -1, gmul = -1;
     if (ilp < 0) {
-        const char *e = getenv("PG_K3_ILP"); ilp = e ? atoi(e) : 4;
-        e = getenv("PG_K3_EVICT"); evict = e ? atoi(e) : 1;
+        const char *e = getenv("PG_K3_ILP"); ilp = e ? atoi(e) : 1;
+        e = getenv("PG_K3_EVICT"); evict = e ? atoi(e) : 0;
         e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 8;
     }
     int grid = pg_num_sms() * gmul;

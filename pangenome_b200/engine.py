@@ -336,7 +336,7 @@ class TwoPhaseBuilder:
         if ev is not None:
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record(st)
-        partition_kmers(packed, self.k, self.mode, n_rec, self.owner_bits, self.sub_bits, buckets=b)
+        self.buckets = b = partition_kmers(packed, self.k, self.mode, n_rec, self.owner_bits, self.sub_bits, buckets=b)
         if ev is not None:
             e[1].record(st)
         check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, _stream()),

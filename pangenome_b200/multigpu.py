@@ -1,0 +1,275 @@
+"""Hash-partitioned dBG build across the GPUs of one box (one process per GPU,
+``torch.distributed``; NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+The reference has no distributed path; this is the split SURVEY.md 8(e)
+prescribes.  Per rank:
+
+  1. K1 + K2a on the rank's own records: every position emits one 16-byte
+     update record into bucket (owner, sub) - owner = low bits of mix64(key)
+     (which rank's table holds the key), sub = top bits (which L2-sized region
+     of that table);
+  2. exchange: a W x S count matrix, then the buckets themselves - one
+     all-to-all of equal-sized (padded) blocks, the only collective on the data
+     path;
+  3. K3 on what arrived, region by region (all sources of sub 0, then sub 1, ..).
+
+Every key lives on exactly one rank, so tables never need merging; the merged
+export is the concatenation of the ranks' exports (the short-record sentinel is
+summed).  Count saturation happens at export, after all occurrences of a key -
+from every rank - were added on its owner (SURVEY 8e "result invariance").
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def log2_exact(n):
+    b = n.bit_length() - 1
+    if n < 1 or (1 << b) != n:
+        raise ValueError("world size must be a power of two (1, 2, 4, 8), got %d" % n)
+    return b
+
+
+def exchange_blocks(send, world):
+    """send: tensor [world, block] (row d goes to rank d) -> recv [world, block]
+    (row s came from rank s).  NCCL: all_to_all_single; gloo (CPU tests) has no
+    all-to-all, so it is emulated with all_gather."""
+    if world == 1:
+        return send.clone()
+    recv = torch.empty_like(send)
+    if dist.get_backend() == "nccl":
+        dist.all_to_all_single(recv.view(-1), send.view(-1))
+    else:
+        rank = dist.get_rank()
+        gathered = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(gathered, send)
+        for s in range(world):
+            recv[s] = gathered[s][rank]
+    return recv
+
+
+def segment_plan(recv_counts, part_cap):
+    """recv_counts: int64 [world, n_sub] (records rank s sent me for region b).
+    Returns (seg_off, seg_cnt) in region-major order so K3 sweeps one table
+    region at a time: segment (b, s) starts at record (s * n_sub + b) * part_cap."""
+    world, n_sub = recv_counts.shape
+    src = torch.arange(world, dtype=torch.int64, device=recv_counts.device).view(1, world)
+    sub = torch.arange(n_sub, dtype=torch.int64, device=recv_counts.device).view(n_sub, 1)
+    seg_off = ((src * n_sub + sub) * part_cap).reshape(-1).contiguous()
+    seg_cnt = recv_counts.t().reshape(-1).contiguous()
+    return seg_off, seg_cnt
+
+
+class DistributedBuilder:
+    """Reusable buffers for the distributed build of same-sized shards."""
+
+    def __init__(self, k, n_positions_local, world, rank, device="cuda", sub_bytes=8 << 20):
+        from . import engine
+        self.engine = engine
+        self.L = _lib.load()
+        self.k, self.world, self.rank = int(min(max(1, k), 27)), world, rank
+        self.owner_bits = log2_exact(world)
+        # every rank sizes for the global worst case: all positions distinct, spread evenly
+        n_glob = torch.tensor([n_positions_local], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(n_glob, op=dist.ReduceOp.SUM)
+        self.n_positions_global = int(n_glob.item())
+        per_rank = (self.n_positions_global + world - 1) // world
+        cap = engine.next_pow2(max(1024, int(per_rank / 0.5) + 1))
+        self.table = engine.DbgTable(cap, self.k, _lib.PG_MODE_CANONICAL, device=device)
+        self.sub_bits = engine.sub_bits_for(cap, sub_bytes)
+        self.n_sub = 1 << self.sub_bits
+        n_parts = world * self.n_sub
+        # the largest shard decides the block size every rank uses (blocks must be equal-sized)
+        m = torch.tensor([n_positions_local], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        self.part_cap = int(int(m.item()) / n_parts * 1.25) + 4096
+        self.buckets = engine.RecordBuckets(n_parts, self.part_cap, device)
+        self.launches_per_build = 4
+
+    def build(self, packed, n_rec, ev=None):
+        eng, L, t, b = self.engine, self.L, self.table, self.buckets
+        t.clear()
+        st = torch.cuda.current_stream()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if ev is not None else None
+        if n_rec > 0:
+            g_begin, g_end = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
+            eng.check(L.pg_count_short(ctypes.byref(t.c), eng._ptr(packed.d_seq_off), n_rec, g_begin, g_end, eng._stream()),
+                      "pg_count_short")
+        if e:
+            e[0].record(st)
+        if n_rec > 0:
+            desc = _lib.PgTable(None, 2, None, _lib.PG_MODE_CANONICAL, self.k)
+            eng.check(L.pg_kmer_partition(ctypes.byref(desc), eng._ptr(packed.pk2), eng._ptr(packed.amb),
+                                          eng._ptr(packed.d_seq_off), n_rec, g_begin, g_end, self.owner_bits, self.sub_bits,
+                                          eng._ptr(b.records), b.part_cap, eng._ptr(b.counts), eng._stream()),
+                      "pg_kmer_partition")
+        else:
+            b.counts.zero_()
+        if e:
+            e[1].record(st)
+        # ---- the exchange: counts, then the padded buckets (row d of [world, n_sub * part_cap * 2] goes to rank d)
+        recv_counts = exchange_blocks(b.counts.view(self.world, self.n_sub), self.world)
+        recv = exchange_blocks(b.records.view(self.world, -1), self.world)
+        if e:
+            e[2].record(st)
+        seg_off, seg_cnt = segment_plan(recv_counts, b.part_cap)
+        eng.check(L.pg_insert_records(ctypes.byref(t.c), eng._ptr(recv), eng._ptr(seg_off), eng._ptr(seg_cnt),
+                                      int(seg_off.numel()), eng._stream()), "pg_insert_records")
+        if e:
+            e[3].record(st)
+            for name, i in (("partition", 0), ("exchange", 1), ("insert", 2)):
+                ev.setdefault(name, []).append((e[i], e[i + 1]))
+        self._last = (recv, seg_off, seg_cnt)      # keep alive until the stream has consumed them
+        return t
+
+    def verify(self):
+        if int(self.buckets.counts.max().item()) > self.buckets.part_cap:
+            raise _lib.PgError("record bucket overflow on rank %d" % self.rank)
+        if self.table.overflowed():
+            raise _lib.PgError("dBG table overflow on rank %d" % self.rank)
+
+
+def gather_export(table, world, rank):
+    """Merged (keys, vals, cnts) of the distributed dBG on rank 0 (test / small outputs only)."""
+    k, v, c = table.export(sort=False)
+    short = int(table.stats_host()[_lib.PG_STAT_SHORT])
+    sent = np.uint64(0xFFFFFFFFFFFFFFFF)
+    keep = k != sent                               # the sentinel is merged separately
+    k, v, c = k[keep], v[keep], c[keep]
+    if world == 1:
+        parts, shorts = [(k, v, c)], [short]
+    else:
+        parts, shorts = [None] * world, [None] * world
+        dist.all_gather_object(parts, (k, v, c))
+        dist.all_gather_object(shorts, short)
+    if rank != 0:
+        return None
+    K = np.concatenate([p[0] for p in parts])
+    V = np.concatenate([p[1] for p in parts])
+    C = np.concatenate([p[2] for p in parts])
+    tot_short = sum(shorts)
+    if tot_short > 0:
+        K = np.append(K, sent)
+        V = np.append(V, np.uint16(32))
+        C = np.append(C, np.uint8(min(tot_short, 255)))
+    o = np.argsort(K, kind="stable")
+    return K[o], V[o], C[o]
+
+
+def bench(args, world, rank, local, ClockSampler=None):
+    """bench.py --gpus N (N > 1): weak scaling, every rank builds from its own 10 x 5 Mbp shard
+    (same ancestor, rank-specific genomes), one all-to-all per step."""
+    import time
+    from . import engine, synth
+    sys_path_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    k = args.k
+    genomes, length = (10, 5_000_000) if args.workload == "cfg2" else (4, 1_000_000)
+    anc = np.random.default_rng(1).integers(0, 4, length, dtype=np.uint8)
+    recs = []
+    for g in range(genomes):
+        gid = rank * genomes + g
+        recs.append((b"g%d synthetic" % gid, synth._ACGT[synth._snp_copy(np.random.default_rng(100 + gid), anc, 0.01)]))
+    data = synth.fasta_bytes(recs)
+    host = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+    d_fasta = host.to("cuda", non_blocking=True)
+    torch.cuda.synchronize()
+    packed = engine.PackedSeqs(d_fasta)
+    n_rec = packed.n_rec
+    n_ins_local = packed.n_insertions(k)
+    builder = DistributedBuilder(k, packed.n_positions(k), world, rank)
+    stream = torch.cuda.current_stream()
+    kev = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(record=False):
+        p = engine.PackedSeqs(d_fasta)
+        return builder.build(p, n_rec, ev=kev if record else None)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    builder.verify()
+    clocks = ClockSampler(local) if (ClockSampler and rank == 0) else None
+    if clocks:
+        clocks.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    e0.record(stream)
+    for _ in range(args.steps):
+        t = step(record=True)
+    e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop() if clocks else None
+    builder.verify()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([n_ins_local], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    used, entries = t.count()
+    ent = torch.tensor([used], dtype=torch.int64, device="cuda")
+    dist.all_reduce(ent, op=dist.ReduceOp.SUM)
+    avg = lambda name: sum(a.elapsed_time(b) for a, b in kev[name]) / len(kev[name])
+    stage = torch.tensor([avg("partition"), avg("exchange"), avg("insert")], dtype=torch.float64, device="cuda")
+    dist.all_reduce(stage, op=dist.ReduceOp.MAX)
+
+    # end to end: pinned host bytes -> H2D -> build -> D2H of the table statistics
+    def step_e2e():
+        d = host.to("cuda", non_blocking=True)
+        p = engine.PackedSeqs(d)
+        tt = builder.build(p, n_rec)
+        return tt.stats_host()
+    for _ in range(2):
+        step_e2e()
+    dist.barrier()
+    torch.cuda.synchronize()
+    g0, g1 = ev(), ev()
+    g0.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    g1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ems = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms_step = float(ms.item()) / args.steps
+        n_ins = int(tot.item())
+        e2e_ms = float(ems.item()) / args.steps
+        peak = 6552.3
+        pp = os.path.join(sys_path_root, "MEASURED_PEAKS.json")
+        if os.path.isfile(pp):
+            peak = float(json.load(open(pp))["hbm_gbs"])
+        ins_ms = float(stage[2].item())
+        alg = 16.0 * n_ins / world
+        block_bytes = builder.n_sub * builder.part_cap * 16
+        line = {
+            "metric": "dbg_build_kmers_per_s", "value": n_ins / (ms_step * 1e-3) / 1e9, "unit": "G k-mers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "%d x (%d x %d bp genomes, 1%% SNP, shared ancestor), hash-partitioned table, NCCL all-to-all"
+                       % (world, genomes, length), "k": k, "rc": True, "insertions_per_step": n_ins,
+                       "table_slots_per_gpu": builder.table.capacity, "distinct_canonical_keys": int(ent.item()),
+                       "l2": "every step clears and updates a table larger than L2 on every rank"},
+            "e2e": {"value": n_ins / (e2e_ms * 1e-3) / 1e9, "unit": "G k-mers/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(host.numel()) * world, "d2h_bytes_per_step": (8 * 8 + 4 * 8 + 16 * (n_rec + 1)) * world},
+            "gpu_launches": (3 + builder.launches_per_build) * args.steps * world,
+            "clocks": clk,
+            "stages_ms": {"partition": float(stage[0].item()), "exchange": float(stage[1].item()), "insert": ins_ms},
+            "exchange_bytes_per_gpu_per_step": block_bytes * (world - 1),
+            "roofline": {"kernel": "k3_insert_records", "bound": "hbm", "achieved": alg / (ins_ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / (ins_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "convention": "per GPU: 16 B per insertion owned by the rank (SURVEY 8d)"},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
