@@ -251,7 +251,7 @@ def main():
         d = host.to("cuda", non_blocking=True)
         p = engine.PackedSeqs(d)
         tt = builder.build(p, n_rec)
-        return tt.count()            # (occupied slots, dBG entries) - synchronises
+        return tt.stats_host()       # D2H of the table statistics (distinct keys, overflow flag, ...) - synchronises
     for _ in range(2):
         step_e2e()
     torch.cuda.synchronize()
@@ -262,6 +262,8 @@ def main():
     g1.record(stream)
     torch.cuda.synchronize()
     builder.verify()
+    if int(st[_lib.PG_STAT_USED]) != used:
+        raise SystemExit("bench: e2e build reports %d distinct keys, expected %d" % (int(st[_lib.PG_STAT_USED]), used))
     e2e_ms = g0.elapsed_time(g1) / args.steps
     e2e_val = n_ins / (e2e_ms * 1e-3) / 1e9
     cs = t.checksum()

@@ -48,7 +48,7 @@ extern "C" {
 /* indices into the int64 stats block of a table */
 #define PG_STAT_OVERFLOW 0     /* != 0: probing gave up, table too small          */
 #define PG_STAT_SHORT 1        /* insertions of the short-record sentinel key (Q5) */
-#define PG_STAT_USED 2         /* occupied slots (filled by pg_table_count)        */
+#define PG_STAT_USED 2         /* occupied slots: kept by the inserts, recomputed by pg_table_count */
 #define PG_STAT_ENTRIES 3      /* entries in reference convention (pg_table_count) */
 #define PG_STAT_WORDS 8
 

@@ -22,6 +22,7 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
                uint64_t pow5km1, int64_t w_first, int64_t n_tiles) {
     __shared__ __align__(16) uint64_t s_pk[K2_TILE_WORDS + 4];
     __shared__ __align__(16) uint32_t s_am[K2_TILE_WORDS + 8];
+    uint32_t n_claimed = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t w0 = w_first + tile * K2_TILE_WORDS;
         __syncthreads();
@@ -46,15 +47,16 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
                 pg_occ_vals(w, j, g - rs, re - rs, k, vf, vr);
                 if (MODE == PG_MODE_CANONICAL) {
                     PgUpdate u = pg_canonical_update(F, R, vf, vr);
-                    table_upsert(t, u.key, u.masks, u.inc);
+                    table_upsert(t, u.key, u.masks, u.inc, n_claimed);
                 } else {
-                    table_upsert(t, F, vf, 1);
-                    if (MODE == PG_MODE_LITERAL_RC) table_upsert(t, R, vr, 1);
+                    table_upsert(t, F, vf, 1, n_claimed);
+                    if (MODE == PG_MODE_LITERAL_RC) table_upsert(t, R, vr, 1, n_claimed);
                 }
             }
             pg_codes_roll(w, j, k, pow5km1, F, R);
         }
     }
+    publish_claims(t, n_claimed);
 }
 
 // records shorter than k insert the sentinel key 2^64-1 once per strand (Q5, build_dbg :1089-1090)
@@ -255,8 +257,6 @@ extern "C" int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const ui
         return pg_fail(PG_ERR_INVALID, "pg_kmer_insert: packed buffers must be 16-byte aligned");
     cudaStream_t stream = (cudaStream_t)stream_;
     TableView tv = make_view(t);
-    int strands = t->mode == PG_MODE_LITERAL ? 1 : 2;
-    (void)strands;
     rc = pg_count_short(t, d_seq_off, n_rec, g_begin, g_end, stream_); if (rc) return rc;
     if (g_end > g_begin && n_rec > 0) {
         int64_t w_first = (g_begin >> 5) & ~(int64_t)3;                 // multiple of 4 words -> 16-byte aligned staging

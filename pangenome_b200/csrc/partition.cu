@@ -58,6 +58,7 @@ k2a_partition(PartArgs a) {
     uint32_t *s_tick = s_off + a.n_parts;                                    // n_parts: tickets
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_tick + a.n_parts + (a.n_parts & 1));
     __shared__ uint32_t s_nrec;
+    __shared__ uint32_t s_chunk[32];
     const uint64_t pol = pg_policy_evict_first();
 
     auto emit = [&](int slot, uint64_t key, uint32_t masks, uint32_t inc) {
@@ -148,21 +149,34 @@ k2a_partition(PartArgs a) {
         if (!done)
             for (int e = 0; e < KP_G * RPP; e++) s_pid[threadIdx.x * KP_G * RPP + e] = NOREC;
         __syncthreads();
-        // ---- 2. reserve space: one global atomicAdd per bucket per tile; local exclusive offsets ----
-        if (threadIdx.x < 32) {     // warp 0 scans the histogram in chunks of 32
-            uint32_t carry = 0;
-            for (int base = 0; base < a.n_parts; base += 32) {
-                int i = base + threadIdx.x;
-                uint32_t h = i < a.n_parts ? s_hist[i] : 0, inc = h;
-                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += y; }
-                if (i < a.n_parts) {
-                    s_off[i] = carry + inc - h;
-                    s_base[i] = h ? atomicAdd(a.part_counts + i, (unsigned long long)h) : 0ull;
-                }
-                carry += __shfl_sync(0xffffffffu, inc, 31);
+        // ---- 2. reserve space: one global atomicAdd per bucket per tile (all in flight at once, every
+        // thread owns buckets tid, tid+128, ..) and local exclusive offsets by a block scan of the histogram
+        {
+            const int lane = threadIdx.x & 31;
+            uint32_t run = 0;       // exclusive prefix of the 32-bucket chunks this thread has seen (same for the whole warp)
+            for (int base = 0; base < a.n_parts; base += KP_THREADS) {
+                const int i = base + threadIdx.x;
+                uint32_t h = i < a.n_parts ? s_hist[i] : 0;
+                if (i < a.n_parts) s_base[i] = h ? atomicAdd(a.part_counts + i, (unsigned long long)h) : 0ull;
+                uint32_t inc = h;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+                if (i < a.n_parts) s_off[i] = inc - h;                       // offset inside its 32-bucket chunk
+                if (lane == 31) s_chunk[i >> 5] = inc;                       // chunk total (chunks past n_parts hold 0)
+                (void)run;
             }
-            if (threadIdx.x == 0) s_nrec = carry;
         }
+        __syncthreads();
+        if (threadIdx.x < 32) {       // exclusive scan of the <= 32 chunk totals
+            const int nchunk = (a.n_parts + 31) >> 5;
+            uint32_t v = (int)threadIdx.x < nchunk ? s_chunk[threadIdx.x] : 0, inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += y; }
+            s_chunk[threadIdx.x] = inc - v;
+            if (threadIdx.x == 31) s_nrec = inc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.n_parts; i += KP_THREADS) s_off[i] += s_chunk[i >> 5];
         __syncthreads();
         const uint32_t nrec = s_nrec;
         if (nrec == 0) continue;
@@ -194,6 +208,7 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const uint64_t pol = pg_policy_evict_first();
+    uint32_t n_claimed = 0;
     for (int s = 0; s < n_seg; s++) {
         const int64_t off = __ldg(seg_off + s), cnt = __ldg(seg_cnt + s);
         for (int64_t i = i0; i < cnt; i += stride * K3_ILP) {
@@ -210,9 +225,10 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
 #pragma unroll
             for (int u = 0; u < K3_ILP; u++)
                 if (i + u * stride < cnt)
-                    table_upsert_from(t, home[u], ck[u], cv[u], (uint64_t)r[u].x | ((uint64_t)r[u].y << 32), r[u].z, r[u].w);
+                    table_upsert_from(t, home[u], ck[u], cv[u], (uint64_t)r[u].x | ((uint64_t)r[u].y << 32), r[u].z, r[u].w, n_claimed);
         }
     }
+    publish_claims(t, n_claimed);
 }
 
 int part_smem_bytes(int mode, int n_parts) {

@@ -26,14 +26,14 @@ __device__ __forceinline__ void slot_merge(uint64_t *p, uint64_t cv, uint32_t ma
 // Continue an upsert from slot s whose contents (ck, cv) were already loaded.
 // returns the slot index the key lives in (claimed if absent), or -1 when probing gives up
 __device__ __forceinline__ int64_t table_upsert_from(const TableView &t, uint64_t s, uint64_t ck, uint64_t cv, uint64_t key,
-                                                     uint32_t masks, uint32_t inc) {
+                                                     uint32_t masks, uint32_t inc, uint32_t &n_claimed) {
     for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
         uint64_t *p = t.slots + 2 * s;
         if (probe) pg_ld_slot(p, ck, cv);
         if (ck == PG_EMPTY) {
             // empty slots always hold {EMPTY, 0}: claim key + first masks + first count at once
             pg_cas128(p, PG_EMPTY, 0ull, key, (uint64_t)masks | ((uint64_t)inc << 32), ck, cv);
-            if (ck == PG_EMPTY) return (int64_t)s;
+            if (ck == PG_EMPTY) { n_claimed++; return (int64_t)s; }
         }
         if (ck == key) { slot_merge(p, cv, masks, inc); return (int64_t)s; }
         s = (s + 1) & t.capmask;
@@ -41,10 +41,16 @@ __device__ __forceinline__ int64_t table_upsert_from(const TableView &t, uint64_
     atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
     return -1;
 }
-__device__ __forceinline__ int64_t table_upsert(const TableView &t, uint64_t key, uint32_t masks, uint32_t inc) {
+__device__ __forceinline__ int64_t table_upsert(const TableView &t, uint64_t key, uint32_t masks, uint32_t inc, uint32_t &n_claimed) {
     uint64_t s = tv_home(t, key), ck, cv;
     pg_ld_slot(t.slots + 2 * s, ck, cv);
-    return table_upsert_from(t, s, ck, cv, key, masks, inc);
+    return table_upsert_from(t, s, ck, cv, key, masks, inc, n_claimed);
+}
+// one atomicAdd per warp: slots claimed by this kernel -> PG_STAT_USED (distinct keys, kept by the inserts)
+__device__ __forceinline__ void publish_claims(const TableView &t, uint32_t n_claimed) {
+    n_claimed = __reduce_add_sync(0xffffffffu, n_claimed);
+    if ((threadIdx.x & 31) == 0 && n_claimed)
+        atomicAdd(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_USED), (unsigned long long)n_claimed);
 }
 
 // largest r in [-1, n_rec) with seq_off[r] <= g   (r = -1: g precedes the first record)

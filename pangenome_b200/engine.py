@@ -140,6 +140,11 @@ class DbgTable:
     def stats_host(self):
         return self.stats.cpu().numpy()
 
+    def n_keys(self):
+        """Occupied slots as counted by the inserts themselves (one atomicAdd per warp on claim):
+        distinct canonical pairs in PG_MODE_CANONICAL, distinct literal keys otherwise."""
+        return int(self.stats_host()[_lib.PG_STAT_USED])
+
     def count(self):
         check(self.L.pg_table_count(ctypes.byref(self.c), _stream()), "pg_table_count")
         s = self.stats_host()
@@ -322,21 +327,26 @@ class TwoPhaseBuilder:
         part_cap = int(n_positions * per_pos / n_parts * 1.25) + 4096
         self.buckets = RecordBuckets(n_parts, part_cap, device)
         self.launches_per_build = 4          # clear, count_short, k2a_partition, k3_insert_records
+        self.side = torch.cuda.Stream(device=device)   # the table clear (DRAM-write bound) overlaps K2a (ALU bound)
 
     def build(self, packed, n_rec, ev=None):
         """Enqueue clear + K2a + K3 (no synchronisation).  ``ev`` = optional dict receiving CUDA
         event pairs around the two kernels."""
         t, b, L = self.table, self.buckets, self.L
-        t.clear()
+        st = torch.cuda.current_stream()
+        self.side.wait_stream(st)            # whoever still reads the previous table finishes first
+        with torch.cuda.stream(self.side):
+            t.clear()
         if n_rec == 0:
+            st.wait_stream(self.side)
             return t
         g_begin, g_end = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
-        check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
-        st = torch.cuda.current_stream()
         if ev is not None:
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record(st)
         self.buckets = b = partition_kmers(packed, self.k, self.mode, n_rec, self.owner_bits, self.sub_bits, buckets=b)
+        st.wait_stream(self.side)            # K3 needs the cleared table
+        check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
         if ev is not None:
             e[1].record(st)
         check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, _stream()),

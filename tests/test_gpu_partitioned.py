@@ -65,3 +65,22 @@ def test_partitioned_skew_falls_back(eng):
     packed = eng.PackedSeqs(eng.to_device_bytes(data))
     t, _, _ = eng.build_dbg_partitioned(packed, 21, sub_bytes=1 << 12)
     assert t.checksum() == oracle.table_checksum(*ref["dbg"])
+
+
+def test_inserts_count_distinct_keys(eng):
+    """PG_STAT_USED is kept by the insert kernels themselves (fused and two-phase)."""
+    data = pangenome(6, 200_000)
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    t1, _ = eng.build_dbg(packed, 27)
+    kept = t1.n_keys()
+    used, _ = t1.count()
+    assert kept == used
+    t2, _, _ = eng.build_dbg_partitioned(packed, 27)
+    assert t2.n_keys() == used
+    from pangenome_b200 import _lib
+    b = eng.TwoPhaseBuilder(27, _lib.PG_MODE_CANONICAL, packed.n_positions(27))
+    for _ in range(3):                      # reused buffers, clear overlapped on a side stream
+        t3 = b.build(packed, packed.n_rec)
+        assert t3.n_keys() == used
+        assert t3.checksum() == t1.checksum()
+    b.verify()
