@@ -234,6 +234,16 @@ int pg_label_regions(const pg_graph *g, const int64_t *d_hit_g, const uint64_t *
                      int32_t *d_row_rec, int64_t *d_row_end, int32_t *d_row_label, int64_t cap_rows, int64_t *d_n_rows,
                      void *d_ws, int64_t ws_bytes, pg_stream_t stream);
 
+/* ---- host-side text writers (HOST pointers) -------------------------------------------
+ * The side files of seq2graph (kmer_numba.py:1893-1904 and the cluster file `mcl` leaves):
+ * pg_host_write_xyz: "code0_v0\tcode1_v1\tweight\n" per edge in the order given;
+ * pg_host_write_mcl: one tab-separated line of "code_v5" names per label; input sorted by
+ *                    (label, code, v5).
+ */
+int pg_host_write_xyz(const char *path, const uint64_t *c0, const uint32_t *v0, const uint64_t *c1,
+                      const uint32_t *v1, const uint32_t *w, int64_t n);
+int pg_host_write_mcl(const char *path, const uint64_t *code, const uint32_t *v5, const int64_t *label, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -154,13 +154,13 @@ __global__ void k_table_checksum(const uint64_t *__restrict__ slots, int64_t cap
 }
 
 // ---- K4: reduced dBG -----------------------------------------------------------------------------
-__global__ void k4_rdbg_count(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k,
+__global__ void k4_rdbg_count(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k, uint64_t pow5_mid,
                               const int64_t *__restrict__ stats, unsigned long long *out) {
     unsigned long long ns = 0, nm = 0;
     int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t i = i0; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
         uint64_t key, v; pg_ld_slot(slots + 2 * i, key, v);
-        uint32_t f = pg_rdbg_flags(key, v, mode, k);
+        uint32_t f = pg_rdbg_flags_fast(key, v, mode, k, pow5_mid);
         ns += f != 0; nm += (f & 1u) + ((f >> 1) & 1u);
     }
     if (i0 == 0 && stats[PG_STAT_SHORT] > 0) nm += 1;   // sentinel: val 32 -> in-popcount 0 -> member
@@ -168,12 +168,12 @@ __global__ void k4_rdbg_count(const uint64_t *__restrict__ slots, int64_t cap, i
     if ((threadIdx.x & 31) == 0) { if (ns) atomicAdd(out, ns); if (nm) atomicAdd(out + 1, nm); }
 }
 
-__global__ void k4_rdbg_select(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k,
+__global__ void k4_rdbg_select(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k, uint64_t pow5_mid,
                                const int64_t *__restrict__ stats, TableView rd) {
     int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t i = i0; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
         uint64_t key, v; pg_ld_slot(slots + 2 * i, key, v);
-        uint32_t f = pg_rdbg_flags(key, v, mode, k);
+        uint32_t f = pg_rdbg_flags_fast(key, v, mode, k, pow5_mid);
         if (!f) continue;
         // every key arrives exactly once: claim with CAS, then plain stores of masks + flags
         uint64_t s = tv_home(rd, key);
@@ -317,7 +317,7 @@ extern "C" int pg_rdbg_count(const pg_table *dbg, int64_t *d_out, pg_stream_t st
     if (!d_out) return pg_fail(PG_ERR_INVALID, "pg_rdbg_count: null output");
     cudaStream_t stream = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(int64_t), stream));
-    k4_rdbg_count<<<scan_grid(dbg->capacity, 256), 256, 0, stream>>>(dbg->d_slots, dbg->capacity, dbg->mode, dbg->k, dbg->d_stats,
+    k4_rdbg_count<<<scan_grid(dbg->capacity, 256), 256, 0, stream>>>(dbg->d_slots, dbg->capacity, dbg->mode, dbg->k, pg_pow5(dbg->k / 2), dbg->d_stats,
                                                                    reinterpret_cast<unsigned long long *>(d_out));
     PG_CUDA(cudaGetLastError());
     return PG_OK;
@@ -329,7 +329,7 @@ extern "C" int pg_rdbg_select(const pg_table *dbg, const pg_table *rdbg, pg_stre
     if (dbg->mode != rdbg->mode || dbg->k != rdbg->k) return pg_fail(PG_ERR_INVALID, "pg_rdbg_select: mode/k mismatch");
     cudaStream_t stream = (cudaStream_t)stream_;
     TableView rd = make_view(rdbg);
-    k4_rdbg_select<<<scan_grid(dbg->capacity, 256), 256, 0, stream>>>(dbg->d_slots, dbg->capacity, dbg->mode, dbg->k, dbg->d_stats, rd);
+    k4_rdbg_select<<<scan_grid(dbg->capacity, 256), 256, 0, stream>>>(dbg->d_slots, dbg->capacity, dbg->mode, dbg->k, pg_pow5(dbg->k / 2), dbg->d_stats, rd);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

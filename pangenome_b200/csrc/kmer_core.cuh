@@ -91,6 +91,25 @@ PG_HD int pg_slot_entries(uint64_t key, uint64_t v, int mode, int k, PgEntry e[2
     e[1].key = rk; e[1].val = (masks >> 16) & 0xFFFu; e[1].cnt = c255;
     return 2;
 }
+// Same, without materialising the rc key (callers that only need the values): n = 1 or 2 entries,
+// vals[o] = 12-bit value of orientation o.  pow5_mid = 5^(k/2) lets odd-k keys skip the rc computation.
+PG_HD int pg_slot_vals(uint64_t key, uint64_t v, int mode, int k, uint64_t pow5_mid, uint32_t vals[2]) {
+    if (key == PG_EMPTY) return 0;
+    uint32_t masks = (uint32_t)v;
+    vals[0] = masks & 0xFFFu; vals[1] = (masks >> 16) & 0xFFFu;
+    if (mode != PG_MODE_CANONICAL) return 1;
+    if (pg_maybe_palindrome(key, k, pow5_mid) && pg_rc_code(key, k) == key) return 1;
+    return 2;
+}
+PG_HD uint32_t pg_rdbg_flags_fast(uint64_t key, uint64_t v, int mode, int k, uint64_t pow5_mid) {
+    uint32_t vals[2];
+    int n = pg_slot_vals(key, v, mode, k, pow5_mid, vals);
+    if (n == 0) return 0;
+    uint32_t f = pg_is_rdbg(vals[0]) ? 1u : 0u;
+    if (n == 2 && pg_is_rdbg(vals[1])) f |= 2u;
+    if (key == 0) f |= 4u;
+    return f;
+}
 
 // flags of an rdBG slot: bit0/bit1 = orientation 0/1 is a member, bit2 = phantom key 0 (Q6)
 PG_HD uint32_t pg_rdbg_flags(uint64_t key, uint64_t v, int mode, int k) {

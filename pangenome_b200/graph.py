@@ -83,7 +83,7 @@ class RdbgGraph:
 
     def edges(self, rd):
         """(c0, v0, c1, v1, w) sorted into the reference's .xyz file order
-        (first-insertion order of the edge dict)."""
+        (first-insertion order of the edge dict).  The sort runs on the device."""
         _, ne = self.counts()
         dev = self.stats.device
         c0 = torch.empty(max(ne, 1), dtype=torch.int64, device=dev)
@@ -96,13 +96,14 @@ class RdbgGraph:
         check(self.L.pg_graph_export_edges(ctypes.byref(self.c), ctypes.byref(rd.c), _ptr(c0), _ptr(v0), _ptr(c1), _ptr(v1),
                                            _ptr(w), _ptr(first), ne, _ptr(d_n), _stream()), "pg_graph_export_edges")
         assert int(d_n.item()) == ne
-        order = np.argsort(first[:ne].cpu().numpy().view(np.uint64), kind="stable")
-        f = lambda t, dt: t[:ne].cpu().numpy().view(dt)[order]
+        order = torch.argsort(first[:ne], stable=True)        # ordinals are < 2^63: signed order == unsigned order
+        f = lambda t, dt: t[:ne][order].cpu().numpy().view(dt)
         return f(c0, np.uint64), f(v0, np.uint32), f(c1, np.uint64), f(v1, np.uint32), f(w, np.uint32)
 
-    def components(self, rd, min_weight=1):
-        """K7 + host ordering.  Returns (nslot, code, v5, label) per node; label =
-        rank of the node's component under (size descending, smallest (code, v5))."""
+    def components(self, rd, min_weight=1, to_host=True):
+        """K7 + component ordering.  Returns (nslot, code, v5, label) per graph node; label = rank
+        of the node's component under (size descending, smallest (code, v5)).  The union-find is
+        a kernel; the ordering uses device sorts; labels are written to the node table directly."""
         check(self.L.pg_graph_components(ctypes.byref(self.c), int(min_weight), _stream()), "pg_graph_components")
         nn, _ = self.counts()
         dev = self.stats.device
@@ -114,21 +115,32 @@ class RdbgGraph:
         check(self.L.pg_graph_export_nodes(ctypes.byref(self.c), ctypes.byref(rd.c), _ptr(nslot), _ptr(code), _ptr(v5),
                                            _ptr(root), nn, _ptr(d_n), _stream()), "pg_graph_export_nodes")
         nn = int(d_n.item())          # nodes that appear in at least one edge (<= inserted node slots)
-        nslot = nslot[:nn].cpu().numpy().view(np.uint32)
-        code = code[:nn].cpu().numpy().view(np.uint64)
-        v5 = v5[:nn].cpu().numpy().view(np.uint32)
-        root = root[:nn].cpu().numpy().view(np.uint32)
+        self.node_label.fill_(-1)
         if nn == 0:
-            return nslot, code, v5, np.zeros(0, np.int64)
-        order = np.lexsort((v5, code))                       # nodes ascending by (code, v5)
+            z = np.zeros(0, np.uint32)
+            return z, np.zeros(0, np.uint64), z, np.zeros(0, np.int64)
+        nslot, code, v5, root = nslot[:nn].long(), code[:nn], v5[:nn].long(), root[:nn].long()
+        # nodes ascending by (code, v5): codes are < 5^27 < 2^63, so int64 order is the unsigned order
+        o1 = torch.argsort(v5, stable=True)
+        order = o1[torch.argsort(code[o1], stable=True)]
         roots_sorted = root[order]
-        uniq, first_idx, counts = np.unique(roots_sorted, return_index=True, return_counts=True)
-        # first_idx = rank of the component's smallest node; order components by (-size, that rank)
-        comp_order = np.lexsort((first_idx, -counts))
-        label_of_comp = np.empty(uniq.size, np.int64)
-        label_of_comp[comp_order] = np.arange(uniq.size)
-        label = label_of_comp[np.searchsorted(uniq, root)]
-        return nslot, code, v5, label
+        uniq, inverse, counts = torch.unique(roots_sorted, return_inverse=True, return_counts=True)
+        rank = torch.arange(nn, device=dev)
+        first_idx = torch.full((uniq.numel(),), nn, dtype=torch.int64, device=dev).scatter_reduce_(0, inverse, rank, "amin")
+        c1 = torch.argsort(first_idx, stable=True)
+        comp_order = c1[torch.argsort(-counts[c1], stable=True)]          # (size desc, smallest node asc)
+        label_of_comp = torch.empty_like(comp_order)
+        label_of_comp[comp_order] = torch.arange(uniq.numel(), device=dev)
+        label_sorted = label_of_comp[inverse]                             # per node, in (code, v5) order
+        self.node_label.index_put_((nslot[order],), label_sorted.to(torch.int32))
+        self.n_components = int(uniq.numel())
+        if not to_host:
+            return None
+        # host copies, sorted by (label, code, v5) - the order the cluster file is written in
+        o3 = torch.argsort(label_sorted, stable=True)
+        fin = order[o3]
+        return (nslot[fin].cpu().numpy().astype(np.uint32), code[fin].cpu().numpy().view(np.uint64),
+                v5[fin].cpu().numpy().astype(np.uint32), label_sorted[o3].cpu().numpy())
 
     def set_labels(self, nslot, label):
         """Upload one label per graph node; every other node slot gets -1 (never matches in K8)."""
@@ -174,6 +186,22 @@ class GraphResult:
     def xyz_lines(self):
         c0, v0, c1, v1, w = self.edges
         return ["%d_%d\t%d_%d\t%d" % t for t in zip(c0.tolist(), v0.tolist(), c1.tolist(), v1.tolist(), w.tolist())]
+
+    def write_xyz(self, path):
+        """<qry>_rdbg_weight.xyz (kmer_numba.py:1893-1904) through the C++ writer of libpgdbg."""
+        c0, v0, c1, v1, w = [np.ascontiguousarray(x) for x in self.edges]
+        L = _lib.load()
+        P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        check(L.pg_host_write_xyz(path.encode(), P(c0), P(v0), P(c1), P(v1), P(w), int(c0.size)), "pg_host_write_xyz")
+
+    def write_mcl(self, path):
+        """The cluster file (what `mcl -o` leaves, :1911): one line of node names per component."""
+        nslot, code, v5, label = self.nodes
+        order = np.lexsort((v5, code, label))
+        code, v5, label = [np.ascontiguousarray(x[order]) for x in (code, v5, label.astype(np.int64))]
+        L = _lib.load()
+        P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        check(L.pg_host_write_mcl(path.encode(), P(code), P(v5), P(label), int(code.size)), "pg_host_write_mcl")
 
     def mcl_lines(self):
         """One line per component, like the cluster file the reference reads (:1918-1929)."""
@@ -261,7 +289,8 @@ def seq2graph_device(packed, rd, k, Ns=2 ** 63, rc=False, min_weight=1, mcl_line
         lab = labels_from_mcl(mcl_lines, res.edges)
         label = np.array([lab[(c, v)] for c, v in zip(code.tolist(), v5.tolist())], dtype=np.int64)
     res.nodes = (nslot, code, v5, label)
-    g.set_labels(nslot, label)
+    if mcl_lines is not None:
+        g.set_labels(nslot, label)
     for h in hits:
         rec, start, end, lab_ = g.regions(h, packed, k)
         res.rows_raw.append((rec, start, end, 1 if h.strand == 0 else -1, lab_))

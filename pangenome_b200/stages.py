@@ -72,15 +72,9 @@ def seq2graph(qry, kmer=13, bits=5, Ns=1e6, brkpt="./breakpoint_rdbg.npz", rdbg_
             if mcl_lines and mcl_lines[-1] == "":
                 mcl_lines.pop()
     res = graph.seq2graph_device(packed, rdbg_dict.table, kmer, Ns=Ns, rc=bool(rc), min_weight=min_weight, mcl_lines=mcl_lines)
-    with open(oname, "w") as f:
-        lines = res.xyz_lines()
-        if lines:
-            f.write("\n".join(lines) + "\n")
+    res.write_xyz(oname)
     if mcl_lines is None and write_mcl:
-        with open(oname + ".mcl", "w") as f:
-            ml = res.mcl_lines()
-            if ml:
-                f.write("\n".join(ml) + "\n")
+        res.write_mcl(oname + ".mcl")
     for seqid, st, ed, strand, lab in res.rows(packed, data):
         out.write("%s\t%d\t%d\t%s\t%d\n" % (seqid, st, ed, strand, lab))
     code, v5, label = res.nodes[1], res.nodes[2], res.nodes[3]
