@@ -113,6 +113,28 @@ PG_HD ChunkCls classify16(const uint32_t w[4], int n_file, bool has_last) {
     return c;
 }
 
+// Pass A only needs the line structure: newline and '>' masks (no digits, no ambiguity plane).
+PG_HD ChunkCls classify16_lines(const uint32_t w[4], int n_file, bool has_last) {
+    ChunkCls c;
+    c.nl = c.gt = c.amb = c.dig = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t x = w[j];
+        uint32_t nl80 = ~swar_nonzero80(x ^ 0x0A0A0A0Au) & 0x80808080u;
+        uint32_t gt80 = ~swar_nonzero80(x ^ 0x3E3E3E3Eu) & 0x80808080u;
+        c.nl |= swar_flags4(nl80) << (4 * j);
+        c.gt |= swar_flags4(gt80) << (4 * j);
+    }
+    uint32_t infile = n_file >= 16 ? 0xFFFFu : ((1u << (n_file < 0 ? 0 : n_file)) - 1u);
+    c.real_nl = pg_popc(c.nl & infile);
+    if (has_last) {
+        int first_forced = n_file > 0 ? n_file - 1 : 0;
+        uint32_t forced = (0xFFFFu << first_forced) & 0xFFFFu;
+        c.nl |= forced; c.gt &= ~forced;
+    }
+    return c;
+}
+
 struct ChunkRun {
     uint32_t seqmask;   // bytes that are bases
     uint32_t hs;        // bytes that start a header line
@@ -123,6 +145,18 @@ struct ChunkRun {
 PG_HD ChunkRun chunk_run(const ChunkCls &c, uint32_t entry) {
     ChunkRun r;
     uint32_t nl = c.nl & 0xFFFFu;
+    if (c.gt == 0) {   // fast path (almost every chunk): no '>' byte, so no header can start here
+        r.hs = 0;
+        if (nl == 0) {
+            r.seqmask = entry == ST_HEADER ? 0u : 0xFFFFu;
+            r.exit_state = entry == ST_HEADER ? ST_HEADER : ST_SEQ;
+        } else {
+            uint32_t after_first = ~((2u << pg_ctz(nl)) - 1u);
+            r.seqmask = ~nl & 0xFFFFu & (entry == ST_HEADER ? after_first : 0xFFFFFFFFu);
+            r.exit_state = (nl & 0x8000u) ? ST_LINE_START : ST_SEQ;
+        }
+        return r;
+    }
     uint32_t ls = ((nl << 1) | (entry == ST_LINE_START ? 1u : 0u)) & 0xFFFFu;   // line starts
     r.hs = ls & c.gt & ~nl;
     uint32_t starts = r.hs | (entry == ST_HEADER ? 1u : 0u);
@@ -149,6 +183,18 @@ PG_HD ChunkRun chunk_run(const ChunkCls &c, uint32_t entry) {
 
 PG_HD Sum3 chunk_sum3(const ChunkCls &c) {
     Sum3 s;
+    if (c.gt == 0) {   // fast path: the entry state only decides whether the bytes before the first '\n' are bases
+        uint32_t nl = c.nl & 0xFFFFu;
+        if (nl == 0) {
+            s.v[ST_LINE_START] = SV_MAKE(ST_SEQ, 0, 16); s.v[ST_HEADER] = SV_MAKE(ST_HEADER, 0, 0); s.v[ST_SEQ] = SV_MAKE(ST_SEQ, 0, 16);
+        } else {
+            uint32_t ex = (nl & 0x8000u) ? ST_LINE_START : ST_SEQ;
+            uint32_t all = 16u - pg_popc(nl);
+            uint32_t tail = pg_popc(~nl & 0xFFFFu & ~((2u << pg_ctz(nl)) - 1u));
+            s.v[ST_LINE_START] = SV_MAKE(ex, 0, all); s.v[ST_HEADER] = SV_MAKE(ex, 0, tail); s.v[ST_SEQ] = SV_MAKE(ex, 0, all);
+        }
+        return s;
+    }
 #pragma unroll
     for (uint32_t e = 0; e < 3; e++) {
         ChunkRun r = chunk_run(c, e);

@@ -90,6 +90,7 @@ __device__ __forceinline__ void tile_scan4(const Sum3 mine[K1_NSUB], Sum3 *s_agg
     __syncthreads();
 }
 
+template <bool LINES_ONLY>
 __device__ __forceinline__ void load_classify4(const uint8_t *fasta, int64_t nbytes, int64_t tile_off, ChunkCls c[K1_NSUB]) {
     uint4 v[K1_NSUB];
     const bool full = tile_off + K1_TILE <= nbytes;
@@ -101,7 +102,7 @@ __device__ __forceinline__ void load_classify4(const uint8_t *fasta, int64_t nby
         for (int i = 0; i < K1_NSUB; i++) {
             uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
             int64_t left = nbytes - (tile_off + ((int64_t)i * K1_THREADS + threadIdx.x) * 16);
-            c[i] = classify16(w, 16, left <= 16);
+            c[i] = LINES_ONLY ? classify16_lines(w, 16, left <= 16) : classify16(w, 16, left <= 16);
         }
     } else {
 #pragma unroll
@@ -116,7 +117,7 @@ k1_tile_summaries(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t nti
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         if (threadIdx.x == 0) s_nl = 0;
         ChunkCls c[K1_NSUB];
-        load_classify4(fasta, nbytes, tile * K1_TILE, c);
+        load_classify4<true>(fasta, nbytes, tile * K1_TILE, c);
         Sum3 mine[K1_NSUB], excl[K1_NSUB], total;
         uint32_t my_nl = 0;
 #pragma unroll
@@ -211,7 +212,7 @@ k1_tile_pack(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles,
         TileEntry e = entries[tile];
         if (e.dead) return;
         ChunkCls c[K1_NSUB];
-        load_classify4(fasta, nbytes, tile * K1_TILE, c);          // loads in flight while the staging is cleared
+        load_classify4<false>(fasta, nbytes, tile * K1_TILE, c);   // loads in flight while the staging is cleared
         for (int i = threadIdx.x; i < K1_PKW; i += K1_THREADS) s_pk[i] = 0;
         for (int i = threadIdx.x; i < K1_AMW; i += K1_THREADS) s_am[i] = 0;
         Sum3 mine[K1_NSUB], excl[K1_NSUB], total;

@@ -197,8 +197,11 @@ class GraphResult:
     def write_mcl(self, path):
         """The cluster file (what `mcl -o` leaves, :1911): one line of node names per component."""
         nslot, code, v5, label = self.nodes
-        order = np.lexsort((v5, code, label))
-        code, v5, label = [np.ascontiguousarray(x[order]) for x in (code, v5, label.astype(np.int64))]
+        label = label.astype(np.int64)
+        if label.size > 1 and not (np.all(label[1:] >= label[:-1])):      # components() already delivers (label, code, v5) order
+            order = np.lexsort((v5, code, label))
+            code, v5, label = code[order], v5[order], label[order]
+        code, v5, label = [np.ascontiguousarray(x) for x in (code, v5, label)]
         L = _lib.load()
         P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         check(L.pg_host_write_mcl(path.encode(), P(code), P(v5), P(label), int(code.size)), "pg_host_write_mcl")

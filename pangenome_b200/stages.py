@@ -77,5 +77,38 @@ def seq2graph(qry, kmer=13, bits=5, Ns=1e6, brkpt="./breakpoint_rdbg.npz", rdbg_
         res.write_mcl(oname + ".mcl")
     for seqid, st, ed, strand, lab in res.rows(packed, data):
         out.write("%s\t%d\t%d\t%s\t%d\n" % (seqid, st, ed, strand, lab))
-    code, v5, label = res.nodes[1], res.nodes[2], res.nodes[3]
-    return {(int(c), int(v)): int(l) for c, v, l in zip(code.tolist(), v5.tolist(), label.tolist())}
+    return LabelDict(res.nodes[1], res.nodes[2], res.nodes[3])
+
+
+class LabelDict(dict):
+    """The reference returns label_dct {(code, v5): label}; building millions of Python tuples is the
+    slowest thing left in the CLI, so the dict is only materialised when somebody looks at it."""
+
+    def __init__(self, code, v5, label):
+        super().__init__()
+        self._arrays, self._built = (code, v5, label), False
+
+    def _build(self):
+        if not self._built:
+            self._built = True
+            code, v5, label = self._arrays
+            super().update({(int(c), int(v)): int(l) for c, v, l in zip(code.tolist(), v5.tolist(), label.tolist())})
+
+    def __getitem__(self, k):
+        self._build()
+        return super().__getitem__(k)
+
+    def __contains__(self, k):
+        self._build()
+        return super().__contains__(k)
+
+    def __len__(self):
+        return int(self._arrays[0].size)
+
+    def __iter__(self):
+        self._build()
+        return super().__iter__()
+
+    def items(self):
+        self._build()
+        return super().items()

@@ -1,0 +1,76 @@
+"""BASELINE config 2 at FULL size (10 x 5 Mbp, k = 27) on the GPU against facts computed once by the
+C oracle (tests/golden/cfg2_oracle_facts.json; the oracle is itself pinned to the reference), plus
+size-independent properties: fused == two-phase, rebuild idempotence, strand symmetry of the table."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from pangenome_b200.synth import pangenome
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pangenome_b200 import engine, graph
+    facts = json.load(open(os.path.join(GOLDEN, "cfg2_oracle_facts.json")))
+    data = pangenome(10, 5_000_000)
+    assert hashlib.sha256(data).hexdigest() == facts["file_sha256"]
+    packed = engine.PackedSeqs(engine.to_device_bytes(data))
+    return engine, graph, facts, data, packed
+
+
+def test_cfg2_dbg_checksum_both_builds(ctx):
+    engine, graph, facts, data, packed = ctx
+    assert packed.n_insertions(27) == facts["n_inserts"]
+    t_fused, _ = engine.build_dbg(packed, 27)
+    assert list(t_fused.checksum()) == facts["dbg_checksum"]
+    t_two, _, _ = engine.build_dbg_partitioned(packed, 27)
+    assert list(t_two.checksum()) == facts["dbg_checksum"]
+    assert t_two.n_keys() == t_fused.n_keys() == facts["dbg_entries"] // 2     # no palindromes at odd k without N
+    # idempotence: building again into a fresh table gives the same table
+    t_again, _, _ = engine.build_dbg_partitioned(packed, 27)
+    assert t_again.checksum() == t_two.checksum()
+    # literal two-inserts-per-position mode agrees with the canonical pairing
+    t_lit, _ = engine.build_dbg(packed, 27, mode=1)
+    assert list(t_lit.checksum()) == facts["dbg_checksum"]
+
+
+def test_cfg2_strand_symmetry(ctx):
+    """every key has its reverse complement with the same count (both strands are inserted)"""
+    engine, graph, facts, data, packed = ctx
+    t, _, _ = engine.build_dbg_partitioned(packed, 27)
+    ks, vs, cs = t.export()
+    assert ks.size == facts["dbg_entries"]
+    k = 27
+    x = ks.copy()
+    rc = np.zeros_like(x)
+    for _ in range(k):
+        d = x % np.uint64(5)
+        x //= np.uint64(5)
+        rc = rc * np.uint64(5) + np.where(d == 4, d, np.uint64(3) - d)
+    pos = np.searchsorted(ks, rc)
+    assert np.array_equal(ks[pos], rc)
+    assert np.array_equal(cs[pos], cs)
+
+
+def test_cfg2_rdbg_graph_rows(ctx):
+    engine, graph, facts, data, packed = ctx
+    t, _, _ = engine.build_dbg_partitioned(packed, 27)
+    rd = t.select_rdbg()
+    rk, _ = rd.rdbg_export()
+    assert rk.size == facts["rdbg_entries"]
+    assert hashlib.sha256("\n".join("%d" % v for v in rk.tolist()).encode()).hexdigest() == facts["rdbg_sha256"]
+    res = graph.seq2graph_device(packed, rd, 27)
+    lines = res.xyz_lines()
+    assert len(lines) == facts["xyz_edges"]
+    assert hashlib.sha256("\n".join(lines).encode()).hexdigest() == facts["xyz_fileorder_sha256"]
+    assert res.graph.n_components == facts["n_components"]
+    assert res.rows(packed, data) == [tuple(r) for r in facts["rows"]]
