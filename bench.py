@@ -248,6 +248,7 @@ def main():
 
     # end to end through the public API, host buffers: H2D of the FASTA bytes, build, D2H of the table statistics
     def step_e2e():
+        builder.begin()                                   # table clear overlaps the H2D copy
         d = host.to("cuda", non_blocking=True)
         p = engine.PackedSeqs(d)
         tt = builder.build(p, n_rec)

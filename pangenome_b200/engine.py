@@ -66,22 +66,33 @@ class PackedSeqs:
         self.amb = torch.empty(words, dtype=torch.int32, device=dev)
         ws_bytes = int(L.pg_fasta_workspace_bytes(nbytes))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        self.d_counts = torch.zeros(4, dtype=torch.int64, device=dev)
+        # counts, seq_off and hdr_off share ONE device buffer so the record index comes back in one D2H
         while True:
-            self.d_hdr_off = torch.empty(cap_records + 1, dtype=torch.int64, device=dev)
-            self.d_seq_off = torch.empty(cap_records + 2, dtype=torch.int64, device=dev)
+            idx = torch.empty(4 + (cap_records + 2) + (cap_records + 1), dtype=torch.int64, device=dev)
+            self.d_counts = idx[:4]
+            self.d_seq_off = idx[4:4 + cap_records + 2]
+            self.d_hdr_off = idx[4 + cap_records + 2:]
             check(L.pg_fasta_scan_pack(_ptr(d_fasta) if nbytes else None, nbytes, _ptr(self.pk2), _ptr(self.amb),
                                        nbytes, _ptr(self.d_hdr_off), _ptr(self.d_seq_off), cap_records,
                                        _ptr(self.d_counts), _ptr(ws), ws_bytes, _stream()), "pg_fasta_scan_pack")
-            counts = self.d_counts.cpu().numpy()     # synchronises: the host needs the record index
+            if cap_records <= 1 << 16:
+                h = idx.cpu().numpy()                    # synchronises: the host needs the record index
+                counts = h[:4]
+            else:
+                h = None
+                counts = self.d_counts.cpu().numpy()
             self.n_rec = int(counts[0])
             if self.n_rec <= cap_records:
                 break
             cap_records = next_pow2(self.n_rec + 1)
         self.n_bases = int(counts[1])
         self.n_newlines = int(counts[2])
-        self.seq_off = self.d_seq_off[:self.n_rec + 1].cpu().numpy()
-        self.hdr_off = self.d_hdr_off[:self.n_rec].cpu().numpy()
+        if h is not None:
+            self.seq_off = h[4:4 + self.n_rec + 1].copy()
+            self.hdr_off = h[4 + cap_records + 2:4 + cap_records + 2 + self.n_rec].copy()
+        else:
+            self.seq_off = self.d_seq_off[:self.n_rec + 1].cpu().numpy()
+            self.hdr_off = self.d_hdr_off[:self.n_rec].cpu().numpy()
         self.launches = 3
 
     @property
@@ -329,14 +340,23 @@ class TwoPhaseBuilder:
         self.launches_per_build = 4          # clear, count_short, k2a_partition, k3_insert_records
         self.side = torch.cuda.Stream(device=device)   # the table clear (DRAM-write bound) overlaps K2a (ALU bound)
 
+    def begin(self):
+        """Start clearing the table on the side stream now (e.g. before the H2D copy of the next
+        input); the following build() then skips its own clear."""
+        st = torch.cuda.current_stream()
+        self.side.wait_stream(st)            # whoever still reads the previous table finishes first
+        with torch.cuda.stream(self.side):
+            self.table.clear()
+        self._begun = True
+
     def build(self, packed, n_rec, ev=None):
         """Enqueue clear + K2a + K3 (no synchronisation).  ``ev`` = optional dict receiving CUDA
         event pairs around the two kernels."""
         t, b, L = self.table, self.buckets, self.L
         st = torch.cuda.current_stream()
-        self.side.wait_stream(st)            # whoever still reads the previous table finishes first
-        with torch.cuda.stream(self.side):
-            t.clear()
+        if not getattr(self, "_begun", False):
+            self.begin()
+        self._begun = False
         if n_rec == 0:
             st.wait_stream(self.side)
             return t
