@@ -127,8 +127,10 @@ int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_a
  *                                            of ANY power-of-two table the key's home slot lies in)
  *   d_records holds 2^(owner_bits+sub_bits) buckets of part_cap records each; d_part_counts[b]
  *   = records produced for bucket b (records beyond part_cap are dropped: compare and fall back).
- * pg_insert_records: upsert the records of n_seg segments [seg_off[i], seg_off[i]+seg_cnt[i]) of
- *   d_records, segment after segment, so that the table region being updated stays in L2.
+ * pg_insert_records: upsert the records of n_regions x n_src segments
+ *   [seg_off[b*n_src+j], +seg_cnt[b*n_src+j]) of d_records (record units), region after region
+ *   (n_src = source ranks x pipeline chunks that contributed to a region; 1 on a single GPU), so
+ *   that the table region being updated stays in L2.
  *   Replaces the same reference lines as pg_kmer_insert; the all-to-all between the two calls is
  *   the host's (torch.distributed / NCCL).
  */
@@ -136,7 +138,7 @@ int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *
                       int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
                       uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream);
 int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
-                      const int64_t *d_seg_cnt, int n_seg, pg_stream_t stream);
+                      const int64_t *d_seg_cnt, int n_regions, int n_src, pg_stream_t stream);
 
 /* ---- table read-out ---------------------------------------------------------
  * pg_table_count   : fills PG_STAT_USED / PG_STAT_ENTRIES in t->d_stats.

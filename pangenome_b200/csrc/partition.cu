@@ -198,35 +198,59 @@ k2a_partition(PartArgs a) {
     }
 }
 
-// K3: insert the records of a list of segments, in list order (the grid sweeps the segments together,
-// so the table region under update stays L2-resident).  Four records per thread are in flight at a
-// time: record loads (evict-first in L2), then the four home-slot loads, then the atomics.
-template <int K3_ILP, bool EVICT>
+// K3: insert update records region by region.  The records of table region b arrive as n_src
+// segments (one per source rank / pipeline chunk): seg_off/seg_cnt are [n_regions][n_src] in
+// region-major order and the threads of the whole grid stride over the CONCATENATION of a region's
+// segments, so a region is swept once with every thread busy while its 8 MB of slots sit in L2.
+// The record of the next iteration is loaded before the current one is processed (the record
+// stream comes from HBM, the slots from L2: the two latencies overlap instead of adding up).
+constexpr int K3_MAX_SRC = 64;
+__device__ __forceinline__ bool k3_fetch(const uint4 *__restrict__ records, const int64_t *__restrict__ s_off,
+                                         const int64_t *__restrict__ s_cum, int n_src, int64_t i, uint4 &r) {
+    // s_cum[j] = records of sources < j in this region (s_cum[n_src] = total)
+    if (i >= s_cum[n_src]) return false;
+    int j = 0;
+    while (j + 1 < n_src && i >= s_cum[j + 1]) j++;
+    r = pg_ld_stream(records + s_off[j] + (i - s_cum[j]));
+    return true;
+}
 __global__ void __launch_bounds__(256)
 k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
-                  const int64_t *__restrict__ seg_cnt, int n_seg) {
+                  const int64_t *__restrict__ seg_cnt, int n_regions, int n_src) {
+    __shared__ int64_t s_off[2][K3_MAX_SRC];
+    __shared__ int64_t s_cum[2][K3_MAX_SRC + 1];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const uint64_t pol = pg_policy_evict_first();
     uint32_t n_claimed = 0;
-    for (int s = 0; s < n_seg; s++) {
-        const int64_t off = __ldg(seg_off + s), cnt = __ldg(seg_cnt + s);
-        for (int64_t i = i0; i < cnt; i += stride * K3_ILP) {
-            uint4 r[K3_ILP]; uint64_t home[K3_ILP], ck[K3_ILP], cv[K3_ILP];
-#pragma unroll
-            for (int u = 0; u < K3_ILP; u++)
-                if (i + u * stride < cnt) r[u] = EVICT ? pg_ld_stream_l2first(records + off + i + u * stride, pol) : pg_ld_stream(records + off + i + u * stride);
-#pragma unroll
-            for (int u = 0; u < K3_ILP; u++)
-                if (i + u * stride < cnt) {
-                    home[u] = tv_home(t, (uint64_t)r[u].x | ((uint64_t)r[u].y << 32));
-                    pg_ld_slot(t.slots + 2 * home[u], ck[u], cv[u]);
-                }
-#pragma unroll
-            for (int u = 0; u < K3_ILP; u++)
-                if (i + u * stride < cnt)
-                    table_upsert_from(t, home[u], ck[u], cv[u], (uint64_t)r[u].x | ((uint64_t)r[u].y << 32), r[u].z, r[u].w, n_claimed);
+    auto load_region = [&](int b, int buf) {
+        if (threadIdx.x == 0) {
+            int64_t c = 0;
+            for (int j = 0; j < n_src; j++) {
+                s_off[buf][j] = __ldg(seg_off + (int64_t)b * n_src + j);
+                s_cum[buf][j] = c;
+                c += __ldg(seg_cnt + (int64_t)b * n_src + j);
+            }
+            s_cum[buf][n_src] = c;
         }
+    };
+    load_region(0, 0);
+    __syncthreads();
+    uint4 r;
+    bool have = k3_fetch(records, s_off[0], s_cum[0], n_src, i0, r);
+    for (int b = 0; b < n_regions; b++) {
+        const int buf = b & 1;
+        if (b + 1 < n_regions) load_region(b + 1, buf ^ 1);
+        __syncthreads();
+        int64_t i = i0;
+        while (have) {
+            const uint4 cur = r;
+            i += stride;
+            have = k3_fetch(records, s_off[buf], s_cum[buf], n_src, i, r);          // prefetch within the region
+            const uint64_t key = (uint64_t)cur.x | ((uint64_t)cur.y << 32);
+            table_upsert(t, key, cur.z, cur.w, n_claimed);
+        }
+        if (b + 1 < n_regions) have = k3_fetch(records, s_off[buf ^ 1], s_cum[buf ^ 1], n_src, i0, r);   // first record of the next region
+        __syncthreads();
     }
     publish_claims(t, n_claimed);
 }
@@ -278,27 +302,18 @@ extern "C" int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const
 }
 
 extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
-                                 const int64_t *d_seg_cnt, int n_seg, pg_stream_t stream_) {
+                                 const int64_t *d_seg_cnt, int n_regions, int n_src, pg_stream_t stream_) {
     if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)))
         return pg_fail(PG_ERR_INVALID, "pg_insert_records: bad table");
-    if (n_seg < 0 || (n_seg > 0 && (!d_records || !d_seg_off || !d_seg_cnt))) return pg_fail(PG_ERR_INVALID, "pg_insert_records: bad arguments");
-    if (n_seg == 0) return PG_OK;
+    if (n_regions < 0 || n_src < 1 || n_src > K3_MAX_SRC || (n_regions > 0 && (!d_records || !d_seg_off || !d_seg_cnt)))
+        return pg_fail(PG_ERR_INVALID, "pg_insert_records: bad arguments (n_src must be 1..%d)", K3_MAX_SRC);
+    if (n_regions == 0) return PG_OK;
     if (reinterpret_cast<uintptr_t>(d_records) & 15) return pg_fail(PG_ERR_INVALID, "pg_insert_records: records must be 16-byte aligned");
     TableView tv = make_view(t);
-    static int ilp = -1, evict = -1, gmul = -1;
-    if (ilp < 0) {
-        const char *e = getenv("PG_K3_ILP"); ilp = e ? atoi(e) : 1;
-        e = getenv("PG_K3_EVICT"); evict = e ? atoi(e) : 0;
-        e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 8;
-    }
+    static int gmul = -1;
+    if (gmul < 0) { const char *e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 8; }
     int grid = pg_num_sms() * gmul;
-    const uint4 *rec = reinterpret_cast<const uint4 *>(d_records);
-    cudaStream_t st = (cudaStream_t)stream_;
-#define K3_LAUNCH(I, E) k3_insert_records<I, E><<<grid, 256, 0, st>>>(tv, rec, d_seg_off, d_seg_cnt, n_seg)
-    if (ilp == 1) { if (evict) K3_LAUNCH(1, true); else K3_LAUNCH(1, false); }
-    else if (ilp == 2) { if (evict) K3_LAUNCH(2, true); else K3_LAUNCH(2, false); }
-    else { if (evict) K3_LAUNCH(4, true); else K3_LAUNCH(4, false); }
-#undef K3_LAUNCH
+    k3_insert_records<<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

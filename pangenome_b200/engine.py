@@ -310,7 +310,7 @@ def build_dbg_partitioned(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=No
         check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
         buckets = partition_kmers(packed, k, mode, n_rec, 0, sub_bits, buckets=buckets)
         check(L.pg_insert_records(ctypes.byref(t.c), _ptr(buckets.records), _ptr(buckets.seg_off), _ptr(buckets.counts),
-                                  buckets.n_parts, _stream()), "pg_insert_records")
+                                  buckets.n_parts, 1, _stream()), "pg_insert_records")
         worst = int(buckets.counts.max().item())           # synchronises
         if worst > buckets.part_cap:
             t2, n_rec = build_dbg(packed, k, rc=rc, Ns=Ns, mode=mode, capacity=cap)
@@ -369,7 +369,7 @@ class TwoPhaseBuilder:
         check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
         if ev is not None:
             e[1].record(st)
-        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, _stream()),
+        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, _stream()),
               "pg_insert_records")
         if ev is not None:
             e[2].record(st)

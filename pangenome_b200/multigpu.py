@@ -69,10 +69,9 @@ def segment_plan(recv_counts, part_cap):
 class DistributedBuilder:
     """Reusable buffers for the distributed build of same-sized shards.
 
-    The rank's positions are cut into ``chunks`` ranges that flow through a three-stage pipeline:
-    K2a(c) on the compute stream, the all-to-all of chunk c on a communication stream, K3(c) on
-    the compute stream - so the NVLink exchange of one chunk overlaps the extraction of the next
-    and the insertion of the previous one."""
+    The rank's positions are cut into ``chunks`` ranges: K2a(c) runs on the compute stream while
+    the all-to-all of chunk c-1 runs on a communication stream; one K3 launch then sweeps the
+    table region by region over everything that arrived (world x chunks segments per region)."""
 
     def __init__(self, k, n_positions_local, world, rank, device="cuda", sub_bytes=8 << 20, chunks=4):
         from . import engine
@@ -90,24 +89,35 @@ class DistributedBuilder:
         cap = engine.next_pow2(max(1024, int(per_rank / 0.5) + 1))
         self.table = engine.DbgTable(cap, self.k, _lib.PG_MODE_CANONICAL, device=device)
         self.sub_bits = engine.sub_bits_for(cap, sub_bytes)
-        self.n_sub = 1 << self.sub_bits
-        n_parts = world * self.n_sub
+        self.n_sub = n_sub = 1 << self.sub_bits
+        n_parts = world * n_sub
         # the largest shard decides the block size every rank uses (blocks must be equal-sized)
         m = torch.tensor([n_positions_local], dtype=torch.int64, device=device)
         if world > 1:
             dist.all_reduce(m, op=dist.ReduceOp.MAX)
         per_chunk = (int(m.item()) + self.chunks - 1) // self.chunks + 4096
-        self.part_cap = int(per_chunk / n_parts * 1.25) + 2048
-        self.buckets = [engine.RecordBuckets(n_parts, self.part_cap, device) for _ in range(self.chunks)]
-        self.recv = [torch.empty_like(b.records) for b in self.buckets] if world > 1 else [None] * self.chunks
+        self.part_cap = pc = int(per_chunk / n_parts * 1.25) + 2048
+        C = self.chunks
+        self.send = torch.empty(C, n_parts * pc * 2, dtype=torch.int64, device=device)      # [chunk][owner][sub][part_cap] records
+        self.send_counts = torch.zeros(C, n_parts, dtype=torch.int64, device=device)
+        self.recv = torch.empty_like(self.send) if world > 1 else self.send                  # [chunk][source][sub][part_cap]
+        self.recv_counts = torch.zeros_like(self.send_counts) if world > 1 else self.send_counts
+        # static segment offsets, region-major: segment (b, c, s) = records of source s, chunk c, for table region b
+        c_i = torch.arange(C, dtype=torch.int64, device=device).view(1, C, 1)
+        s_i = torch.arange(world, dtype=torch.int64, device=device).view(1, 1, world)
+        b_i = torch.arange(n_sub, dtype=torch.int64, device=device).view(n_sub, 1, 1)
+        self.seg_off = (((c_i * world + s_i) * n_sub + b_i) * pc).reshape(-1).contiguous()
+        self.seg_cnt = torch.zeros(n_sub * C * world, dtype=torch.int64, device=device)
         self.comm = torch.cuda.Stream(device=device)
         self.side = torch.cuda.Stream(device=device)
-        self.launches_per_build = 2 + 2 * self.chunks      # clear, count_short, chunks x (K2a, K3)
+        self.launches_per_build = 3 + self.chunks      # clear, count_short, chunks x K2a, K3
 
     def build(self, packed, n_rec, ev=None):
         eng, L, t = self.engine, self.L, self.table
+        C, W, n_sub = self.chunks, self.world, self.n_sub
         st = torch.cuda.current_stream()
         self.side.wait_stream(st)
+        self.comm.wait_stream(st)
         with torch.cuda.stream(self.side):
             t.clear()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if ev is not None else None
@@ -116,54 +126,43 @@ class DistributedBuilder:
         g_begin = int(packed.seq_off[0]) if n_rec > 0 else 0
         g_end = int(packed.seq_off[n_rec]) if n_rec > 0 else 0
         span = g_end - g_begin
-        step = ((span + self.chunks - 1) // self.chunks + 2047) // 2048 * 2048 if span > 0 else 0
+        step = ((span + C - 1) // C + 2047) // 2048 * 2048 if span > 0 else 0
         desc = _lib.PgTable(None, 2, None, _lib.PG_MODE_CANONICAL, self.k)
-        plans = []
-        part_done = []
-        for c in range(self.chunks):
-            b = self.buckets[c]
+        for c in range(C):
             lo = min(g_begin + c * step, g_end)
             hi = min(lo + step, g_end)
-            # NB every rank runs every chunk (empty ranges produce empty buckets): the collective must match
+            # NB every rank runs every chunk (empty ranges produce empty buckets): the collectives must match
             eng.check(L.pg_kmer_partition(ctypes.byref(desc), eng._ptr(packed.pk2), eng._ptr(packed.amb),
                                           eng._ptr(packed.d_seq_off), n_rec, lo, hi, self.owner_bits, self.sub_bits,
-                                          eng._ptr(b.records), b.part_cap, eng._ptr(b.counts), eng._stream()),
+                                          eng._ptr(self.send[c]), self.part_cap, eng._ptr(self.send_counts[c]), eng._stream()),
                       "pg_kmer_partition")
-            done = torch.cuda.Event()
-            done.record(st)
-            part_done.append(done)
-            # ---- exchange of chunk c on the communication stream
-            if self.world > 1:
+            if W > 1:
+                done = torch.cuda.Event()
+                done.record(st)
                 self.comm.wait_event(done)
-                with torch.cuda.stream(self.comm):
-                    recv_counts = exchange_blocks(b.counts.view(self.world, self.n_sub), self.world)
-                    dist.all_to_all_single(self.recv[c].view(-1), b.records.view(-1)) if dist.get_backend() == "nccl" \
-                        else self.recv[c].copy_(exchange_blocks(b.records.view(self.world, -1), self.world).view(-1))
-                    seg_off, seg_cnt = segment_plan(recv_counts, b.part_cap)
-                    arrived = torch.cuda.Event()
-                    arrived.record(self.comm)
-                plans.append((self.recv[c], seg_off, seg_cnt, arrived))
-            else:
-                seg_off, seg_cnt = segment_plan(b.counts.view(1, self.n_sub), b.part_cap)
-                plans.append((b.records, seg_off, seg_cnt, None))
+                with torch.cuda.stream(self.comm):       # exchange of chunk c overlaps K2a of chunk c+1
+                    if dist.get_backend() == "nccl":
+                        dist.all_to_all_single(self.recv_counts[c], self.send_counts[c])
+                        dist.all_to_all_single(self.recv[c], self.send[c])
+                    else:
+                        self.recv_counts[c].copy_(exchange_blocks(self.send_counts[c].view(W, n_sub), W).view(-1))
+                        self.recv[c].copy_(exchange_blocks(self.send[c].view(W, -1), W).view(-1))
+        st.wait_stream(self.comm)
         st.wait_stream(self.side)            # K3 needs the cleared table
         if n_rec > 0:
             eng.check(L.pg_count_short(ctypes.byref(t.c), eng._ptr(packed.d_seq_off), n_rec, g_begin, g_end, eng._stream()),
                       "pg_count_short")
-        for recv, seg_off, seg_cnt, arrived in plans:
-            if arrived is not None:
-                st.wait_event(arrived)
-            eng.check(L.pg_insert_records(ctypes.byref(t.c), eng._ptr(recv), eng._ptr(seg_off), eng._ptr(seg_cnt),
-                                          int(seg_off.numel()), eng._stream()), "pg_insert_records")
+        # counts [chunk][source][sub] -> region-major [sub][chunk][source]
+        self.seg_cnt.copy_(self.recv_counts.view(C, W, n_sub).permute(2, 0, 1).reshape(-1))
+        eng.check(L.pg_insert_records(ctypes.byref(t.c), eng._ptr(self.recv), eng._ptr(self.seg_off), eng._ptr(self.seg_cnt),
+                                      n_sub, C * W, eng._stream()), "pg_insert_records")
         if e:
             e[1].record(st)
             ev.setdefault("build", []).append((e[0], e[1]))
-        self._last = plans                     # keep the plan tensors alive until the stream has consumed them
         return t
 
     def verify(self):
-        worst = max(int(b.counts.max().item()) for b in self.buckets)
-        if worst > self.part_cap:
+        if int(self.send_counts.max().item()) > self.part_cap:
             raise _lib.PgError("record bucket overflow on rank %d" % self.rank)
         if self.table.overflowed():
             raise _lib.PgError("dBG table overflow on rank %d" % self.rank)
@@ -296,7 +295,7 @@ def bench(args, world, rank, local, ClockSampler=None):
                     "h2d_bytes_per_step": int(host.numel()) * world, "d2h_bytes_per_step": (8 * 8 + 4 * 8 + 16 * (n_rec + 1)) * world},
             "gpu_launches": (3 + builder.launches_per_build) * args.steps * world,
             "clocks": clk,
-            "stages_ms": {"partition+exchange+insert (pipelined, %d chunks)" % builder.chunks: ins_ms},
+            "stages_ms": {"K2a x %d chunks overlapped with the all-to-all, then K3" % builder.chunks: ins_ms},
             "exchange_bytes_per_gpu_per_step": block_bytes * (world - 1),
             "roofline": {"kernel": "k2a_partition + all-to-all + k3_insert_records (pipelined)", "bound": "hbm",
                          "achieved": alg / (ins_ms * 1e-3) / 1e9, "peak": peak,
