@@ -205,52 +205,44 @@ k2a_partition(PartArgs a) {
 // The record of the next iteration is loaded before the current one is processed (the record
 // stream comes from HBM, the slots from L2: the two latencies overlap instead of adding up).
 constexpr int K3_MAX_SRC = 64;
-__device__ __forceinline__ bool k3_fetch(const uint4 *__restrict__ records, const int64_t *__restrict__ s_off,
-                                         const int64_t *__restrict__ s_cum, int n_src, int64_t i, uint4 &r) {
-    // s_cum[j] = records of sources < j in this region (s_cum[n_src] = total)
-    if (i >= s_cum[n_src]) return false;
-    int j = 0;
-    while (j + 1 < n_src && i >= s_cum[j + 1]) j++;
-    r = pg_ld_stream(records + s_off[j] + (i - s_cum[j]));
-    return true;
+// record i of region b's concatenated segments (false past the end).  No shared memory and no
+// barriers: every warp walks the regions at its own pace, the segment table is read through L1.
+__device__ __forceinline__ bool k3_fetch(const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
+                                         const int64_t *__restrict__ seg_cnt, int n_src, int b, int64_t i, uint4 &r) {
+    const int64_t *off = seg_off + (int64_t)b * n_src, *cnt = seg_cnt + (int64_t)b * n_src;
+    for (int j = 0; j < n_src; j++) {
+        int64_t c = __ldg(cnt + j);
+        if (i < c) { r = pg_ld_stream(records + __ldg(off + j) + i); return true; }
+        i -= c;
+    }
+    return false;
 }
+template <bool PREFETCH>
 __global__ void __launch_bounds__(256)
 k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
                   const int64_t *__restrict__ seg_cnt, int n_regions, int n_src) {
-    __shared__ int64_t s_off[2][K3_MAX_SRC];
-    __shared__ int64_t s_cum[2][K3_MAX_SRC + 1];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     uint32_t n_claimed = 0;
-    auto load_region = [&](int b, int buf) {
-        if (threadIdx.x == 0) {
-            int64_t c = 0;
-            for (int j = 0; j < n_src; j++) {
-                s_off[buf][j] = __ldg(seg_off + (int64_t)b * n_src + j);
-                s_cum[buf][j] = c;
-                c += __ldg(seg_cnt + (int64_t)b * n_src + j);
+    if (PREFETCH) {
+        uint4 r;
+        bool have = k3_fetch(records, seg_off, seg_cnt, n_src, 0, i0, r);
+        for (int b = 0; b < n_regions; b++) {
+            int64_t i = i0;
+            while (have) {
+                const uint4 cur = r;
+                i += stride;
+                have = k3_fetch(records, seg_off, seg_cnt, n_src, b, i, r);
+                table_upsert(t, (uint64_t)cur.x | ((uint64_t)cur.y << 32), cur.z, cur.w, n_claimed);
             }
-            s_cum[buf][n_src] = c;
+            if (b + 1 < n_regions) have = k3_fetch(records, seg_off, seg_cnt, n_src, b + 1, i0, r);
         }
-    };
-    load_region(0, 0);
-    __syncthreads();
-    uint4 r;
-    bool have = k3_fetch(records, s_off[0], s_cum[0], n_src, i0, r);
-    for (int b = 0; b < n_regions; b++) {
-        const int buf = b & 1;
-        if (b + 1 < n_regions) load_region(b + 1, buf ^ 1);
-        __syncthreads();
-        int64_t i = i0;
-        while (have) {
-            const uint4 cur = r;
-            i += stride;
-            have = k3_fetch(records, s_off[buf], s_cum[buf], n_src, i, r);          // prefetch within the region
-            const uint64_t key = (uint64_t)cur.x | ((uint64_t)cur.y << 32);
-            table_upsert(t, key, cur.z, cur.w, n_claimed);
+    } else {
+        for (int b = 0; b < n_regions; b++) {
+            uint4 r;
+            for (int64_t i = i0; k3_fetch(records, seg_off, seg_cnt, n_src, b, i, r); i += stride)
+                table_upsert(t, (uint64_t)r.x | ((uint64_t)r.y << 32), r.z, r.w, n_claimed);
         }
-        if (b + 1 < n_regions) have = k3_fetch(records, s_off[buf ^ 1], s_cum[buf ^ 1], n_src, i0, r);   // first record of the next region
-        __syncthreads();
     }
     publish_claims(t, n_claimed);
 }
@@ -310,10 +302,16 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
     if (n_regions == 0) return PG_OK;
     if (reinterpret_cast<uintptr_t>(d_records) & 15) return pg_fail(PG_ERR_INVALID, "pg_insert_records: records must be 16-byte aligned");
     TableView tv = make_view(t);
-    static int gmul = -1;
-    if (gmul < 0) { const char *e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 8; }
+    static int gmul = -1, prefetch = -1;
+    if (gmul < 0) {
+        const char *e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 8;
+        e = getenv("PG_K3_PREFETCH"); prefetch = e ? atoi(e) : 0;
+    }
     int grid = pg_num_sms() * gmul;
-    k3_insert_records<<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src);
+    if (prefetch)
+        k3_insert_records<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src);
+    else
+        k3_insert_records<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
