@@ -137,6 +137,21 @@ int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_a
 int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                       int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
                       uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream);
+/* Fused extraction + exchange over NVLink peer memory: like pg_kmer_partition, but bucket
+ * (owner, sub) is stored straight into rank `owner`'s receive buffer (d_peer_bases[owner], a
+ * peer-mapped pointer; the own rank's entry is its own buffer) at slice
+ * [my_rank][sub][part_cap] - the layout an all-to-all of the padded buckets would produce.
+ * d_part_counts[(owner << sub_bits) | sub] still counts locally; the host exchanges that small
+ * matrix (which is also the barrier that orders the peer stores before K3).
+ * pg_peer_alloc / open / close / free: CUDA IPC plumbing for those buffers (64-byte handle). */
+int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                          int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
+                          uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
+                          pg_stream_t stream);
+int pg_peer_alloc(int64_t bytes, void **d_ptr, uint8_t *handle64);
+int pg_peer_open(const uint8_t *handle64, void **d_ptr);
+int pg_peer_close(void *d_ptr);
+int pg_peer_free(void *d_ptr);
 int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
                       const int64_t *d_seg_cnt, int n_regions, int n_src, pg_stream_t stream);
 

@@ -14,6 +14,7 @@
 // atomicAdd per bucket per tile to reserve space, reorder through an index permutation) so global
 // stores are coalesced 16-byte runs per bucket.
 #include <stdlib.h>
+#include <string.h>
 #include "table_dev.cuh"
 
 namespace {
@@ -30,6 +31,9 @@ struct PartArgs {
     int64_t t_first, n_tiles;
     int sub_bits, owner_bits; int n_parts;
     uint4 *records; int64_t part_cap; unsigned long long *part_counts;
+    // fused exchange: when `peers` is set, bucket (owner, sub) is written straight into rank `owner`'s
+    // receive buffer over NVLink (peer-mapped pointer), at the slice reserved for source rank `my_rank`
+    uint4 *const *peers; int my_rank;
 };
 
 __device__ __forceinline__ uint32_t part_of(const PartArgs &a, uint64_t key) {
@@ -193,7 +197,15 @@ k2a_partition(PartArgs a) {
             uint32_t i = s_perm[o];
             uint32_t pid = s_pid[i];
             unsigned long long dst = s_base[pid] + (o - s_off[pid]);
-            if ((int64_t)dst < a.part_cap) pg_st_stream_l2first(a.records + (int64_t)pid * a.part_cap + (int64_t)dst, s_rec[i], pol);
+            if ((int64_t)dst < a.part_cap) {
+                if (a.peers) {     // [source rank][sub][part_cap] in the owner's memory: the layout an all-to-all would produce
+                    const uint32_t owner = pid >> a.sub_bits, sub = pid & ((1u << a.sub_bits) - 1u);
+                    uint4 *base = a.peers[owner];
+                    base[(((int64_t)a.my_rank << a.sub_bits) + sub) * a.part_cap + (int64_t)dst] = s_rec[i];
+                } else {
+                    pg_st_stream_l2first(a.records + (int64_t)pid * a.part_cap + (int64_t)dst, s_rec[i], pol);
+                }
+            }
         }
     }
 }
@@ -254,12 +266,13 @@ int part_smem_bytes(int mode, int n_parts) {
 
 }  // namespace
 
-extern "C" int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
-                                 int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
-                                 uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream_) {
+static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                            int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
+                            uint64_t *d_records, uint64_t *const *d_peers, int my_rank, int64_t part_cap,
+                            int64_t *d_part_counts, pg_stream_t stream_) {
     if (!t || t->k < 1 || t->k > 27 || t->mode < 0 || t->mode > 2)
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: bad table descriptor (only mode and k are used)");
-    if (!d_pk2 || !d_amb || !d_seq_off || !d_records || !d_part_counts || n_rec < 0 || g_begin < 0 || g_end < g_begin || part_cap < 1)
+    if (!d_pk2 || !d_amb || !d_seq_off || (!d_records && !d_peers) || !d_part_counts || n_rec < 0 || g_begin < 0 || g_end < g_begin || part_cap < 1)
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: bad arguments");
     if (owner_bits < 0 || owner_bits > 6 || sub_bits < 0 || sub_bits > 10 || (1 << (owner_bits + sub_bits)) > KP_MAX_PARTS)
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: owner_bits/sub_bits out of range");
@@ -273,6 +286,7 @@ extern "C" int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const
     a.t_first = g_begin / KP_TILE; a.n_tiles = (g_end + KP_TILE - 1) / KP_TILE - a.t_first;
     a.sub_bits = sub_bits; a.owner_bits = owner_bits; a.n_parts = n_parts;
     a.records = reinterpret_cast<uint4 *>(d_records); a.part_cap = part_cap;
+    a.peers = reinterpret_cast<uint4 *const *>(d_peers); a.my_rank = my_rank;
     a.part_counts = reinterpret_cast<unsigned long long *>(d_part_counts);
     int smem = part_smem_bytes(t->mode, n_parts);
     int per_sm = 200 * 1024 / smem; if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
@@ -292,6 +306,43 @@ extern "C" int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
+
+extern "C" int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                                 int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
+                                 uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream_) {
+    return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, owner_bits, sub_bits, d_records, nullptr, 0,
+                            part_cap, d_part_counts, stream_);
+}
+
+extern "C" int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                                     int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
+                                     uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
+                                     pg_stream_t stream_) {
+    if (!d_peer_bases || my_rank < 0 || my_rank >= (1 << owner_bits))
+        return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p: bad peer table / rank");
+    return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, owner_bits, sub_bits, nullptr, d_peer_bases, my_rank,
+                            part_cap, d_part_counts, stream_);
+}
+
+// ---- peer memory for the fused exchange (CUDA IPC; one process per GPU) ------------------------
+extern "C" int pg_peer_alloc(int64_t bytes, void **d_ptr, uint8_t *handle64) {
+    if (bytes <= 0 || !d_ptr || !handle64) return pg_fail(PG_ERR_INVALID, "pg_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    PG_CUDA(cudaMalloc(d_ptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    PG_CUDA(cudaIpcGetMemHandle(&h, *d_ptr));
+    memcpy(handle64, &h, 64);
+    return PG_OK;
+}
+extern "C" int pg_peer_open(const uint8_t *handle64, void **d_ptr) {
+    if (!handle64 || !d_ptr) return pg_fail(PG_ERR_INVALID, "pg_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    PG_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PG_OK;
+}
+extern "C" int pg_peer_close(void *d_ptr) { PG_CUDA(cudaIpcCloseMemHandle(d_ptr)); return PG_OK; }
+extern "C" int pg_peer_free(void *d_ptr) { PG_CUDA(cudaFree(d_ptr)); return PG_OK; }
 
 extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
                                  const int64_t *d_seg_cnt, int n_regions, int n_src, pg_stream_t stream_) {

@@ -147,8 +147,13 @@ class DistributedBuilder:
                     else:
                         self.recv_counts[c].copy_(exchange_blocks(self.send_counts[c].view(W, n_sub), W).view(-1))
                         self.recv[c].copy_(exchange_blocks(self.send[c].view(W, -1), W).view(-1))
+        if e:
+            e_part = torch.cuda.Event(enable_timing=True); e_part.record(st)
+            e_comm = torch.cuda.Event(enable_timing=True); e_comm.record(self.comm)
         st.wait_stream(self.comm)
         st.wait_stream(self.side)            # K3 needs the cleared table
+        if e:
+            e_k3 = torch.cuda.Event(enable_timing=True); e_k3.record(st)
         if n_rec > 0:
             eng.check(L.pg_count_short(ctypes.byref(t.c), eng._ptr(packed.d_seq_off), n_rec, g_begin, g_end, eng._stream()),
                       "pg_count_short")
@@ -159,6 +164,9 @@ class DistributedBuilder:
         if e:
             e[1].record(st)
             ev.setdefault("build", []).append((e[0], e[1]))
+            ev.setdefault("k2a_all_chunks", []).append((e[0], e_part))
+            ev.setdefault("until_exchange_done", []).append((e[0], e_comm))
+            ev.setdefault("k3", []).append((e_k3, e[1]))
         return t
 
     def verify(self):
@@ -166,6 +174,125 @@ class DistributedBuilder:
             raise _lib.PgError("record bucket overflow on rank %d" % self.rank)
         if self.table.overflowed():
             raise _lib.PgError("dBG table overflow on rank %d" % self.rank)
+
+
+class PeerBuilder:
+    """Distributed build with the exchange FUSED into K2a: every rank owns a receive buffer
+    [source rank][sub][part_cap] that its peers map through CUDA IPC; K2a's write-out stores each
+    bucket straight into its owner's buffer over NVLink (pg_kmer_partition_p2p), so there is no
+    staging copy and no separate all-to-all of the records.  The only collective left is the
+    all-to-all of the small count matrix, which doubles as the barrier that orders the peer stores
+    before K3.  Two receive buffers alternate between builds: a rank that races ahead into the
+    next build cannot overwrite what a slower peer's K3 is still reading."""
+
+    def __init__(self, k, n_positions_local, world, rank, device="cuda", sub_bytes=8 << 20):
+        from . import engine
+        self.engine = engine
+        self.L = L = _lib.load()
+        self.k, self.world, self.rank = int(min(max(1, k), 27)), world, rank
+        self.owner_bits = log2_exact(world)
+        n_glob = torch.tensor([n_positions_local], dtype=torch.int64, device=device)
+        m = torch.tensor([n_positions_local], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(n_glob, op=dist.ReduceOp.SUM)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        per_rank = (int(n_glob.item()) + world - 1) // world
+        cap = engine.next_pow2(max(1024, int(per_rank / 0.5) + 1))
+        self.table = engine.DbgTable(cap, self.k, _lib.PG_MODE_CANONICAL, device=device)
+        self.sub_bits = engine.sub_bits_for(cap, sub_bytes)
+        self.n_sub = n_sub = 1 << self.sub_bits
+        n_parts = world * n_sub
+        self.part_cap = pc = int(int(m.item()) / n_parts * 1.25) + 4096
+        self.buf_bytes = world * n_sub * pc * 16
+        self.own, self.peer_tables, self._opened = [], [], []
+        for _ in range(2):
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(L.pg_peer_alloc(self.buf_bytes, ctypes.byref(ptr), handle), "pg_peer_alloc")
+            handles = [None] * world
+            if world > 1:
+                dist.all_gather_object(handles, handle.raw)
+            addrs = []
+            for r in range(world):
+                if r == rank:
+                    addrs.append(ptr.value)
+                else:
+                    q = ctypes.c_void_p()
+                    _lib.check(L.pg_peer_open(handles[r], ctypes.byref(q)), "pg_peer_open")
+                    self._opened.append(q)
+                    addrs.append(q.value)
+            self.own.append(ptr)
+            self.peer_tables.append(torch.tensor(addrs, dtype=torch.int64, device=device))
+        self.send_counts = torch.zeros(n_parts, dtype=torch.int64, device=device)
+        self.recv_counts = torch.zeros(n_parts, dtype=torch.int64, device=device)
+        s_i = torch.arange(world, dtype=torch.int64, device=device).view(1, world)
+        b_i = torch.arange(n_sub, dtype=torch.int64, device=device).view(n_sub, 1)
+        self.seg_off = ((s_i * n_sub + b_i) * pc).reshape(-1).contiguous()        # region-major over sources
+        self.seg_cnt = torch.zeros(n_sub * world, dtype=torch.int64, device=device)
+        self.side = torch.cuda.Stream(device=device)
+        self.parity = 0
+        self.chunks = 1
+        self.launches_per_build = 4          # clear, count_short, k2a (fused exchange), k3
+        if world > 1:
+            dist.barrier()
+
+    def build(self, packed, n_rec, ev=None):
+        eng, L, t = self.engine, self.L, self.table
+        W, n_sub = self.world, self.n_sub
+        st = torch.cuda.current_stream()
+        self.side.wait_stream(st)
+        with torch.cuda.stream(self.side):
+            t.clear()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if ev is not None else None
+        if e:
+            e[0].record(st)
+        g_begin = int(packed.seq_off[0]) if n_rec > 0 else 0
+        g_end = int(packed.seq_off[n_rec]) if n_rec > 0 else 0
+        buf = self.parity
+        self.parity ^= 1
+        desc = _lib.PgTable(None, 2, None, _lib.PG_MODE_CANONICAL, self.k)
+        eng.check(L.pg_kmer_partition_p2p(ctypes.byref(desc), eng._ptr(packed.pk2), eng._ptr(packed.amb),
+                                          eng._ptr(packed.d_seq_off), n_rec, g_begin, g_end, self.owner_bits, self.sub_bits,
+                                          eng._ptr(self.peer_tables[buf]), self.rank, self.part_cap,
+                                          eng._ptr(self.send_counts), eng._stream()), "pg_kmer_partition_p2p")
+        if e:
+            e[1].record(st)
+        if W > 1:       # counts row d -> rank d; completes only after every peer's K2a (= all stores into my buffer) finished
+            dist.all_to_all_single(self.recv_counts, self.send_counts)
+        else:
+            self.recv_counts.copy_(self.send_counts)
+        if e:
+            e[2].record(st)
+        st.wait_stream(self.side)
+        if n_rec > 0:
+            eng.check(L.pg_count_short(ctypes.byref(t.c), eng._ptr(packed.d_seq_off), n_rec, g_begin, g_end, eng._stream()),
+                      "pg_count_short")
+        self.seg_cnt.copy_(self.recv_counts.view(W, n_sub).t().reshape(-1))
+        eng.check(L.pg_insert_records(ctypes.byref(t.c), self.own[buf], eng._ptr(self.seg_off), eng._ptr(self.seg_cnt),
+                                      n_sub, W, eng._stream()), "pg_insert_records")
+        if e:
+            e[3].record(st)
+            ev.setdefault("build", []).append((e[0], e[3]))
+            ev.setdefault("k2a_all_chunks", []).append((e[0], e[1]))
+            ev.setdefault("until_exchange_done", []).append((e[0], e[2]))
+            ev.setdefault("k3", []).append((e[2], e[3]))
+        return t
+
+    def verify(self):
+        if int(self.send_counts.max().item()) > self.part_cap:
+            raise _lib.PgError("record bucket overflow on rank %d" % self.rank)
+        if self.table.overflowed():
+            raise _lib.PgError("dBG table overflow on rank %d" % self.rank)
+
+    def close(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        for q in self._opened:
+            self.L.pg_peer_close(q)
+        for p_ in self.own:
+            self.L.pg_peer_free(p_)
+        self._opened, self.own = [], []
 
 
 def gather_export(table, world, rank):
@@ -215,7 +342,9 @@ def bench(args, world, rank, local, ClockSampler=None):
     packed = engine.PackedSeqs(d_fasta)
     n_rec = packed.n_rec
     n_ins_local = packed.n_insertions(k)
-    builder = DistributedBuilder(k, packed.n_positions(k), world, rank)
+    mode = os.environ.get("PG_EXCHANGE", "p2p")
+    builder = PeerBuilder(k, packed.n_positions(k), world, rank) if mode == "p2p" else \
+        DistributedBuilder(k, packed.n_positions(k), world, rank)
     stream = torch.cuda.current_stream()
     kev = {}
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -250,7 +379,7 @@ def bench(args, world, rank, local, ClockSampler=None):
     ent = torch.tensor([used], dtype=torch.int64, device="cuda")
     dist.all_reduce(ent, op=dist.ReduceOp.SUM)
     avg = lambda name: sum(a.elapsed_time(b) for a, b in kev[name]) / len(kev[name])
-    stage = torch.tensor([avg("build")], dtype=torch.float64, device="cuda")
+    stage = torch.tensor([avg("build"), avg("k2a_all_chunks"), avg("until_exchange_done"), avg("k3")], dtype=torch.float64, device="cuda")
     dist.all_reduce(stage, op=dist.ReduceOp.MAX)
 
     # end to end: pinned host bytes -> H2D -> build -> D2H of the table statistics
@@ -283,6 +412,7 @@ def bench(args, world, rank, local, ClockSampler=None):
         ins_ms = float(stage[0].item())
         alg = 16.0 * n_ins / world
         block_bytes = builder.n_sub * builder.part_cap * 16 * builder.chunks
+        sent = torch.zeros(1)
         line = {
             "metric": "dbg_build_kmers_per_s", "value": n_ins / (ms_step * 1e-3) / 1e9, "unit": "G k-mers/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -295,13 +425,18 @@ def bench(args, world, rank, local, ClockSampler=None):
                     "h2d_bytes_per_step": int(host.numel()) * world, "d2h_bytes_per_step": (8 * 8 + 4 * 8 + 16 * (n_rec + 1)) * world},
             "gpu_launches": (3 + builder.launches_per_build) * args.steps * world,
             "clocks": clk,
-            "stages_ms": {"K2a x %d chunks overlapped with the all-to-all, then K3" % builder.chunks: ins_ms},
+            "exchange": "fused into K2a: peer stores over NVLink (CUDA IPC)" if mode == "p2p" else "NCCL all_to_all_single, %d chunks" % builder.chunks,
+            "stages_ms": {"build": ins_ms,
+                          "k2a_all_chunks": float(stage[1].item()), "until_exchange_done": float(stage[2].item()),
+                          "k3": float(stage[3].item())},
             "exchange_bytes_per_gpu_per_step": block_bytes * (world - 1),
-            "roofline": {"kernel": "k2a_partition + all-to-all + k3_insert_records (pipelined)", "bound": "hbm",
+            "roofline": {"kernel": "k2a_partition(+exchange) + k3_insert_records", "bound": "hbm",
                          "achieved": alg / (ins_ms * 1e-3) / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": alg / (ins_ms * 1e-3) / 1e9 / peak, "traffic": None,
                          "convention": "per GPU: 16 B per insertion owned by the rank (SURVEY 8d) over the whole pipelined build"},
         }
         print(json.dumps(line), flush=True)
+    if hasattr(builder, "close"):
+        builder.close()
     dist.barrier()
     dist.destroy_process_group()

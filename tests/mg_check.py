@@ -32,9 +32,11 @@ def main():
             recs.append((b"polyA", b"A" * 700))       # a hot key: every occurrence must reach one owner; count clamps at 255
         shards.append(synth.fasta_bytes(recs, width=70))
     packed = engine.PackedSeqs(engine.to_device_bytes(shards[rank]))
-    for sub_bytes in (8 << 20, 1 << 14):
-        builder = multigpu.DistributedBuilder(k, packed.n_positions(k), world, rank, sub_bytes=sub_bytes)
-        t = builder.build(packed, packed.n_rec)
+    for sub_bytes, cls in ((8 << 20, multigpu.DistributedBuilder), (1 << 14, multigpu.DistributedBuilder),
+                           (8 << 20, multigpu.PeerBuilder), (1 << 14, multigpu.PeerBuilder)):
+        builder = cls(k, packed.n_positions(k), world, rank, sub_bytes=sub_bytes)
+        for _ in range(3):                      # repeated builds: buffer reuse / double buffering
+            t = builder.build(packed, packed.n_rec)
         torch.cuda.synchronize()
         builder.verify()
         merged = multigpu.gather_export(t, world, rank)
@@ -44,7 +46,9 @@ def main():
             assert np.array_equal(ks, ref["dbg"][0]), "keys differ"
             assert np.array_equal(vs, ref["dbg"][1]), "masks differ"
             assert np.array_equal(cs, ref["dbg"][2]), "counts differ"
-            print("mg_check ok: world %d, sub_bytes %d, %d entries, max count %d" % (world, sub_bytes, ks.size, int(cs.max())), flush=True)
+            print("mg_check ok: %s world %d, sub_bytes %d, %d entries, max count %d" % (cls.__name__, world, sub_bytes, ks.size, int(cs.max())), flush=True)
+        if hasattr(builder, "close"):
+            builder.close()
         # every key sits on its owner: low bits of mix64(key)
         k_local, _, _ = t.export(sort=False)
     dist.barrier()
