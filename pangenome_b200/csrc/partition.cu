@@ -19,10 +19,10 @@
 
 namespace {
 
-constexpr int KP_THREADS = 128;
 constexpr int KP_G = 16;                               // positions per thread
-constexpr int KP_TILE = KP_THREADS * KP_G;             // 2048 positions per CTA tile
-constexpr int KP_MAX_REC = 2 * KP_TILE;                // literal-rc mode emits two records per position
+// CTA tile = THREADS x 16 positions: 128 threads (2048 positions, 40 KB of smem, 5 CTAs/SM) for the
+// single-GPU path; 256 threads (4096 positions) when buckets are peer memory - twice the run length
+// per bucket on NVLink and half the per-tile bookkeeping when there are many buckets
 constexpr int KP_MAX_PARTS = 1024;
 
 struct PartArgs {
@@ -47,9 +47,10 @@ __device__ __forceinline__ uint32_t part_of(const PartArgs &a, uint64_t key) {
 __device__ __forceinline__ uint32_t lastc4_f(uint32_t d) { return (0x02080401u >> (8 * d)) & 0xffu; }
 __device__ __forceinline__ uint32_t lastc4_r(uint32_t d) { return (0x01040802u >> (8 * d)) & 0xffu; }
 
-template <int MODE>
+template <int MODE, int KP_THREADS>
 __global__ void __launch_bounds__(KP_THREADS)
 k2a_partition(PartArgs a) {
+    constexpr int KP_TILE = KP_THREADS * KP_G;
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int RPP = (MODE == PG_MODE_LITERAL_RC) ? 2 : 1;               // records per position
     constexpr int MAXR = KP_TILE * RPP;
@@ -259,8 +260,8 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
     publish_claims(t, n_claimed);
 }
 
-int part_smem_bytes(int mode, int n_parts) {
-    int maxr = mode == PG_MODE_LITERAL_RC ? KP_MAX_REC : KP_TILE;
+int part_smem_bytes(int mode, int n_parts, int threads) {
+    int maxr = (mode == PG_MODE_LITERAL_RC ? 2 : 1) * threads * KP_G;
     return maxr * 16 + maxr * 2 * 2 + (3 * n_parts + (n_parts & 1)) * 4 + n_parts * 8 + 16;
 }
 
@@ -283,26 +284,34 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
     PartArgs a;
     a.pk2 = reinterpret_cast<const uint64_t *>(d_pk2); a.amb = d_amb; a.n_words = ((g_end + 31) >> 5) + 4;
     a.seq_off = d_seq_off; a.n_rec = n_rec; a.g_begin = g_begin; a.g_end = g_end; a.k = t->k; a.pow5km1 = pg_pow5(t->k - 1);
-    a.t_first = g_begin / KP_TILE; a.n_tiles = (g_end + KP_TILE - 1) / KP_TILE - a.t_first;
+    static int thr_env = -1;
+    if (thr_env < 0) { const char *e = getenv("PG_K2A_THREADS"); thr_env = e ? atoi(e) : 0; }
+    const int threads = (thr_env == 128 || thr_env == 256) ? thr_env : (d_peers ? 256 : 128);
+    const int tile = threads * KP_G;
+    a.t_first = g_begin / tile; a.n_tiles = (g_end + tile - 1) / tile - a.t_first;
     a.sub_bits = sub_bits; a.owner_bits = owner_bits; a.n_parts = n_parts;
     a.records = reinterpret_cast<uint4 *>(d_records); a.part_cap = part_cap;
     a.peers = reinterpret_cast<uint4 *const *>(d_peers); a.my_rank = my_rank;
     a.part_counts = reinterpret_cast<unsigned long long *>(d_part_counts);
-    int smem = part_smem_bytes(t->mode, n_parts);
+    int smem = part_smem_bytes(t->mode, n_parts, threads);
     int per_sm = 200 * 1024 / smem; if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
     int64_t maxg = (int64_t)pg_num_sms() * per_sm;
     int grid = (int)(a.n_tiles < maxg ? a.n_tiles : maxg);
-    switch (t->mode) {
-    case PG_MODE_LITERAL:
-        PG_CUDA(cudaFuncSetAttribute(k2a_partition<PG_MODE_LITERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k2a_partition<PG_MODE_LITERAL><<<grid, KP_THREADS, smem, st>>>(a); break;
-    case PG_MODE_LITERAL_RC:
-        PG_CUDA(cudaFuncSetAttribute(k2a_partition<PG_MODE_LITERAL_RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k2a_partition<PG_MODE_LITERAL_RC><<<grid, KP_THREADS, smem, st>>>(a); break;
-    default:
-        PG_CUDA(cudaFuncSetAttribute(k2a_partition<PG_MODE_CANONICAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k2a_partition<PG_MODE_CANONICAL><<<grid, KP_THREADS, smem, st>>>(a); break;
+#define K2A_LAUNCH(M, T)                                                                                            \
+    do {                                                                                                            \
+        PG_CUDA(cudaFuncSetAttribute(k2a_partition<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+        k2a_partition<M, T><<<grid, T, smem, st>>>(a);                                                              \
+    } while (0)
+    if (threads == 128) {
+        if (t->mode == PG_MODE_LITERAL) K2A_LAUNCH(PG_MODE_LITERAL, 128);
+        else if (t->mode == PG_MODE_LITERAL_RC) K2A_LAUNCH(PG_MODE_LITERAL_RC, 128);
+        else K2A_LAUNCH(PG_MODE_CANONICAL, 128);
+    } else {
+        if (t->mode == PG_MODE_LITERAL) K2A_LAUNCH(PG_MODE_LITERAL, 256);
+        else if (t->mode == PG_MODE_LITERAL_RC) K2A_LAUNCH(PG_MODE_LITERAL_RC, 256);
+        else K2A_LAUNCH(PG_MODE_CANONICAL, 256);
     }
+#undef K2A_LAUNCH
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

@@ -199,7 +199,9 @@ class PeerBuilder:
         per_rank = (int(n_glob.item()) + world - 1) // world
         cap = engine.next_pow2(max(1024, int(per_rank / 0.5) + 1))
         self.table = engine.DbgTable(cap, self.k, _lib.PG_MODE_CANONICAL, device=device)
-        self.sub_bits = engine.sub_bits_for(cap, sub_bytes)
+        # owner x sub buckets are written in runs over NVLink: keep their number <= 256 so a 4096-position
+        # tile still gives ~16-record (256-byte) runs; fewer table regions per rank is the price
+        self.sub_bits = min(engine.sub_bits_for(cap, sub_bytes), max(0, int(os.environ.get("PG_MG_PARTBITS", "8")) - self.owner_bits))
         self.n_sub = n_sub = 1 << self.sub_bits
         n_parts = world * n_sub
         self.part_cap = pc = int(int(m.item()) / n_parts * 1.25) + 4096
