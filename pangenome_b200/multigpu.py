@@ -88,7 +88,7 @@ class DistributedBuilder:
         per_rank = (self.n_positions_global + world - 1) // world
         cap = engine.next_pow2(max(1024, int(per_rank / 0.5) + 1))
         self.table = engine.DbgTable(cap, self.k, _lib.PG_MODE_CANONICAL, device=device)
-        self.sub_bits = engine.sub_bits_for(cap, sub_bytes)
+        self.sub_bits = min(engine.sub_bits_for(cap, sub_bytes), 10 - self.owner_bits)      # K2a handles <= 1024 buckets
         self.n_sub = n_sub = 1 << self.sub_bits
         n_parts = world * n_sub
         # the largest shard decides the block size every rank uses (blocks must be equal-sized)
