@@ -251,6 +251,20 @@ int pg_label_regions(const pg_graph *g, const int64_t *d_hit_g, const uint64_t *
                      int32_t *d_row_rec, int64_t *d_row_end, int32_t *d_row_label, int64_t cap_rows, int64_t *d_n_rows,
                      void *d_ws, int64_t ws_bytes, pg_stream_t stream);
 
+/* ---- multi-GPU plumbing for the stages after the dBG --------------------------------------
+ * pg_table_export_raw / pg_table_insert_raw: move occupied slots {key, 64-bit value word} between
+ *   tables (all-gather of the per-rank rdBG tables into one full rdBG table per rank; values are
+ *   OR-ed, keys are unique across ranks).
+ * pg_hits_decode: node key -> literal base-5 code (rank independent);
+ * pg_hits_rekey : (code, v5) -> node key in THIS rank's rdBG table, so that hits gathered from all
+ *   ranks can run through K6-K8 on one rank.
+ */
+int pg_table_export_raw(const pg_table *t, uint64_t *d_keys, uint64_t *d_vals, int64_t cap, int64_t *d_n, pg_stream_t stream);
+int pg_table_insert_raw(const pg_table *t, const uint64_t *d_keys, const uint64_t *d_vals, int64_t n, pg_stream_t stream);
+int pg_hits_decode(const pg_table *rdbg, const uint64_t *d_hit_node, int64_t n, uint64_t *d_hit_code, pg_stream_t stream);
+int pg_hits_rekey(const pg_table *rdbg, const uint64_t *d_hit_code, const uint32_t *d_hit_v5, int64_t n, uint64_t *d_hit_node,
+                  pg_stream_t stream);
+
 /* ---- host-side text writers (HOST pointers) -------------------------------------------
  * The side files of seq2graph (kmer_numba.py:1893-1904 and the cluster file `mcl` leaves):
  * pg_host_write_xyz: "code0_v0\tcode1_v1\tweight\n" per edge in the order given;

@@ -53,6 +53,10 @@ SIGNATURES = {
     "pg_rdbg_count": (c_int, [PT, c_vp, c_vp]),
     "pg_rdbg_select": (c_int, [PT, PT, c_vp]),
     "pg_rdbg_export": (c_int, [PT, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "pg_table_export_raw": (c_int, [PT, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "pg_table_insert_raw": (c_int, [PT, c_vp, c_vp, c_i64, c_vp]),
+    "pg_hits_decode": (c_int, [PT, c_vp, c_i64, c_vp, c_vp]),
+    "pg_hits_rekey": (c_int, [PT, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "pg_host_write_xyz": (c_int, [ctypes.c_char_p, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64]),
     "pg_host_write_mcl": (c_int, [ctypes.c_char_p, c_vp, c_vp, c_vp, c_i64]),
     "pg_path_workspace_bytes": (c_i64, [c_i64]),

@@ -421,6 +421,47 @@ __global__ void k8_rows(const uint32_t *__restrict__ flag, const int64_t *__rest
     row_rec[o] = rec; row_end[o] = m_p[i] + k; row_label[o] = m_label[i];
 }
 
+// ---- raw slot transfer + rank-independent hits (multi-GPU path stages) --------------------------
+__global__ void k_export_raw(const uint64_t *__restrict__ slots, int64_t cap, uint64_t *keys, uint64_t *vals, int64_t out_cap,
+                             unsigned long long *n_out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    uint64_t k = slots[2 * i];
+    if (k == PG_EMPTY) return;
+    unsigned long long at = atomicAdd(n_out, 1ull);
+    if ((int64_t)at < out_cap) { keys[at] = k; vals[at] = slots[2 * i + 1]; }
+}
+__global__ void k_insert_raw(TableView t, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = keys[i], s = tv_home(t, key);
+    for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
+        uint64_t *p = t.slots + 2 * s;
+        uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)PG_EMPTY, (unsigned long long)key);
+        if (old == PG_EMPTY || old == key) { atomicOr(reinterpret_cast<unsigned long long *>(p + 1), (unsigned long long)vals[i]); return; }
+        s = (s + 1) & t.capmask;
+    }
+    atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
+}
+// node key (local rdBG slot, orientation, v5) -> the reference's literal code: what another rank can re-key
+__global__ void k_hits_decode(const uint64_t *__restrict__ hit_node, int64_t n, const uint64_t *__restrict__ rd_slots, int64_t rd_cap,
+                              int mode, int k, uint64_t *__restrict__ hit_code) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t c; uint32_t v;
+    node_decode(hit_node[i], rd_slots, rd_cap, mode, k, c, v);
+    hit_code[i] = c;
+}
+// literal code + v5 -> node key of THIS rank's rdBG table (the code is a member or the phantom key 0 by construction)
+__global__ void k_hits_rekey(TableView rd, int mode, int k, const uint64_t *__restrict__ hit_code, const uint32_t *__restrict__ hit_v5,
+                             int64_t n, uint64_t *__restrict__ hit_node) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t lit = hit_code[i], other = mode == PG_MODE_CANONICAL ? pg_rc_code(lit, k) : lit, so = 0;
+    if (!rdbg_hit(rd, mode, lit, other, so)) so = ((rd.capmask + 1) << 1);      // cannot happen for gathered hits; keep it total
+    hit_node[i] = (so << NODE_V_BITS) | hit_v5[i];
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads > 0 ? (n + threads - 1) / threads : 1); }
 
 int check_graph(const pg_graph *g, const char *who) {
@@ -592,6 +633,44 @@ extern "C" int pg_label_regions(const pg_graph *g, const int64_t *d_hit_g, const
     k8_run_ends<<<mb, 256, 0, st>>>(nxt, reach, m_label, m_host, flag);
     exclusive_scan(flag, m_host, off, bsum, d_n_rows, st);
     k8_rows<<<mb, 256, 0, st>>>(flag, off, m_host, m_p, m_rec, m_label, k, d_row_rec, d_row_end, d_row_label, cap_rows);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_table_export_raw(const pg_table *t, uint64_t *d_keys, uint64_t *d_vals, int64_t cap, int64_t *d_n, pg_stream_t stream_) {
+    int rc = check_tab(t, "pg_table_export_raw"); if (rc) return rc;
+    if (!d_keys || !d_vals || !d_n || cap < 0) return pg_fail(PG_ERR_INVALID, "pg_table_export_raw: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream_;
+    PG_CUDA(cudaMemsetAsync(d_n, 0, 8, st));
+    k_export_raw<<<blocks_for(t->capacity, 256), 256, 0, st>>>(t->d_slots, t->capacity, d_keys, d_vals, cap, reinterpret_cast<unsigned long long *>(d_n));
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_table_insert_raw(const pg_table *t, const uint64_t *d_keys, const uint64_t *d_vals, int64_t n, pg_stream_t stream_) {
+    int rc = check_tab(t, "pg_table_insert_raw"); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_keys || !d_vals))) return pg_fail(PG_ERR_INVALID, "pg_table_insert_raw: bad arguments");
+    if (n == 0) return PG_OK;
+    k_insert_raw<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(make_view(t), d_keys, d_vals, n);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_hits_decode(const pg_table *rdbg, const uint64_t *d_hit_node, int64_t n, uint64_t *d_hit_code, pg_stream_t stream_) {
+    int rc = check_tab(rdbg, "pg_hits_decode"); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_hit_node || !d_hit_code))) return pg_fail(PG_ERR_INVALID, "pg_hits_decode: bad arguments");
+    if (n == 0) return PG_OK;
+    k_hits_decode<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(d_hit_node, n, rdbg->d_slots, rdbg->capacity, rdbg->mode, rdbg->k, d_hit_code);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_hits_rekey(const pg_table *rdbg, const uint64_t *d_hit_code, const uint32_t *d_hit_v5, int64_t n, uint64_t *d_hit_node,
+                             pg_stream_t stream_) {
+    int rc = check_tab(rdbg, "pg_hits_rekey"); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_hit_code || !d_hit_v5 || !d_hit_node))) return pg_fail(PG_ERR_INVALID, "pg_hits_rekey: bad arguments");
+    if (n == 0) return PG_OK;
+    k_hits_rekey<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(make_view(rdbg), rdbg->mode, rdbg->k, d_hit_code, d_hit_v5, n, d_hit_node);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

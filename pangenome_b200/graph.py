@@ -224,7 +224,7 @@ class GraphResult:
     def rows(self, packed, data):
         """[(seqid, start, end, strand, label)] in the reference's print order:
         per record, forward rows then rc rows mirrored to (n-end, n-start, '-')."""
-        ids = record_ids(packed, data)
+        ids = packed.ids if data is None else record_ids(packed, data)     # a multi-GPU global index brings its ids
         lens = packed.seq_lengths
         per_rec = {}
         for rec, start, end, sign, lab in self.rows_raw:

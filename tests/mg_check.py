@@ -49,8 +49,18 @@ def main():
             print("mg_check ok: %s world %d, sub_bytes %d, %d entries, max count %d" % (cls.__name__, world, sub_bytes, ks.size, int(cs.max())), flush=True)
         if hasattr(builder, "close"):
             builder.close()
-        # every key sits on its owner: low bits of mix64(key)
-        k_local, _, _ = t.export(sort=False)
+        if cls is multigpu.PeerBuilder and sub_bytes == 8 << 20:
+            # stages 2-5 distributed: rdBG all-gather, hits gathered to rank 0, K6-K8 there
+            for c_flag in (2, 3):
+                res, rows = multigpu.seq2graph_distributed(packed, t, k, world, rank, shards[rank], rc=bool(c_flag & 1))
+                if rank == 0:
+                    full = oracle.run(b"".join(shards), k, c=c_flag)
+                    rk, _ = res.rdbg.rdbg_export()
+                    assert np.array_equal(rk, full["rdbg"]), "rdBG differs"
+                    assert res.xyz_lines() == full["xyz"], "xyz differs"
+                    assert rows == full["rows"], "rows differ"
+                    print("mg_check ok: distributed graph -c %d: %d rdBG nodes, %d edges, %d rows" %
+                          (c_flag, rk.size, len(full["xyz"]), len(rows)), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -53,3 +53,25 @@ def test_log2_exact():
     assert [multigpu.log2_exact(n) for n in (1, 2, 4, 8)] == [0, 1, 2, 3]
     with pytest.raises(ValueError):
         multigpu.log2_exact(3)
+
+
+def _gv_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pangenome_b200 import multigpu
+    t = torch.arange(rank * 10, rank * 10 + rank + 1, dtype=torch.int64)       # rank r contributes r+1 items
+    cat, sizes = multigpu.gather_varlen(t, world)
+    out[rank] = (cat.tolist() == [0, 10, 11] and sizes == [1, 2])
+    e, _ = multigpu.gather_varlen(torch.zeros(0, dtype=torch.int64), world)
+    out[rank] = out[rank] and e.numel() == 0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_varlen_gloo():
+    world = 2
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_gv_worker, args=(world, 29573, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world)) and len(out) == world
