@@ -413,7 +413,7 @@ def seq2graph_distributed(packed, table, k, world, rank, data, rc=False, min_wei
         g_pos, _ = gather_varlen(pos, world)
         g_rec, _ = gather_varlen(rec + rec_base, world)
         g_v5, _ = gather_varlen(v5, world)
-        g_v6, _ = gather_varlen(h.v6[:n], world)
+        g_v6, _ = gather_varlen(h.v6[:n].to(torch.int32), world)      # NCCL has no int16
         all_hits.append((g_code, g_pos, g_rec, g_v5, g_v6))
     if rank != 0:
         return None, None
@@ -424,7 +424,7 @@ def seq2graph_distributed(packed, table, k, world, rank, data, rc=False, min_wei
         node = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
         chk(L.pg_hits_rekey(ctypes.byref(rd.c), P(g_code), P(g_v5.contiguous()), n, P(node), S()), "pg_hits_rekey")
         gg = gidx.d_seq_off[g_rec] + g_pos if n else g_pos
-        hits.append(graph.Hits(gg.contiguous(), node, g_rec.to(torch.int32).contiguous(), g_v6.contiguous(), n, strand))
+        hits.append(graph.Hits(gg.contiguous(), node, g_rec.to(torch.int32).contiguous(), g_v6.to(torch.int16).contiguous(), n, strand))
     total = sum(h.n for h in hits)
     g = graph.RdbgGraph(total, dev)
     for h in hits:
