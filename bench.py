@@ -222,6 +222,7 @@ def main():
     kev = {}
 
     def step_device(record=False):
+        builder.begin()                                     # table clear on the side stream, overlaps K1 and K2a
         p = engine.PackedSeqs(d_fasta)                      # K1 (3 launches) + small D2H of the record index
         return builder.build(p, n_rec, ev=kev if record else None)   # clear, count_short, K2a, K3
 

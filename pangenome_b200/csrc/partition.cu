@@ -286,7 +286,7 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
     a.seq_off = d_seq_off; a.n_rec = n_rec; a.g_begin = g_begin; a.g_end = g_end; a.k = t->k; a.pow5km1 = pg_pow5(t->k - 1);
     static int thr_env = -1;
     if (thr_env < 0) { const char *e = getenv("PG_K2A_THREADS"); thr_env = e ? atoi(e) : 0; }
-    const int threads = (thr_env == 128 || thr_env == 256) ? thr_env : (d_peers ? 256 : 128);
+    const int threads = (thr_env == 128 || thr_env == 256 || thr_env == 512) ? thr_env : (d_peers ? 256 : 128);
     const int tile = threads * KP_G;
     a.t_first = g_begin / tile; a.n_tiles = (g_end + tile - 1) / tile - a.t_first;
     a.sub_bits = sub_bits; a.owner_bits = owner_bits; a.n_parts = n_parts;
@@ -306,10 +306,14 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
         if (t->mode == PG_MODE_LITERAL) K2A_LAUNCH(PG_MODE_LITERAL, 128);
         else if (t->mode == PG_MODE_LITERAL_RC) K2A_LAUNCH(PG_MODE_LITERAL_RC, 128);
         else K2A_LAUNCH(PG_MODE_CANONICAL, 128);
-    } else {
+    } else if (threads == 256) {
         if (t->mode == PG_MODE_LITERAL) K2A_LAUNCH(PG_MODE_LITERAL, 256);
         else if (t->mode == PG_MODE_LITERAL_RC) K2A_LAUNCH(PG_MODE_LITERAL_RC, 256);
         else K2A_LAUNCH(PG_MODE_CANONICAL, 256);
+    } else {
+        if (t->mode == PG_MODE_LITERAL_RC) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: 512-thread tiles do not fit the literal-rc mode");
+        if (t->mode == PG_MODE_LITERAL) K2A_LAUNCH(PG_MODE_LITERAL, 512);
+        else K2A_LAUNCH(PG_MODE_CANONICAL, 512);
     }
 #undef K2A_LAUNCH
     PG_CUDA(cudaGetLastError());

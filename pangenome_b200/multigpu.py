@@ -238,13 +238,21 @@ class PeerBuilder:
         if world > 1:
             dist.barrier()
 
+    def begin(self):
+        """Start clearing the table on the side stream (call before K1 / the H2D copy)."""
+        st = torch.cuda.current_stream()
+        self.side.wait_stream(st)
+        with torch.cuda.stream(self.side):
+            self.table.clear()
+        self._begun = True
+
     def build(self, packed, n_rec, ev=None):
         eng, L, t = self.engine, self.L, self.table
         W, n_sub = self.world, self.n_sub
         st = torch.cuda.current_stream()
-        self.side.wait_stream(st)
-        with torch.cuda.stream(self.side):
-            t.clear()
+        if not getattr(self, "_begun", False):
+            self.begin()
+        self._begun = False
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if ev is not None else None
         if e:
             e[0].record(st)
@@ -469,6 +477,8 @@ def bench(args, world, rank, local, ClockSampler=None):
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(record=False):
+        if hasattr(builder, "begin"):
+            builder.begin()                 # table clear overlaps K1 and K2a
         p = engine.PackedSeqs(d_fasta)
         return builder.build(p, n_rec, ev=kev if record else None)
 
@@ -503,6 +513,8 @@ def bench(args, world, rank, local, ClockSampler=None):
 
     # end to end: pinned host bytes -> H2D -> build -> D2H of the table statistics
     def step_e2e():
+        if hasattr(builder, "begin"):
+            builder.begin()
         d = host.to("cuda", non_blocking=True)
         p = engine.PackedSeqs(d)
         tt = builder.build(p, n_rec)
