@@ -274,6 +274,13 @@ int pg_hits_rekey(const pg_table *rdbg, const uint64_t *d_hit_code, const uint32
 int pg_host_write_xyz(const char *path, const uint64_t *c0, const uint32_t *v0, const uint64_t *c1,
                       const uint32_t *v1, const uint32_t *w, int64_t n);
 int pg_host_write_mcl(const char *path, const uint64_t *code, const uint32_t *v5, const int64_t *label, int64_t n);
+/* `_db.npz` interop (dump :243-261, load_on_disk :289-335): lay (key, val, count) entries out as the
+ * slot arrays of the reference's `oakht` (prime capacity, FNV-1a over the low 4 key bytes, quadratic
+ * probing) so that `kmer_numba.py -d` can read a GPU-built dBG.  pg_host_oakht_capacity = the capacity
+ * the reference's own table reaches after that many distinct keys. */
+int64_t pg_host_oakht_capacity(int64_t n_entries);
+int pg_host_build_oakht(const uint64_t *keys, const uint16_t *vals, const uint8_t *cnts, int64_t n, int64_t cap,
+                        uint64_t *okeys, uint16_t *ovals, uint8_t *ocnts);
 
 #ifdef __cplusplus
 }

@@ -4,9 +4,10 @@
 
 Same flags (``-i -k -n -c -r -d -R -D``; ``-k27`` and ``-k 27`` forms; unknown
 flags such as ``-m`` are skipped exactly like upstream, F1), same ``# `` banner
-lines, same table rows, same side-file names.  Extra long options (ignored by
-the reference's parser, so scripts stay portable): ``--min-edge-weight W``,
-``--no-mcl-file``.
+lines, same table rows, same side-file names.  ``-d`` / ``-D`` read tables in the
+reference's ``.npz`` layout.  Extra long options (ignored by the reference's parser,
+so scripts stay portable): ``--min-edge-weight W``, ``--no-mcl-file``, ``--dump-db``
+(write ``<input>_db.npz`` like the reference always does).
 """
 import sys
 from time import time
@@ -68,18 +69,37 @@ def entry_point(argv, out=sys.stdout):
     if not qry:
         manual_print(out)
         raise SystemExit()
-    if args['-d'] or args['-D'] or args['-r'] or args['-R']:
-        raise SystemExit("pangenome_b200: -d/-D/-r/-R (.npz tables and breakpoints of the CPU reference) are not "
-                         "supported by the GPU path; run without them")
+    if args['-r'] or args['-R']:
+        raise SystemExit("pangenome_b200: -r/-R (chunk breakpoints of the CPU reference) are not supported by the "
+                         "GPU path; run without them")
     from . import stages
     p = lambda *a: print(*a, file=out)
+    dbs, rdb = args['-d'], args['-D']
+    rc1 = ((rc & 1) == 1)
+    if dbs or rdb:
+        # kmer_numba.py:2072-2100: start from a dBG (-d) or rdBG (-D) table saved in the reference's .npz layout
+        if not rdb:
+            p('load dBG from disk')
+            p('# build the reduced dBG')
+        kmer_dict = stages.load_dbg(qry, dbs or rdb, kmer)
+        rdbg_dict = stages.dbg2rdbg(kmer_dict)      # an rdBG file only holds members: selecting again keeps all of them
+        del kmer_dict
+        p('# find fr')
+        stages.seq2graph(qry, kmer=kmer, bits=5, Ns=Ns, rdbg_dict=rdbg_dict, rc=rc1, out=out,
+                         min_weight=int(extra['--min-edge-weight']), write_mcl='--no-mcl-file' not in flags)
+        return 0
     p('# build the dBG')
     st = time()
     rc0 = ((rc >> 1) == 1)
     kmer_dict = stages.seq2rdbg(qry, kmer, 5, Ns, rc=rc0)
     p('# finished in', time() - st, 'seconds')
-    # the reference dumps the table to <qry>_db.npz and reloads it here (:2116-2126); the result does
-    # not depend on it and the GPU table stays resident instead
+    # the reference always dumps the table to <qry>_db.npz and reloads it here (:2116-2126); the result does
+    # not depend on it, so the GPU table stays resident and the file is only written on request
+    if '--dump-db' in flags:
+        p('# save dBG to disk')
+        st = time()
+        stages.dump(kmer_dict, qry + '_db')
+        p('# finished in', time() - st, 'seconds')
     p('# build the reduced dBG')
     st = time()
     rdbg_dict = stages.dbg2rdbg(kmer_dict)

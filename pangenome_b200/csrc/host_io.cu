@@ -50,3 +50,46 @@ extern "C" int pg_host_write_mcl(const char *path, const uint64_t *code, const u
     fclose(f);
     return PG_OK;
 }
+
+// ---- `_db.npz` interop (kmer_numba.py dump :243-261 / load_on_disk :289-335) --------------------
+// The reference stores its dBG as the raw arrays of its open-addressing table `oakht`; to hand a
+// GPU-built dBG to the reference's `-d` option the entries must be laid out the way its `pointer()`
+// (:521-538) will probe for them: prime capacity, FNV-1a over the low 4 key bytes (:400-411),
+// quadratic probing j = (j0 + t*t) % M.  Host code: this is file-format work, not the hot path.
+namespace {
+bool oak_isprime(int64_t n) {
+    if (n <= 1 || n % 2 == 0 || n % 3 == 0) return false;
+    for (int64_t i = 5; i * i <= n; i += 6) if (n % i == 0 || n % (i + 2) == 0) return false;
+    return true;
+}
+int64_t oak_find_prime(int64_t n) { for (;; n++) if (oak_isprime(n)) return n; }
+inline uint64_t oak_fnv4(uint64_t v) {
+    uint64_t a = 0xcbf29ce484222325ull;
+    for (int i = 0; i < 4; i++) { a ^= (v & 0xff); a *= 0x100000001b3ull; v >>= 8; }
+    return a;
+}
+}  // namespace
+
+// capacity the reference's table has after inserting n distinct keys: starts at prime >= 2^20
+// (init_dict ignores its capacity argument, :1121) and grows x1.62 whenever size/capacity > 0.75
+extern "C" int64_t pg_host_oakht_capacity(int64_t n_entries) {
+    int64_t cap = oak_find_prime(1 << 20);
+    while ((double)n_entries / (double)cap > 0.75) cap = oak_find_prime((int64_t)((double)cap * 1.62));
+    return cap;
+}
+
+extern "C" int pg_host_build_oakht(const uint64_t *keys, const uint16_t *vals, const uint8_t *cnts, int64_t n, int64_t cap,
+                                   uint64_t *okeys, uint16_t *ovals, uint8_t *ocnts) {
+    if (n < 0 || cap < 1 || n > cap || !okeys || !ovals || !ocnts) return pg_fail(PG_ERR_INVALID, "pg_host_build_oakht: bad arguments");
+    memset(okeys, 0, (size_t)cap * 8); memset(ovals, 0, (size_t)cap * 2); memset(ocnts, 0, (size_t)cap);
+    for (int64_t i = 0; i < n; i++) {
+        int64_t j = (int64_t)(oak_fnv4(keys[i]) % (uint64_t)cap), j0 = j;
+        for (int64_t t = 0; t < cap; t++) {
+            if (ocnts[j] == 0 || okeys[j] == keys[i]) break;
+            j = (j0 + t * t) % cap;
+        }
+        if (ocnts[j] != 0 && okeys[j] != keys[i]) return pg_fail(PG_ERR_CAPACITY, "pg_host_build_oakht: probe sequence exhausted");
+        okeys[j] = keys[i]; ovals[j] = vals[i]; ocnts[j] = cnts[i] ? cnts[i] : 1;
+    }
+    return PG_OK;
+}

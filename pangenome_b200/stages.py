@@ -50,6 +50,22 @@ def seq2rdbg(qry, kmer=13, bits=5, Ns=1e6, chunk=2 ** 32, brkpt="./breakpoint", 
     return DbgHandle(table, packed, raw, n_rec)
 
 
+def dump(kmer_dict, fn):
+    """kmer_numba.py dump (:243-261): ``<fn>.npz`` in the reference's oakht layout."""
+    from . import npz
+    return npz.dump(kmer_dict.table, fn)
+
+
+def load_dbg(qry, fn, kmer):
+    """``-d`` / ``-D``: a table saved by the reference (or by ``dump``) + the packed input."""
+    from . import npz
+    kmer = min(max(1, int(kmer)), 27)
+    data = _read(qry)
+    packed = engine.PackedSeqs(engine.to_device_bytes(data))
+    table = npz.load(fn, kmer, device=packed.pk2.device)
+    return DbgHandle(table, packed, data.tobytes(), packed.n_rec)
+
+
 def dbg2rdbg(kmer_dict):
     """Stage 2: keep nodes with indegree != 1 or outdegree != 1."""
     rd = kmer_dict.table.select_rdbg()

@@ -36,3 +36,24 @@ def test_cli_test_fsa(tmp_path):
     out3 = io.StringIO()
     cli.entry_point(["prog", "-i", str(fa), "-k", "27"], out=out3)
     assert [l for l in out3.getvalue().split("\n") if l and not l.startswith("#")] == []
+
+
+def test_cli_dump_db_and_reload(tmp_path):
+    """--dump-db writes <input>_db.npz in the reference's layout; -d starts from it."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import numpy as np
+    from pangenome_b200 import cli
+    case = {c["name"]: c for c in load_small_cases()}["nasty_k11_lf"]
+    fa = tmp_path / "n.fa"
+    fa.write_bytes(case["input_latin1"].encode("latin-1"))
+    out = io.StringIO()
+    cli.entry_point(["prog", "-i", str(fa), "-k", "11", "--dump-db", "--no-mcl-file"], out=out)
+    rows = [l for l in out.getvalue().split("\n") if l and not l.startswith("#")]
+    assert rows == ["%s\t%d\t%d\t%s\t%d" % tuple(r) for r in case["rows"]]
+    z = np.load(str(fa) + "_db.npz")
+    assert int(z["parameters"][2]) == len(case["dbg"])
+    out2 = io.StringIO()
+    cli.entry_point(["prog", "-i", str(fa), "-k", "11", "-d", str(fa) + "_db.npz", "--no-mcl-file"], out=out2)
+    assert [l for l in out2.getvalue().split("\n") if l and "\t" in l] == rows
