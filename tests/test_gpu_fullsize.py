@@ -74,3 +74,24 @@ def test_cfg2_rdbg_graph_rows(ctx):
     assert hashlib.sha256("\n".join(lines).encode()).hexdigest() == facts["xyz_fileorder_sha256"]
     assert res.graph.n_components == facts["n_components"]
     assert res.rows(packed, data) == [tuple(r) for r in facts["rows"]]
+
+
+def test_cfg3_full_size_checksum():
+    """BASELINE config 3 (200 x 5 Mbp = 1 Gbp, k = 27): 2.0 G insertions; the table checksum must equal
+    the C oracle's (tests/golden/cfg3_oracle_facts.json, 14 CPU-minutes to produce).  Needs ~70 GB of HBM."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a 180 GB B200")
+    from pangenome_b200 import engine
+    facts = json.load(open(os.path.join(GOLDEN, "cfg3_oracle_facts.json")))
+    data = pangenome(200, 5_000_000)
+    assert len(data) == facts["file_bytes"] and hashlib.sha256(data).hexdigest() == facts["file_sha256"]
+    packed = engine.PackedSeqs(engine.to_device_bytes(data))
+    del data
+    f = facts["k"]["27"]
+    assert packed.n_insertions(27) == f["n_inserts"]
+    t, _, buckets = engine.build_dbg_partitioned(packed, 27)
+    assert list(t.checksum()) == f["dbg_checksum"]
+    assert t.n_keys() * 2 == f["dbg_entries"]
