@@ -210,6 +210,7 @@ def main():
     torch.cuda.synchronize()
     builder.verify()
     cap = table.capacity
+    est_keys = builder.last_estimate
     used, entries = table.count()
     ref_table, _ = engine.build_dbg(packed, k)              # the fused single-launch path must agree
     ref_sum = ref_table.checksum()
@@ -290,6 +291,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": wl, "k": k, "rc": True, "insertions_per_step": n_ins, "bases": packed.n_bases,
                    "table_slots": cap, "table_bytes": cap * 16, "distinct_canonical_keys": used,
+                   "estimated_keys_from_1_in_256_sample": est_keys, "load_factor": used / cap,
                    "l2": "every step clears and randomly updates the %.1f GB table (> 126 MB L2), which evicts the input" % (cap * 16 / 1e9)},
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host.numel()),
                 "d2h_bytes_per_step": int(8 * 8 + 4 * 8 + 16 * (packed.n_rec + 1))},

@@ -127,6 +127,11 @@ int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_a
  *                                            of ANY power-of-two table the key's home slot lies in)
  *   d_records holds 2^(owner_bits+sub_bits) buckets of part_cap records each; d_part_counts[b]
  *   = records produced for bucket b (records beyond part_cap are dropped: compare and fall back).
+ *   Optional distinct-key estimator (d_sample_keys != NULL): keys whose mix has bits 8..15 == 0 - a 1/256
+ *   sample of the key space - are collected in a power-of-two CAS set the caller filled with 0xFF;
+ *   *d_sample_count (caller-zeroed) ends as its size, so 256 x that estimates the slots the table needs
+ *   (a value >= 2^40 means the set overflowed: use the upper bound).  This is how the table is sized
+ *   BEFORE it is cleared and filled - the reference instead grows x1.62 and rehashes (:423-474).
  * pg_insert_records: upsert the records of n_regions x n_src segments
  *   [seg_off[b*n_src+j], +seg_cnt[b*n_src+j]) of d_records (record units), region after region
  *   (n_src = source ranks x pipeline chunks that contributed to a region; 1 on a single GPU), so
@@ -136,7 +141,8 @@ int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_a
  */
 int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                       int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
-                      uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream);
+                      uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts,
+                      uint64_t *d_sample_keys, int64_t sample_cap, int64_t *d_sample_count, pg_stream_t stream);
 /* Fused extraction + exchange over NVLink peer memory: like pg_kmer_partition, but bucket
  * (owner, sub) is stored straight into rank `owner`'s receive buffer (d_peer_bases[owner], a
  * peer-mapped pointer; the own rank's entry is its own buffer) at slice

@@ -40,7 +40,7 @@ SIGNATURES = {
     "pg_table_clear": (c_int, [PT, c_vp]),
     "pg_kmer_insert": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "pg_count_short": (c_int, [PT, c_vp, c_i64, c_i64, c_i64, c_vp]),
-    "pg_kmer_partition": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
+    "pg_kmer_partition": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "pg_kmer_partition_p2p": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_int, c_i64, c_vp, c_vp]),
     "pg_peer_alloc": (c_int, [c_i64, ctypes.POINTER(c_vp), ctypes.c_char_p]),
     "pg_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),

@@ -34,10 +34,29 @@ struct PartArgs {
     // fused exchange: when `peers` is set, bucket (owner, sub) is written straight into rank `owner`'s
     // receive buffer over NVLink (peer-mapped pointer), at the slice reserved for source rank `my_rank`
     uint4 *const *peers; int my_rank;
+    // distinct-key estimator: keys whose mix has bits 8..15 == 0 (a 1/256 sample of the KEY space, so every
+    // occurrence of a sampled key is sampled) go into a small CAS set; 256 x its size estimates the table
+    uint64_t *sample_keys; uint64_t sample_mask; unsigned long long *sample_count;
 };
+
+__device__ __forceinline__ void sample_key(const PartArgs &a, uint64_t key, uint64_t h) {
+    uint64_t s = (h >> 16) & a.sample_mask;
+    for (uint64_t probe = 0; probe <= a.sample_mask; probe++) {
+        uint64_t ck = a.sample_keys[s];
+        if (ck == key) return;
+        if (ck == PG_EMPTY) {
+            uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(a.sample_keys + s), (unsigned long long)PG_EMPTY, (unsigned long long)key);
+            if (old == PG_EMPTY) { atomicAdd(a.sample_count, 1ull); return; }
+            if (old == key) return;
+        }
+        s = (s + 1) & a.sample_mask;
+    }
+    atomicAdd(a.sample_count, 1ull << 40);     // set full: poison the estimate so the host falls back to the upper bound
+}
 
 __device__ __forceinline__ uint32_t part_of(const PartArgs &a, uint64_t key) {
     uint64_t h = pg_mix64(key);
+    if (a.sample_keys && ((h >> 8) & 0xFFu) == 0) sample_key(a, key, h);
     uint32_t sub = a.sub_bits ? (uint32_t)(h >> (64 - a.sub_bits)) : 0u;      // hash prefix = table region (tv_home)
     uint32_t owner = a.owner_bits ? (uint32_t)(h & ((1u << a.owner_bits) - 1u)) : 0u;   // low bits: disjoint from the slot bits
     return (owner << a.sub_bits) | sub;
@@ -270,7 +289,8 @@ int part_smem_bytes(int mode, int n_parts, int threads) {
 static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                             int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
                             uint64_t *d_records, uint64_t *const *d_peers, int my_rank, int64_t part_cap,
-                            int64_t *d_part_counts, pg_stream_t stream_) {
+                            int64_t *d_part_counts, uint64_t *d_sample_keys, int64_t sample_cap, int64_t *d_sample_count,
+                            pg_stream_t stream_) {
     if (!t || t->k < 1 || t->k > 27 || t->mode < 0 || t->mode > 2)
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: bad table descriptor (only mode and k are used)");
     if (!d_pk2 || !d_amb || !d_seq_off || (!d_records && !d_peers) || !d_part_counts || n_rec < 0 || g_begin < 0 || g_end < g_begin || part_cap < 1)
@@ -293,6 +313,13 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
     a.records = reinterpret_cast<uint4 *>(d_records); a.part_cap = part_cap;
     a.peers = reinterpret_cast<uint4 *const *>(d_peers); a.my_rank = my_rank;
     a.part_counts = reinterpret_cast<unsigned long long *>(d_part_counts);
+    a.sample_keys = nullptr; a.sample_mask = 0; a.sample_count = nullptr;
+    if (d_sample_keys) {
+        if (!d_sample_count || sample_cap < 2 || (sample_cap & (sample_cap - 1)))
+            return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: sample set needs a power-of-two capacity and a counter");
+        a.sample_keys = d_sample_keys; a.sample_mask = (uint64_t)sample_cap - 1;
+        a.sample_count = reinterpret_cast<unsigned long long *>(d_sample_count);
+    }
     int smem = part_smem_bytes(t->mode, n_parts, threads);
     int per_sm = 200 * 1024 / smem; if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
     int64_t maxg = (int64_t)pg_num_sms() * per_sm;
@@ -322,9 +349,10 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
 
 extern "C" int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                                  int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
-                                 uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream_) {
+                                 uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, uint64_t *d_sample_keys,
+                                 int64_t sample_cap, int64_t *d_sample_count, pg_stream_t stream_) {
     return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, owner_bits, sub_bits, d_records, nullptr, 0,
-                            part_cap, d_part_counts, stream_);
+                            part_cap, d_part_counts, d_sample_keys, sample_cap, d_sample_count, stream_);
 }
 
 extern "C" int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
@@ -334,7 +362,7 @@ extern "C" int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, c
     if (!d_peer_bases || my_rank < 0 || my_rank >= (1 << owner_bits))
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p: bad peer table / rank");
     return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, owner_bits, sub_bits, nullptr, d_peer_bases, my_rank,
-                            part_cap, d_part_counts, stream_);
+                            part_cap, d_part_counts, nullptr, 0, nullptr, stream_);
 }
 
 // ---- peer memory for the fused exchange (CUDA IPC; one process per GPU) ------------------------

@@ -139,6 +139,14 @@ class DbgTable:
     def clear(self):
         check(self.L.pg_table_clear(ctypes.byref(self.c), _stream()), "pg_table_clear")
 
+    def set_capacity(self, capacity):
+        """Use only the first ``capacity`` (power of two) slots of the allocated buffer."""
+        capacity = next_pow2(capacity)
+        if 2 * capacity > self.slots.numel():
+            raise PgError("set_capacity(%d) exceeds the allocated %d slots" % (capacity, self.slots.numel() // 2))
+        self.capacity = capacity
+        self.c.capacity = capacity
+
     def insert(self, packed, n_rec=None, g_begin=None, g_end=None):
         n_rec = packed.n_rec if n_rec is None else n_rec
         if n_rec == 0:
@@ -260,7 +268,35 @@ class RecordBuckets:
         self.seg_off = torch.arange(n_parts, dtype=torch.int64, device=device) * part_cap
 
 
-def partition_kmers(packed, k, mode, n_rec, owner_bits, sub_bits, g_begin=None, g_end=None, slack=1.25, buckets=None):
+class KeySampler:
+    """The 1/256 key-space sample K2a can collect to estimate the number of distinct keys, i.e. how
+    big the table has to be, before the table is cleared and filled (pg_kmer_partition)."""
+    RATE = 256
+
+    def __init__(self, n_positions, device):
+        self.cap = next_pow2(max(1024, n_positions // self.RATE * 2 + 1024))
+        self.keys = torch.empty(self.cap, dtype=torch.int64, device=device)
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def reset(self):
+        self.keys.fill_(-1)
+        self.count.zero_()
+
+    def estimate(self):
+        """Estimated distinct keys, or None if the sample set overflowed (synchronises)."""
+        c = int(self.count.item())
+        return None if c >= (1 << 40) else c * self.RATE
+
+
+def capacity_for(est_keys, upper, load=0.35, margin=1.05):
+    """Power-of-two capacity for an estimated number of keys (load ends up in (load/2, load])."""
+    if est_keys is None:
+        return upper
+    return min(upper, next_pow2(max(1024, int(est_keys * margin / load) + 1)))
+
+
+def partition_kmers(packed, k, mode, n_rec, owner_bits, sub_bits, g_begin=None, g_end=None, slack=1.25, buckets=None,
+                    sampler=None):
     """K2a over records [0, n_rec): returns RecordBuckets (no synchronisation)."""
     L = _lib.load()
     n_parts = 1 << (owner_bits + sub_bits)
@@ -271,9 +307,12 @@ def partition_kmers(packed, k, mode, n_rec, owner_bits, sub_bits, g_begin=None, 
     if buckets is None or buckets.n_parts != n_parts or buckets.part_cap < part_cap:
         buckets = RecordBuckets(n_parts, part_cap, packed.pk2.device)
     desc = PgTable(None, 2, None, mode, k)          # only mode and k are read by K2a
+    if sampler is not None:
+        sampler.reset()
     check(L.pg_kmer_partition(ctypes.byref(desc), _ptr(packed.pk2), _ptr(packed.amb), _ptr(packed.d_seq_off), n_rec,
                               g_begin, g_end, owner_bits, sub_bits, _ptr(buckets.records), buckets.part_cap,
-                              _ptr(buckets.counts), _stream()), "pg_kmer_partition")
+                              _ptr(buckets.counts), _ptr(sampler.keys) if sampler else None, sampler.cap if sampler else 0,
+                              _ptr(sampler.count) if sampler else None, _stream()), "pg_kmer_partition")
     return buckets
 
 
@@ -285,30 +324,31 @@ def sub_bits_for(capacity, sub_bytes=32 << 20):
     return bits
 
 
-def build_dbg_partitioned(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=None, sub_bytes=32 << 20, buckets=None,
+def build_dbg_partitioned(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=None, sub_bytes=8 << 20, buckets=None,
                           table=None):
-    """Two-phase build (K2a + K3).  Falls back to the fused kernel when a bucket overflows
-    (pathological hash skew, e.g. one k-mer making up most of the input)."""
+    """Two-phase build (K2a + K3).  K2a runs first and samples the key space, so the table is sized
+    from an estimate of the distinct keys (load 0.18-0.35) instead of the positions upper bound.
+    Falls back to the fused kernel when a bucket overflows (pathological hash skew, e.g. one k-mer
+    making up most of the input)."""
     k = int(min(max(1, k), 27))
     if mode is None:
         mode = _lib.PG_MODE_CANONICAL if rc else _lib.PG_MODE_LITERAL
     n_rec = packed.record_prefix(Ns, 2 if rc else 1)
     npos = packed.n_positions(k, n_rec)
     per_pos = 2 if mode == _lib.PG_MODE_LITERAL_RC else 1
-    cap = next_pow2(max(1024, capacity or int(npos * per_pos / _DEFAULT_LOAD) + 1))
+    upper = next_pow2(max(1024, int(npos * per_pos / _DEFAULT_LOAD) + 1))
     L = _lib.load()
+    dev = packed.pk2.device
+    if n_rec == 0:
+        return DbgTable(capacity or 1024, k, mode, device=dev), n_rec, buckets
+    sub_bits = sub_bits_for(capacity or upper, sub_bytes)
+    sampler = None if capacity else KeySampler(npos * per_pos, dev)
+    buckets = partition_kmers(packed, k, mode, n_rec, 0, sub_bits, buckets=buckets, sampler=sampler)
+    cap = next_pow2(capacity) if capacity else capacity_for(sampler.estimate(), upper)
+    g_begin, g_end = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
     for _ in range(6):
-        sub_bits = sub_bits_for(cap, sub_bytes)
-        if table is not None and table.capacity == cap and table.mode == mode and table.k == k:
-            t = table
-            t.clear()
-        else:
-            t = DbgTable(cap, k, mode, device=packed.pk2.device)
-        if n_rec == 0:
-            return t, n_rec, buckets
-        g_begin, g_end = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
+        t = DbgTable(cap, k, mode, device=dev)
         check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
-        buckets = partition_kmers(packed, k, mode, n_rec, 0, sub_bits, buckets=buckets)
         check(L.pg_insert_records(ctypes.byref(t.c), _ptr(buckets.records), _ptr(buckets.seg_off), _ptr(buckets.counts),
                                   buckets.n_parts, 1, _stream()), "pg_insert_records")
         worst = int(buckets.counts.max().item())           # synchronises
@@ -318,31 +358,37 @@ def build_dbg_partitioned(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=No
         if not t.overflowed():
             return t, n_rec, buckets
         cap *= 2
-        table = None
     raise PgError("dBG table kept overflowing up to capacity %d" % cap)
 
 
 class TwoPhaseBuilder:
     """Reusable buffers for repeated two-phase builds of same-sized inputs (bench / serving loop):
-    the table and the record buckets stay resident in HBM between calls."""
+    the table and the record buckets stay resident in HBM between calls.  Each build runs K2a first
+    (which also samples the key space), sizes the table from the estimate - a small D2H - then clears
+    just that much of the buffer and runs K3."""
 
-    def __init__(self, k, mode, n_positions, device="cuda", capacity=None, sub_bytes=8 << 20, owner_bits=0):
+    def __init__(self, k, mode, n_positions, device="cuda", capacity=None, sub_bytes=8 << 20, owner_bits=0, estimate=True):
         self.L = _lib.load()
         self.k, self.mode = int(min(max(1, k), 27)), int(mode)
         per_pos = 2 if mode == _lib.PG_MODE_LITERAL_RC else 1
         cap = next_pow2(max(1024, capacity or int(n_positions * per_pos / _DEFAULT_LOAD) + 1))
+        self.cap_max = cap
         self.table = DbgTable(cap, self.k, self.mode, device=device)
         self.sub_bits = sub_bits_for(cap, sub_bytes)
         self.owner_bits = owner_bits
         n_parts = 1 << (self.sub_bits + owner_bits)
         part_cap = int(n_positions * per_pos / n_parts * 1.25) + 4096
         self.buckets = RecordBuckets(n_parts, part_cap, device)
-        self.launches_per_build = 4          # clear, count_short, k2a_partition, k3_insert_records
-        self.side = torch.cuda.Stream(device=device)   # the table clear (DRAM-write bound) overlaps K2a (ALU bound)
+        self.sampler = KeySampler(n_positions * per_pos, device) if (estimate and not capacity) else None
+        self.launches_per_build = 4          # k2a_partition, clear, count_short, k3_insert_records
+        self.side = torch.cuda.Stream(device=device)
+        self.last_estimate = None
 
     def begin(self):
-        """Start clearing the table on the side stream now (e.g. before the H2D copy of the next
-        input); the following build() then skips its own clear."""
+        """Without the estimator the (full) table clear can start early on the side stream, e.g. before
+        the H2D copy of the next input; with it the capacity is only known after K2a."""
+        if self.sampler is not None:
+            return
         st = torch.cuda.current_stream()
         self.side.wait_stream(st)            # whoever still reads the previous table finishes first
         with torch.cuda.stream(self.side):
@@ -350,31 +396,42 @@ class TwoPhaseBuilder:
         self._begun = True
 
     def build(self, packed, n_rec, ev=None):
-        """Enqueue clear + K2a + K3 (no synchronisation).  ``ev`` = optional dict receiving CUDA
-        event pairs around the two kernels."""
+        """K2a, (estimate -> capacity), clear, K3.  ``ev`` = optional dict receiving CUDA event pairs
+        around the kernels."""
         t, b, L = self.table, self.buckets, self.L
         st = torch.cuda.current_stream()
-        if not getattr(self, "_begun", False):
+        if self.sampler is None and not getattr(self, "_begun", False):
             self.begin()
         self._begun = False
         if n_rec == 0:
             st.wait_stream(self.side)
+            if self.sampler is not None:
+                t.clear()
             return t
         g_begin, g_end = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
         if ev is not None:
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             e[0].record(st)
-        self.buckets = b = partition_kmers(packed, self.k, self.mode, n_rec, self.owner_bits, self.sub_bits, buckets=b)
-        st.wait_stream(self.side)            # K3 needs the cleared table
-        check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
+        self.buckets = b = partition_kmers(packed, self.k, self.mode, n_rec, self.owner_bits, self.sub_bits, buckets=b,
+                                           sampler=self.sampler)
         if ev is not None:
             e[1].record(st)
+        if self.sampler is not None:
+            self.last_estimate = self.sampler.estimate()            # 8-byte D2H, synchronises
+            t.set_capacity(capacity_for(self.last_estimate, self.cap_max))
+            t.clear()
+        else:
+            st.wait_stream(self.side)        # K3 needs the cleared table
+        check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
+        if ev is not None:
+            e[2].record(st)
         check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, _stream()),
               "pg_insert_records")
         if ev is not None:
-            e[2].record(st)
+            e[3].record(st)
             ev.setdefault("partition", []).append((e[0], e[1]))
-            ev.setdefault("insert", []).append((e[1], e[2]))
+            ev.setdefault("size+clear", []).append((e[1], e[2]))
+            ev.setdefault("insert", []).append((e[2], e[3]))
         return t
 
     def verify(self):

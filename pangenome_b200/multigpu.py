@@ -134,7 +134,8 @@ class DistributedBuilder:
             # NB every rank runs every chunk (empty ranges produce empty buckets): the collectives must match
             eng.check(L.pg_kmer_partition(ctypes.byref(desc), eng._ptr(packed.pk2), eng._ptr(packed.amb),
                                           eng._ptr(packed.d_seq_off), n_rec, lo, hi, self.owner_bits, self.sub_bits,
-                                          eng._ptr(self.send[c]), self.part_cap, eng._ptr(self.send_counts[c]), eng._stream()),
+                                          eng._ptr(self.send[c]), self.part_cap, eng._ptr(self.send_counts[c]), None, 0, None,
+                                          eng._stream()),
                       "pg_kmer_partition")
             if W > 1:
                 done = torch.cuda.Event()
