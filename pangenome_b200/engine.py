@@ -342,9 +342,11 @@ def build_dbg_partitioned(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=No
     if n_rec == 0:
         return DbgTable(capacity or 1024, k, mode, device=dev), n_rec, buckets
     sub_bits = sub_bits_for(capacity or upper, sub_bytes)
-    sampler = None if capacity else KeySampler(npos * per_pos, dev)
+    # sparse tables are faster for K3 (see TwoPhaseBuilder); estimate only when the upper bound is expensive
+    want_estimate = capacity is None and upper * 16 > 0.35 * torch.cuda.mem_get_info(dev)[0]
+    sampler = KeySampler(npos * per_pos, dev) if want_estimate else None
     buckets = partition_kmers(packed, k, mode, n_rec, 0, sub_bits, buckets=buckets, sampler=sampler)
-    cap = next_pow2(capacity) if capacity else capacity_for(sampler.estimate(), upper)
+    cap = next_pow2(capacity) if capacity else (capacity_for(sampler.estimate(), upper) if sampler else upper)
     g_begin, g_end = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
     for _ in range(6):
         t = DbgTable(cap, k, mode, device=dev)
@@ -367,7 +369,7 @@ class TwoPhaseBuilder:
     (which also samples the key space), sizes the table from the estimate - a small D2H - then clears
     just that much of the buffer and runs K3."""
 
-    def __init__(self, k, mode, n_positions, device="cuda", capacity=None, sub_bytes=8 << 20, owner_bits=0, estimate=True):
+    def __init__(self, k, mode, n_positions, device="cuda", capacity=None, sub_bytes=8 << 20, owner_bits=0, estimate=None):
         self.L = _lib.load()
         self.k, self.mode = int(min(max(1, k), 27)), int(mode)
         per_pos = 2 if mode == _lib.PG_MODE_LITERAL_RC else 1
@@ -379,6 +381,12 @@ class TwoPhaseBuilder:
         n_parts = 1 << (self.sub_bits + owner_bits)
         part_cap = int(n_positions * per_pos / n_parts * 1.25) + 4096
         self.buckets = RecordBuckets(n_parts, part_cap, device)
+        # K3 is fastest on a sparse table (measured on config 2: load 0.125 -> 1.02 ms, 0.25 -> 1.10 ms, 0.5 -> 1.33 ms)
+        # and the clear overlaps K1/K2a, so the positions upper bound is used while it is affordable; the
+        # estimator takes over when that table would eat a large part of the free HBM (config-5 scale)
+        if estimate is None:
+            free = torch.cuda.mem_get_info(device)[0] if torch.cuda.is_available() else 0
+            estimate = cap * 16 > 0.35 * free
         self.sampler = KeySampler(n_positions * per_pos, device) if (estimate and not capacity) else None
         self.launches_per_build = 4          # k2a_partition, clear, count_short, k3_insert_records
         self.side = torch.cuda.Stream(device=device)

@@ -84,3 +84,18 @@ def test_inserts_count_distinct_keys(eng):
         assert t3.n_keys() == used
         assert t3.checksum() == t1.checksum()
     b.verify()
+
+
+def test_table_sized_from_key_sample(eng):
+    """K2a's 1/256 key-space sample estimates the distinct keys within a few percent; a table sized
+    from it gives the same result as the upper-bound table."""
+    from pangenome_b200 import _lib
+    data = pangenome(8, 400_000)
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    ref_t, _ = eng.build_dbg(packed, 27)
+    b = eng.TwoPhaseBuilder(27, _lib.PG_MODE_CANONICAL, packed.n_positions(27), estimate=True)
+    t = b.build(packed, packed.n_rec)
+    b.verify()
+    assert abs(b.last_estimate - ref_t.n_keys()) < 0.05 * ref_t.n_keys()
+    assert t.capacity < b.cap_max and 0.17 < t.n_keys() / t.capacity <= 0.36
+    assert t.checksum() == ref_t.checksum()
