@@ -35,6 +35,19 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
         w.aprv = s_am[threadIdx.x + 3]; w.acur = s_am[threadIdx.x + 4]; w.anxt = s_am[threadIdx.x + 5];
         int64_t r = find_record(seq_off, n_rec, g0);
         int64_t rs = r >= 0 ? __ldg(seq_off + r) : 0, re = __ldg(seq_off + r + 1);
+        auto upsert_pos = [&](int, uint64_t F, uint64_t R, uint32_t vf, uint32_t vr) {
+            if (MODE == PG_MODE_CANONICAL) {
+                PgUpdate u = pg_canonical_update(F, R, vf, vr);
+                table_upsert(t, u.key, u.masks, u.inc, n_claimed);
+            } else {
+                table_upsert(t, F, vf, 1, n_claimed);
+                if (MODE == PG_MODE_LITERAL_RC) table_upsert(t, R, vr, 1, n_claimed);
+            }
+        };
+        if (pg_is_interior(w, g0, 32, k, rs, re, r >= 0, g_begin, g_end)) {
+            pg_interior_visit<32>(w, 0, k, pow5km1, upsert_pos);      // fast path: no record edge, no ambiguity
+            continue;
+        }
         uint64_t F, R;
         pg_codes_init(w, 0, k, F, R);
 #pragma unroll 1
@@ -45,13 +58,7 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
             if (g >= g_begin && r >= 0 && g + k <= re) {
                 uint32_t vf, vr;
                 pg_occ_vals(w, j, g - rs, re - rs, k, vf, vr);
-                if (MODE == PG_MODE_CANONICAL) {
-                    PgUpdate u = pg_canonical_update(F, R, vf, vr);
-                    table_upsert(t, u.key, u.masks, u.inc, n_claimed);
-                } else {
-                    table_upsert(t, F, vf, 1, n_claimed);
-                    if (MODE == PG_MODE_LITERAL_RC) table_upsert(t, R, vr, 1, n_claimed);
-                }
+                upsert_pos(j, F, R, vf, vr);
             }
             pg_codes_roll(w, j, k, pow5km1, F, R);
         }

@@ -62,6 +62,47 @@ PG_HD void pg_codes_roll(const PgWindow &w, int j, int k, uint64_t pow5km1, uint
     R = (R - (uint64_t)pg_cdig(dout) * pow5km1) * 5 + pg_cdig(din);
 }
 
+// ---- interior fast path -------------------------------------------------------------------------
+// 64 bits of the digit stream starting at base j of the window (j in [-1, 63]); only valid where the
+// window holds real bases.
+PG_HD uint64_t pg_win64(const PgWindow &w, int j) {
+    if (j < 0) return (w.cur << 2) | (w.prv >> 62);
+    if (j == 0) return w.cur;
+    if (j < 32) return (w.cur >> (2 * j)) | (w.nxt << (64 - 2 * j));
+    return w.nxt >> (2 * (j - 32));
+}
+// 4-entry lastc tables for ACGT digits (A0 G1 C2 T3): forward A1 G4 C8 T2, complemented T2 C8 G4 A1
+PG_HD uint32_t pg_lastc4_f(uint32_t d) { return (0x02080401u >> (8 * d)) & 0xffu; }
+PG_HD uint32_t pg_lastc4_r(uint32_t d) { return (0x01040802u >> (8 * d)) & 0xffu; }
+
+// Can G positions starting at stream offset g0 take the fast path?  All of them (and their prev / next
+// bases) must be ACGT and lie strictly inside one record [rs, re): no '#', '$', Q1 or ambiguity.
+PG_HD bool pg_is_interior(const PgWindow &w, int64_t g0, int G, int k, int64_t rs, int64_t re, bool have_rec,
+                          int64_t g_begin, int64_t g_end) {
+    return !w.any_amb() && have_rec && g0 - 2 >= rs && g0 + G + k + 1 <= re && g0 >= g_begin && g0 + G <= g_end;
+}
+// Visit G consecutive interior positions (window index j0 .. j0+G-1, j0 + G <= 32): f(q, F, R, vf, vr).
+// Every digit is a constant-shift field of three 64-bit views; codes roll with one multiply each.
+template <int G, class Fn>
+PG_HD void pg_interior_visit(const PgWindow &w, int j0, int k, uint64_t pow5km1, Fn &&f) {
+    const uint64_t dprev_w = pg_win64(w, j0 - 1), dout_w = pg_win64(w, j0), din_w = pg_win64(w, j0 + k);
+    uint64_t F = 0, R = 0, p5 = 1;
+    for (int i = 0; i < k; i++) {
+        uint32_t d = (uint32_t)(dout_w >> (2 * i)) & 3u;      // k <= 27 digits: all inside the 64-bit view
+        F += (uint64_t)d * p5; R = R * 5 + (3u - d); p5 *= 5;
+    }
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+        const uint32_t dp = (uint32_t)(dprev_w >> (2 * q)) & 3u, dout = (uint32_t)(dout_w >> (2 * q)) & 3u,
+                       din = (uint32_t)(din_w >> (2 * q)) & 3u;
+        const uint32_t vf = (pg_lastc4_f(dp) << 6) | pg_lastc4_f(din);
+        const uint32_t vr = (pg_lastc4_r(din) << 6) | pg_lastc4_r(dp);
+        f(q, F, R, vf, vr);
+        F = (F - dout) * PG_INV5 + (uint64_t)din * pow5km1;
+        R = (R - (uint64_t)(3u - dout) * pow5km1) * 5 + (3u - din);
+    }
+}
+
 // What one position contributes to a table in each mode.
 struct PgUpdate { uint64_t key; uint32_t masks; uint32_t inc; };
 // canonical pairing: slot key = min(F, R); masks = m(orientation 0) | m(orientation 1) << 16,

@@ -62,10 +62,6 @@ __device__ __forceinline__ uint32_t part_of(const PartArgs &a, uint64_t key) {
     return (owner << a.sub_bits) | sub;
 }
 
-// 4-entry lastc tables for ACGT digits (A0 G1 C2 T3): forward A1 G4 C8 T2, complemented T2 C8 G4 A1
-__device__ __forceinline__ uint32_t lastc4_f(uint32_t d) { return (0x02080401u >> (8 * d)) & 0xffu; }
-__device__ __forceinline__ uint32_t lastc4_r(uint32_t d) { return (0x01040802u >> (8 * d)) & 0xffu; }
-
 template <int MODE, int KP_THREADS>
 __global__ void __launch_bounds__(KP_THREADS)
 k2a_partition(PartArgs a) {
@@ -118,32 +114,9 @@ k2a_partition(PartArgs a) {
             int64_t r = find_record(a.seq_off, a.n_rec, g0);
             int64_t rs = r >= 0 ? __ldg(a.seq_off + r) : 0, re = __ldg(a.seq_off + r + 1);
             const int k = a.k;
-            const bool interior = !w.any_amb() && r >= 0 && g0 - 2 >= rs && g0 + KP_G + k + 1 <= re &&
-                                  g0 >= a.g_begin && g0 + KP_G <= a.g_end;
-            if (interior) {
-                // ---- fast path: 16 ACGT positions strictly inside one record.  prev / next are plain
-                // neighbours (no '#', '$', Q1 or ambiguity), every digit is a constant-shift field.
-                // 64-bit views starting at base j0-1, j0 and j0+k (only their low 32 bits are needed)
-                const uint64_t v0 = j0 ? ((w.cur >> (2 * j0)) | (w.nxt << (64 - 2 * j0))) : w.cur;           // bases j0 ..
-                const uint64_t v1 = j0 ? (w.nxt >> (2 * j0)) : w.nxt;                                        // bases j0+32 ..
-                const uint32_t dprev_w = (uint32_t)((v0 << 2) | ((j0 ? (w.cur >> (2 * j0 - 2)) : (w.prv >> 62)) & 3u));   // bases j0-1 ..
-                const uint32_t dout_w = (uint32_t)v0;
-                const uint32_t din_w = (uint32_t)((v0 >> (2 * k)) | (v1 << (64 - 2 * k)));                   // bases j0+k ..
-                uint64_t F = 0, R = 0, p5 = 1;
-                for (int i = 0; i < k; i++) {
-                    uint32_t d = (uint32_t)(v0 >> (2 * i)) & 3u;
-                    F += (uint64_t)d * p5; R = R * 5 + (3u - d); p5 *= 5;
-                }
-                p5 = a.pow5km1;
-#pragma unroll
-                for (int q = 0; q < KP_G; q++) {
-                    const uint32_t dp = (dprev_w >> (2 * q)) & 3u, dout = (dout_w >> (2 * q)) & 3u, din = (din_w >> (2 * q)) & 3u;
-                    const uint32_t vf = (lastc4_f(dp) << 6) | lastc4_f(din);
-                    const uint32_t vr = (lastc4_r(din) << 6) | lastc4_r(dp);
-                    emit_pos(q, F, R, vf, vr);
-                    F = (F - dout) * PG_INV5 + (uint64_t)din * p5;
-                    R = (R - (uint64_t)(3u - dout) * p5) * 5 + (3u - din);
-                }
+            if (pg_is_interior(w, g0, KP_G, k, rs, re, r >= 0, a.g_begin, a.g_end)) {
+                // ---- fast path: 16 ACGT positions strictly inside one record (kmer_core.cuh)
+                pg_interior_visit<KP_G>(w, j0, k, a.pow5km1, emit_pos);
                 done = true;
             } else {
                 // ---- generic path: record edges, ambiguity codes, range ends (all the quirks) ----

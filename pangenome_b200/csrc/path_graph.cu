@@ -135,19 +135,26 @@ k5_mark(TableView rd, int mode, SeqArgs a, int strand, uint32_t *__restrict__ hi
             w.prv = s_pk[threadIdx.x + 1]; w.cur = s_pk[threadIdx.x + 2]; w.nxt = s_pk[threadIdx.x + 3];
             w.aprv = s_am[threadIdx.x + 3]; w.acur = s_am[threadIdx.x + 4]; w.anxt = s_am[threadIdx.x + 5];
             int64_t r = find_record(a.seq_off, a.n_rec, g0);
-            int64_t re = __ldg(a.seq_off + r + 1);
-            uint64_t F, R;
-            pg_codes_init(w, 0, a.k, F, R);
-#pragma unroll 1
-            for (int j = 0; j < 32; j++) {
-                const int64_t g = g0 + j;
-                if (g >= a.g_end) break;
-                while (r + 1 < a.n_rec && g >= re) { r++; re = __ldg(a.seq_off + r + 1); }
-                if (g >= a.g_begin && r >= 0 && g + a.k <= re) {
+            int64_t rs = r >= 0 ? __ldg(a.seq_off + r) : 0, re = __ldg(a.seq_off + r + 1);
+            if (pg_is_interior(w, g0, 32, a.k, rs, re, r >= 0, a.g_begin, a.g_end)) {
+                pg_interior_visit<32>(w, 0, a.k, a.pow5km1, [&](int q, uint64_t F, uint64_t R, uint32_t, uint32_t) {
                     uint64_t so;
-                    if (rdbg_hit(rd, mode, strand ? R : F, strand ? F : R, so)) bits |= 1u << j;
+                    if (rdbg_hit(rd, mode, strand ? R : F, strand ? F : R, so)) bits |= 1u << q;
+                });
+            } else {
+                uint64_t F, R;
+                pg_codes_init(w, 0, a.k, F, R);
+#pragma unroll 1
+                for (int j = 0; j < 32; j++) {
+                    const int64_t g = g0 + j;
+                    if (g >= a.g_end) break;
+                    while (r + 1 < a.n_rec && g >= re) { r++; re = __ldg(a.seq_off + r + 1); }
+                    if (g >= a.g_begin && r >= 0 && g + a.k <= re) {
+                        uint64_t so;
+                        if (rdbg_hit(rd, mode, strand ? R : F, strand ? F : R, so)) bits |= 1u << j;
+                    }
+                    pg_codes_roll(w, j, a.k, a.pow5km1, F, R);
                 }
-                pg_codes_roll(w, j, a.k, a.pow5km1, F, R);
             }
         }
         hitbits[w0 - a.w_first + threadIdx.x] = bits;
