@@ -205,7 +205,7 @@ def main():
     packed = engine.PackedSeqs(d_fasta)
     n_ins = packed.n_insertions(k)
     n_rec = packed.record_prefix(2 ** 63, 2)
-    builder = engine.TwoPhaseBuilder(k, _lib.PG_MODE_CANONICAL, packed.n_positions(k))
+    builder = engine.TwoPhaseBuilder(k, _lib.PG_MODE_CANONICAL, packed.n_positions(k), estimate=False)
     table = builder.build(packed, n_rec)
     torch.cuda.synchronize()
     builder.verify()
@@ -223,9 +223,11 @@ def main():
     kev = {}
 
     def step_device(record=False):
+        # no host synchronisation inside a step: K1's record index stays on the device and K2a / K3 take
+        # their bounds from it (pg_kmer_partition_dev), so the host runs ahead of the GPU
         builder.begin()                                     # table clear on the side stream, overlaps K1 and K2a
-        p = engine.PackedSeqs(d_fasta)                      # K1 (3 launches) + small D2H of the record index
-        return builder.build(p, n_rec, ev=kev if record else None)   # clear, count_short, K2a, K3
+        p = engine.PackedSeqs(d_fasta, lazy=True)           # K1 (3 launches)
+        return builder.build_async(p, ev=kev if record else None)    # K2a, count_short, K3
 
     for _ in range(args.warmup):
         step_device()
@@ -252,8 +254,8 @@ def main():
     def step_e2e():
         builder.begin()                                   # table clear overlaps the H2D copy
         d = host.to("cuda", non_blocking=True)
-        p = engine.PackedSeqs(d)
-        tt = builder.build(p, n_rec)
+        p = engine.PackedSeqs(d, lazy=True)
+        tt = builder.build_async(p)
         return tt.stats_host()       # D2H of the table statistics (distinct keys, overflow flag, ...) - synchronises
     for _ in range(2):
         step_e2e()

@@ -158,6 +158,16 @@ int pg_peer_alloc(int64_t bytes, void **d_ptr, uint8_t *handle64);
 int pg_peer_open(const uint8_t *handle64, void **d_ptr);
 int pg_peer_close(void *d_ptr);
 int pg_peer_free(void *d_ptr);
+/* Device-argument variants for a fully asynchronous build of ALL records of a packed stream: n_rec and the
+ * stream range are read on the device from pg_fasta_scan_pack's outputs (d_counts, d_seq_off; cap_records as
+ * passed to it; max_bases = an upper bound such as the file size, for grid sizing), so K1 -> K2a -> K3 can be
+ * enqueued back to back.  If the record index was truncated (n_rec > cap_records) bucket 0's count is set to
+ * 2^62 and nothing else is written: the host notices at its next read-back and falls back. */
+int pg_kmer_partition_dev(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                          const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
+                          uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream);
+int pg_count_short_dev(const pg_table *t, const int64_t *d_seq_off, const int64_t *d_counts, int64_t cap_records,
+                       pg_stream_t stream);
 int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
                       const int64_t *d_seg_cnt, int n_regions, int n_src, pg_stream_t stream);
 

@@ -80,6 +80,18 @@ __global__ void k2_count_short(const int64_t *__restrict__ seq_off, int64_t n_re
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long *>(stats + PG_STAT_SHORT), (unsigned long long)mine);
 }
 
+// device-args variant: all records, n_rec read from K1's count block
+__global__ void k2_count_short_dev(const int64_t *__restrict__ seq_off, const int64_t *__restrict__ counts, int64_t cap_records,
+                                   int k, int strands, int64_t *stats) {
+    int64_t n_rec = counts[0];
+    if (n_rec > cap_records) return;
+    int64_t mine = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rec; i += (int64_t)gridDim.x * blockDim.x)
+        if (seq_off[i + 1] - seq_off[i] < k) mine += strands;
+    mine = __reduce_add_sync(0xffffffffu, (unsigned)mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(reinterpret_cast<unsigned long long *>(stats + PG_STAT_SHORT), (unsigned long long)mine);
+}
+
 __global__ void k_table_clear(uint4 *slots, int64_t n_slots, int64_t *stats) {
     const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_slots; i += (int64_t)gridDim.x * blockDim.x)
@@ -251,6 +263,16 @@ extern "C" int pg_count_short(const pg_table *t, const int64_t *d_seq_off, int64
     int strands = t->mode == PG_MODE_LITERAL ? 1 : 2;
     // a record is owned by the range holding its offset; the range that ends the stream also owns trailing empty records
     k2_count_short<<<(unsigned)((n_rec + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(d_seq_off, n_rec, g_begin, g_end, g_end, t->k, strands, t->d_stats);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_count_short_dev(const pg_table *t, const int64_t *d_seq_off, const int64_t *d_counts, int64_t cap_records,
+                                  pg_stream_t stream_) {
+    int rc = check_table(t, "pg_count_short_dev"); if (rc) return rc;
+    if (!d_seq_off || !d_counts || cap_records < 0) return pg_fail(PG_ERR_INVALID, "pg_count_short_dev: bad arguments");
+    int strands = t->mode == PG_MODE_LITERAL ? 1 : 2;
+    k2_count_short_dev<<<32, 256, 0, (cudaStream_t)stream_>>>(d_seq_off, d_counts, cap_records, t->k, strands, t->d_stats);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

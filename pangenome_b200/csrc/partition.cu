@@ -37,6 +37,9 @@ struct PartArgs {
     // distinct-key estimator: keys whose mix has bits 8..15 == 0 (a 1/256 sample of the KEY space, so every
     // occurrence of a sampled key is sampled) go into a small CAS set; 256 x its size estimates the table
     uint64_t *sample_keys; uint64_t sample_mask; unsigned long long *sample_count;
+    // device-side arguments: when set, n_rec / the stream range come from K1's count block and record
+    // index ON THE DEVICE, so the host can enqueue K1 -> K2a -> K3 without waiting for K1's result
+    const int64_t *d_counts; int64_t cap_records;
 };
 
 __device__ __forceinline__ void sample_key(const PartArgs &a, uint64_t key, uint64_t h) {
@@ -66,6 +69,19 @@ template <int MODE, int KP_THREADS>
 __global__ void __launch_bounds__(KP_THREADS)
 k2a_partition(PartArgs a) {
     constexpr int KP_TILE = KP_THREADS * KP_G;
+    if (a.d_counts) {      // all records of the packed stream, bounds read from the device
+        const int64_t n_rec = a.d_counts[0];
+        if (n_rec > a.cap_records) {          // the record index was truncated: poison bucket 0, the host falls back
+            if (blockIdx.x == 0 && threadIdx.x == 0) a.part_counts[0] = 1ull << 62;
+            return;
+        }
+        a.n_rec = n_rec;
+        a.g_begin = n_rec > 0 ? a.seq_off[0] : 0;
+        a.g_end = n_rec > 0 ? a.seq_off[n_rec] : 0;
+        a.n_words = ((a.g_end + 31) >> 5) + 4;
+        a.t_first = a.g_begin / KP_TILE;
+        a.n_tiles = (a.g_end + KP_TILE - 1) / KP_TILE - a.t_first;
+    }
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int RPP = (MODE == PG_MODE_LITERAL_RC) ? 2 : 1;               // records per position
     constexpr int MAXR = KP_TILE * RPP;
@@ -263,7 +279,7 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
                             int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
                             uint64_t *d_records, uint64_t *const *d_peers, int my_rank, int64_t part_cap,
                             int64_t *d_part_counts, uint64_t *d_sample_keys, int64_t sample_cap, int64_t *d_sample_count,
-                            pg_stream_t stream_) {
+                            const int64_t *d_counts, int64_t cap_records, int64_t max_bases, pg_stream_t stream_) {
     if (!t || t->k < 1 || t->k > 27 || t->mode < 0 || t->mode > 2)
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: bad table descriptor (only mode and k are used)");
     if (!d_pk2 || !d_amb || !d_seq_off || (!d_records && !d_peers) || !d_part_counts || n_rec < 0 || g_begin < 0 || g_end < g_begin || part_cap < 1)
@@ -273,6 +289,7 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
     cudaStream_t st = (cudaStream_t)stream_;
     int n_parts = 1 << (owner_bits + sub_bits);
     PG_CUDA(cudaMemsetAsync(d_part_counts, 0, (size_t)n_parts * 8, st));
+    if (d_counts) { n_rec = 1; g_begin = 0; g_end = max_bases > 0 ? max_bases : 1; }     // grid sizing only; the kernel reads the real values
     if (n_rec == 0 || g_end == g_begin) return PG_OK;
     PartArgs a;
     a.pk2 = reinterpret_cast<const uint64_t *>(d_pk2); a.amb = d_amb; a.n_words = ((g_end + 31) >> 5) + 4;
@@ -286,6 +303,7 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
     a.records = reinterpret_cast<uint4 *>(d_records); a.part_cap = part_cap;
     a.peers = reinterpret_cast<uint4 *const *>(d_peers); a.my_rank = my_rank;
     a.part_counts = reinterpret_cast<unsigned long long *>(d_part_counts);
+    a.d_counts = d_counts; a.cap_records = cap_records;
     a.sample_keys = nullptr; a.sample_mask = 0; a.sample_count = nullptr;
     if (d_sample_keys) {
         if (!d_sample_count || sample_cap < 2 || (sample_cap & (sample_cap - 1)))
@@ -325,7 +343,17 @@ extern "C" int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const
                                  uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, uint64_t *d_sample_keys,
                                  int64_t sample_cap, int64_t *d_sample_count, pg_stream_t stream_) {
     return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, owner_bits, sub_bits, d_records, nullptr, 0,
-                            part_cap, d_part_counts, d_sample_keys, sample_cap, d_sample_count, stream_);
+                            part_cap, d_part_counts, d_sample_keys, sample_cap, d_sample_count, nullptr, 0, 0, stream_);
+}
+
+// Same as pg_kmer_partition over ALL records of a packed stream, but n_rec and the stream range are read on
+// the device from K1's outputs (d_counts[0], d_seq_off) - nothing K1 produced has to reach the host first.
+extern "C" int pg_kmer_partition_dev(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                                     const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
+                                     uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream_) {
+    if (!d_counts || cap_records < 0 || max_bases < 0) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_dev: bad arguments");
+    return partition_launch(t, d_pk2, d_amb, d_seq_off, 1, 0, 1, owner_bits, sub_bits, d_records, nullptr, 0,
+                            part_cap, d_part_counts, nullptr, 0, nullptr, d_counts, cap_records, max_bases, stream_);
 }
 
 extern "C" int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
@@ -335,7 +363,7 @@ extern "C" int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, c
     if (!d_peer_bases || my_rank < 0 || my_rank >= (1 << owner_bits))
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p: bad peer table / rank");
     return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, owner_bits, sub_bits, nullptr, d_peer_bases, my_rank,
-                            part_cap, d_part_counts, nullptr, 0, nullptr, stream_);
+                            part_cap, d_part_counts, nullptr, 0, nullptr, nullptr, 0, 0, stream_);
 }
 
 // ---- peer memory for the fused exchange (CUDA IPC; one process per GPU) ------------------------

@@ -54,9 +54,12 @@ class PackedSeqs:
     """Result of K1 (pg_fasta_scan_pack): the 2-bit packed base stream plus the
     record index.  Replaces what seqio_jit_ (kmer_numba.py:135-168) yields."""
 
-    def __init__(self, d_fasta, cap_records=1 << 12):
+    def __init__(self, d_fasta, cap_records=1 << 12, lazy=False):
+        """``lazy``: enqueue K1 and return without reading the record index back; ``n_rec``,
+        ``seq_off`` ... are fetched (one D2H, synchronising) the first time the host asks for them.
+        The device-argument kernels (pg_kmer_partition_dev, ...) never need them on the host."""
         _require_cuda()
-        L = _lib.load()
+        self.L = L = _lib.load()
         self.d_fasta = d_fasta
         nbytes = int(d_fasta.numel())
         dev = d_fasta.device
@@ -64,36 +67,56 @@ class PackedSeqs:
         words = int(L.pg_pack_words(nbytes))
         self.pk2 = torch.empty(words, dtype=torch.int32, device=dev)
         self.amb = torch.empty(words, dtype=torch.int32, device=dev)
-        ws_bytes = int(L.pg_fasta_workspace_bytes(nbytes))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self._ws_bytes = int(L.pg_fasta_workspace_bytes(nbytes))
+        self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=dev)
+        self.launches = 3
+        self._host = None
+        self._launch(cap_records)
+        if not lazy:
+            self._fetch()
+
+    def _launch(self, cap_records):
         # counts, seq_off and hdr_off share ONE device buffer so the record index comes back in one D2H
+        L, nbytes = self.L, self.nbytes
+        self.cap_records = cap_records
+        idx = torch.empty(4 + (cap_records + 2) + (cap_records + 1), dtype=torch.int64, device=self.pk2.device)
+        self._idx = idx
+        self.d_counts = idx[:4]
+        self.d_seq_off = idx[4:4 + cap_records + 2]
+        self.d_hdr_off = idx[4 + cap_records + 2:]
+        check(L.pg_fasta_scan_pack(_ptr(self.d_fasta) if nbytes else None, nbytes, _ptr(self.pk2), _ptr(self.amb),
+                                   nbytes, _ptr(self.d_hdr_off), _ptr(self.d_seq_off), cap_records,
+                                   _ptr(self.d_counts), _ptr(self._ws), self._ws_bytes, _stream()), "pg_fasta_scan_pack")
+
+    def _fetch(self):
+        if self._host is not None:
+            return self._host
         while True:
-            idx = torch.empty(4 + (cap_records + 2) + (cap_records + 1), dtype=torch.int64, device=dev)
-            self.d_counts = idx[:4]
-            self.d_seq_off = idx[4:4 + cap_records + 2]
-            self.d_hdr_off = idx[4 + cap_records + 2:]
-            check(L.pg_fasta_scan_pack(_ptr(d_fasta) if nbytes else None, nbytes, _ptr(self.pk2), _ptr(self.amb),
-                                       nbytes, _ptr(self.d_hdr_off), _ptr(self.d_seq_off), cap_records,
-                                       _ptr(self.d_counts), _ptr(ws), ws_bytes, _stream()), "pg_fasta_scan_pack")
-            if cap_records <= 1 << 16:
-                h = idx.cpu().numpy()                    # synchronises: the host needs the record index
+            cap = self.cap_records
+            if cap <= 1 << 16:
+                h = self._idx.cpu().numpy()              # synchronises: the host needs the record index
                 counts = h[:4]
             else:
                 h = None
                 counts = self.d_counts.cpu().numpy()
-            self.n_rec = int(counts[0])
-            if self.n_rec <= cap_records:
+            n_rec = int(counts[0])
+            if n_rec <= cap:
                 break
-            cap_records = next_pow2(self.n_rec + 1)
-        self.n_bases = int(counts[1])
-        self.n_newlines = int(counts[2])
+            self._launch(next_pow2(n_rec + 1))           # the index was truncated: pack again with room for it
         if h is not None:
-            self.seq_off = h[4:4 + self.n_rec + 1].copy()
-            self.hdr_off = h[4 + cap_records + 2:4 + cap_records + 2 + self.n_rec].copy()
+            seq_off = h[4:4 + n_rec + 1].copy()
+            hdr_off = h[4 + cap + 2:4 + cap + 2 + n_rec].copy()
         else:
-            self.seq_off = self.d_seq_off[:self.n_rec + 1].cpu().numpy()
-            self.hdr_off = self.d_hdr_off[:self.n_rec].cpu().numpy()
-        self.launches = 3
+            seq_off = self.d_seq_off[:n_rec + 1].cpu().numpy()
+            hdr_off = self.d_hdr_off[:n_rec].cpu().numpy()
+        self._host = dict(n_rec=n_rec, n_bases=int(counts[1]), n_newlines=int(counts[2]), seq_off=seq_off, hdr_off=hdr_off)
+        return self._host
+
+    n_rec = property(lambda self: self._fetch()["n_rec"])
+    n_bases = property(lambda self: self._fetch()["n_bases"])
+    n_newlines = property(lambda self: self._fetch()["n_newlines"])
+    seq_off = property(lambda self: self._fetch()["seq_off"])
+    hdr_off = property(lambda self: self._fetch()["hdr_off"])
 
     @property
     def seq_lengths(self):
@@ -442,9 +465,41 @@ class TwoPhaseBuilder:
             ev.setdefault("insert", []).append((e[2], e[3]))
         return t
 
+    def build_async(self, packed, ev=None):
+        """K2a + K3 over ALL records of ``packed`` with device-side arguments: nothing is read back
+        from K1, so pack -> partition -> insert is enqueued back to back (PackedSeqs(lazy=True)).
+        Needs the upper-bound table (no estimator) and a record index that fits ``cap_records``
+        (otherwise verify() raises and the caller uses build())."""
+        if self.sampler is not None:
+            raise PgError("build_async sizes the table before K2a: construct the builder with estimate=False")
+        t, b, L = self.table, self.buckets, self.L
+        st = torch.cuda.current_stream()
+        if not getattr(self, "_begun", False):
+            self.begin()
+        self._begun = False
+        if ev is not None:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(st)
+        desc = PgTable(None, 2, None, self.mode, self.k)
+        check(L.pg_kmer_partition_dev(ctypes.byref(desc), _ptr(packed.pk2), _ptr(packed.amb), _ptr(packed.d_seq_off),
+                                      _ptr(packed.d_counts), packed.cap_records, packed.nbytes, self.owner_bits, self.sub_bits,
+                                      _ptr(b.records), b.part_cap, _ptr(b.counts), _stream()), "pg_kmer_partition_dev")
+        st.wait_stream(self.side)            # K3 needs the cleared table
+        check(L.pg_count_short_dev(ctypes.byref(t.c), _ptr(packed.d_seq_off), _ptr(packed.d_counts), packed.cap_records, _stream()),
+              "pg_count_short_dev")
+        if ev is not None:
+            e[1].record(st)
+        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, _stream()),
+              "pg_insert_records")
+        if ev is not None:
+            e[2].record(st)
+            ev.setdefault("partition", []).append((e[0], e[1]))
+            ev.setdefault("insert", []).append((e[1], e[2]))
+        return t
+
     def verify(self):
         """After a synchronise: raise if a bucket or the table overflowed."""
         if int(self.buckets.counts.max().item()) > self.buckets.part_cap:
-            raise PgError("record bucket overflow (hash skew): use build_dbg()")
+            raise PgError("record bucket overflow (hash skew) or truncated record index: use build_dbg()")
         if self.table.overflowed():
             raise PgError("dBG table overflow")

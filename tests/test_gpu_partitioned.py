@@ -99,3 +99,29 @@ def test_table_sized_from_key_sample(eng):
     assert abs(b.last_estimate - ref_t.n_keys()) < 0.05 * ref_t.n_keys()
     assert t.capacity < b.cap_max and 0.17 < t.n_keys() / t.capacity <= 0.36
     assert t.checksum() == ref_t.checksum()
+
+
+def test_async_build_device_args(eng):
+    """pack -> partition -> insert enqueued without reading K1's record index back (device-side bounds)."""
+    from pangenome_b200 import _lib
+    for data in (pangenome(5, 300_000), b">a\nACGTACGTTGCAAGGCTTAACCGGATAGGCTTACGATCGGATCTTAGGA\n>s\nACG\n>e\n\n>b\nTTGACGGTCATTGCAGGCATTACGGATCGATCGGCTAGCTAGGCTAGG\n"):
+        ref_p = eng.PackedSeqs(eng.to_device_bytes(data))
+        ref_t, _ = eng.build_dbg(ref_p, 21)
+        b = eng.TwoPhaseBuilder(21, _lib.PG_MODE_CANONICAL, max(ref_p.n_positions(21), 64), estimate=False)
+        for _ in range(2):
+            b.begin()
+            p = eng.PackedSeqs(eng.to_device_bytes(data), lazy=True)
+            t = b.build_async(p)
+        b.verify()
+        assert t.checksum() == ref_t.checksum()
+        assert t.export()[0].tolist() == ref_t.export()[0].tolist()
+        assert p.seq_off.tolist() == ref_p.seq_off.tolist()          # the lazy index is still available afterwards
+    # a record index that does not fit cap_records is reported, not silently truncated
+    many = b"".join(b">r%d\nACGTTGCAAGGCTTAACCGGATAGG\n" % i for i in range(40))
+    p = eng.PackedSeqs(eng.to_device_bytes(many), cap_records=8, lazy=True)
+    b = eng.TwoPhaseBuilder(11, _lib.PG_MODE_CANONICAL, 4096, estimate=False)
+    b.build_async(p)
+    import pytest as _pt
+    with _pt.raises(_lib.PgError):
+        b.verify()
+    assert p.n_rec == 40                                             # fetching re-packs with a larger index
