@@ -135,7 +135,8 @@ int pg_kmer_insert(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_a
  * pg_insert_records: upsert the records of n_regions x n_src segments
  *   [seg_off[b*n_src+j], +seg_cnt[b*n_src+j]) of d_records (record units), region after region
  *   (n_src = source ranks x pipeline chunks that contributed to a region; 1 on a single GPU), so
- *   that the table region being updated stays in L2.
+ *   that the table region being updated stays in L2.  seg_cap (> 0) clamps every segment count: a count
+ *   above the bucket capacity only says that K2a dropped records, K3 must not read past the bucket.
  *   Replaces the same reference lines as pg_kmer_insert; the all-to-all between the two calls is
  *   the host's (torch.distributed / NCCL).
  */
@@ -169,7 +170,7 @@ int pg_kmer_partition_dev(const pg_table *t, const uint32_t *d_pk2, const uint32
 int pg_count_short_dev(const pg_table *t, const int64_t *d_seq_off, const int64_t *d_counts, int64_t cap_records,
                        pg_stream_t stream);
 int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
-                      const int64_t *d_seg_cnt, int n_regions, int n_src, pg_stream_t stream);
+                      const int64_t *d_seg_cnt, int n_regions, int n_src, int64_t seg_cap, pg_stream_t stream);
 
 /* ---- table read-out ---------------------------------------------------------
  * pg_table_count   : fills PG_STAT_USED / PG_STAT_ENTRIES in t->d_stats.

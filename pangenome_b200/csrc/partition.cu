@@ -229,10 +229,11 @@ constexpr int K3_MAX_SRC = 64;
 // record i of region b's concatenated segments (false past the end).  No shared memory and no
 // barriers: every warp walks the regions at its own pace, the segment table is read through L1.
 __device__ __forceinline__ bool k3_fetch(const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
-                                         const int64_t *__restrict__ seg_cnt, int n_src, int b, int64_t i, uint4 &r) {
+                                         const int64_t *__restrict__ seg_cnt, int n_src, int64_t seg_cap, int b, int64_t i, uint4 &r) {
     const int64_t *off = seg_off + (int64_t)b * n_src, *cnt = seg_cnt + (int64_t)b * n_src;
     for (int j = 0; j < n_src; j++) {
         int64_t c = __ldg(cnt + j);
+        if (c > seg_cap) c = seg_cap;      // a count above the segment capacity means records were dropped (the host checks); never read past it
         if (i < c) { r = pg_ld_stream(records + __ldg(off + j) + i); return true; }
         i -= c;
     }
@@ -241,27 +242,27 @@ __device__ __forceinline__ bool k3_fetch(const uint4 *__restrict__ records, cons
 template <bool PREFETCH>
 __global__ void __launch_bounds__(256)
 k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
-                  const int64_t *__restrict__ seg_cnt, int n_regions, int n_src) {
+                  const int64_t *__restrict__ seg_cnt, int n_regions, int n_src, int64_t seg_cap) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     uint32_t n_claimed = 0;
     if (PREFETCH) {
         uint4 r;
-        bool have = k3_fetch(records, seg_off, seg_cnt, n_src, 0, i0, r);
+        bool have = k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, 0, i0, r);
         for (int b = 0; b < n_regions; b++) {
             int64_t i = i0;
             while (have) {
                 const uint4 cur = r;
                 i += stride;
-                have = k3_fetch(records, seg_off, seg_cnt, n_src, b, i, r);
+                have = k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b, i, r);
                 table_upsert(t, (uint64_t)cur.x | ((uint64_t)cur.y << 32), cur.z, cur.w, n_claimed);
             }
-            if (b + 1 < n_regions) have = k3_fetch(records, seg_off, seg_cnt, n_src, b + 1, i0, r);
+            if (b + 1 < n_regions) have = k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b + 1, i0, r);
         }
     } else {
         for (int b = 0; b < n_regions; b++) {
             uint4 r;
-            for (int64_t i = i0; k3_fetch(records, seg_off, seg_cnt, n_src, b, i, r); i += stride)
+            for (int64_t i = i0; k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b, i, r); i += stride)
                 table_upsert(t, (uint64_t)r.x | ((uint64_t)r.y << 32), r.z, r.w, n_claimed);
         }
     }
@@ -387,12 +388,13 @@ extern "C" int pg_peer_close(void *d_ptr) { PG_CUDA(cudaIpcCloseMemHandle(d_ptr)
 extern "C" int pg_peer_free(void *d_ptr) { PG_CUDA(cudaFree(d_ptr)); return PG_OK; }
 
 extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
-                                 const int64_t *d_seg_cnt, int n_regions, int n_src, pg_stream_t stream_) {
+                                 const int64_t *d_seg_cnt, int n_regions, int n_src, int64_t seg_cap, pg_stream_t stream_) {
     if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)))
         return pg_fail(PG_ERR_INVALID, "pg_insert_records: bad table");
     if (n_regions < 0 || n_src < 1 || n_src > K3_MAX_SRC || (n_regions > 0 && (!d_records || !d_seg_off || !d_seg_cnt)))
         return pg_fail(PG_ERR_INVALID, "pg_insert_records: bad arguments (n_src must be 1..%d)", K3_MAX_SRC);
     if (n_regions == 0) return PG_OK;
+    if (seg_cap <= 0) seg_cap = INT64_MAX;
     if (reinterpret_cast<uintptr_t>(d_records) & 15) return pg_fail(PG_ERR_INVALID, "pg_insert_records: records must be 16-byte aligned");
     TableView tv = make_view(t);
     static int gmul = -1, prefetch = -1;
@@ -402,9 +404,9 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
     }
     int grid = pg_num_sms() * gmul;
     if (prefetch)
-        k3_insert_records<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src);
+        k3_insert_records<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap);
     else
-        k3_insert_records<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src);
+        k3_insert_records<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

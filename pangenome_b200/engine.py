@@ -375,7 +375,7 @@ def build_dbg_partitioned(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=No
         t = DbgTable(cap, k, mode, device=dev)
         check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
         check(L.pg_insert_records(ctypes.byref(t.c), _ptr(buckets.records), _ptr(buckets.seg_off), _ptr(buckets.counts),
-                                  buckets.n_parts, 1, _stream()), "pg_insert_records")
+                                  buckets.n_parts, 1, buckets.part_cap, _stream()), "pg_insert_records")
         worst = int(buckets.counts.max().item())           # synchronises
         if worst > buckets.part_cap:
             t2, n_rec = build_dbg(packed, k, rc=rc, Ns=Ns, mode=mode, capacity=cap)
@@ -456,7 +456,7 @@ class TwoPhaseBuilder:
         check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
         if ev is not None:
             e[2].record(st)
-        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, _stream()),
+        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, b.part_cap, _stream()),
               "pg_insert_records")
         if ev is not None:
             e[3].record(st)
@@ -489,7 +489,7 @@ class TwoPhaseBuilder:
               "pg_count_short_dev")
         if ev is not None:
             e[1].record(st)
-        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, _stream()),
+        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, b.part_cap, _stream()),
               "pg_insert_records")
         if ev is not None:
             e[2].record(st)

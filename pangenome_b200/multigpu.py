@@ -161,7 +161,7 @@ class DistributedBuilder:
         # counts [chunk][source][sub] -> region-major [sub][chunk][source]
         self.seg_cnt.copy_(self.recv_counts.view(C, W, n_sub).permute(2, 0, 1).reshape(-1))
         eng.check(L.pg_insert_records(ctypes.byref(t.c), eng._ptr(self.recv), eng._ptr(self.seg_off), eng._ptr(self.seg_cnt),
-                                      n_sub, C * W, eng._stream()), "pg_insert_records")
+                                      n_sub, C * W, self.part_cap, eng._stream()), "pg_insert_records")
         if e:
             e[1].record(st)
             ev.setdefault("build", []).append((e[0], e[1]))
@@ -280,7 +280,7 @@ class PeerBuilder:
                       "pg_count_short")
         self.seg_cnt.copy_(self.recv_counts.view(W, n_sub).t().reshape(-1))
         eng.check(L.pg_insert_records(ctypes.byref(t.c), self.own[buf], eng._ptr(self.seg_off), eng._ptr(self.seg_cnt),
-                                      n_sub, W, eng._stream()), "pg_insert_records")
+                                      n_sub, W, self.part_cap, eng._stream()), "pg_insert_records")
         if e:
             e[3].record(st)
             ev.setdefault("build", []).append((e[0], e[3]))

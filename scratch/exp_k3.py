@@ -21,7 +21,7 @@ for cap, sub in ((1 << 25, 32 << 20), (1 << 25, 8 << 20), (1 << 27, 128 << 20), 
     sb = engine.sub_bits_for(cap, sub)
     bk = engine.partition_kmers(p, k, 2, n_rec, 0, sb)
     def both():
-        t.clear(); engine.check(L.pg_insert_records(ctypes.byref(t.c), _ptr(bk.records), _ptr(bk.seg_off), _ptr(bk.counts), bk.n_parts, 1, _stream()), "ins")
+        t.clear(); engine.check(L.pg_insert_records(ctypes.byref(t.c), _ptr(bk.records), _ptr(bk.seg_off), _ptr(bk.counts), bk.n_parts, 1, bk.part_cap, _stream()), "ins")
     ms = timeit(both) - clear_ms
     out.append("cap2^%d/%dparts %.3f" % (int(np.log2(cap)), bk.n_parts, ms))
 print("ILP", os.environ.get("PG_K3_ILP"), "EVICT", os.environ.get("PG_K3_EVICT"), "GRID", os.environ.get("PG_K3_GRID"), " | ".join(out), flush=True)

@@ -26,7 +26,7 @@ for cap in (1 << 27, 1 << 25):
         bk = engine.partition_kmers(p, k, 2, n_rec, 0, sb)
         part_ms = timeit(lambda: engine.partition_kmers(p, k, 2, n_rec, 0, sb, buckets=bk))
         def ins():
-            engine.check(L.pg_insert_records(ctypes.byref(t.c), _ptr(bk.records), _ptr(bk.seg_off), _ptr(bk.counts), bk.n_parts, 1, _stream()), "ins")
+            engine.check(L.pg_insert_records(ctypes.byref(t.c), _ptr(bk.records), _ptr(bk.seg_off), _ptr(bk.counts), bk.n_parts, 1, bk.part_cap, _stream()), "ins")
         def both():
             t.clear(); ins()
         ins_ms = timeit(both) - clear_ms

@@ -63,7 +63,7 @@ def test_record_prefix_ns():
     import numpy as np
     from pangenome_b200.engine import PackedSeqs
     p = PackedSeqs.__new__(PackedSeqs)
-    p.seq_off = np.array([0, 100, 250, 400, 1000])
+    p._host = dict(seq_off=np.array([0, 100, 250, 400, 1000]), n_rec=4)
     assert p.record_prefix(2 ** 63, 2) == 4
     assert p.record_prefix(300, 1) == 3      # 100, 250, 400 > 300
     assert p.record_prefix(300, 2) == 2      # 200, 500 > 300
