@@ -141,25 +141,31 @@ def cpu_reference_rate(data, k, sample_bases, prefer="reference"):
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's own CPU code (numba, oracle/_ref; the C port if numba is missing) on a
+    bounded sample of the same workload per step, sized so that the whole run stays within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    data, wl = workload(args.workload)
-    # bounded sample: every step rebuilds the dBG of the first ~1 Mbp (2 M insertions)
-    sample_bases = 1_000_000
+    data, wl = workload(args.workload if args.gpus == 1 or args.workload != "cfg2" else "cfg2")
+    total_steps = max(1, args.warmup + args.steps)
+    budget_s = 150.0
+    # calibrate on a small sample (also warms the JIT), then size the per-step sample to the time budget
+    r0, kind, cores, text = cpu_reference_rate(data, args.k, 100_000)
+    per_step_s = budget_s / total_steps
+    sample_bases = int(min(1_000_000, max(50_000, r0 * 1e9 * per_step_s / 2)))     # 2 insertions per base
     rates = []
     t0 = time.time()
-    kind = cores = text = None
-    for i in range(args.warmup + args.steps):
+    for i in range(total_steps):
         r, kind, cores, text = cpu_reference_rate(data, args.k, sample_bases)
         if i >= args.warmup:
             rates.append(r)
     val = sum(rates) / len(rates)
-    ms = 1e3 * (time.time() - t0) / max(1, args.warmup + args.steps)
+    ms = 1e3 * (time.time() - t0) / total_steps
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": {"workload": wl, "k": args.k, "rc": True},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": text},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": text,
+                             "host_cpus": os.cpu_count()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 

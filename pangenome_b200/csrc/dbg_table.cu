@@ -10,6 +10,7 @@
 // repeats therefore cost one sector read and no atomic.
 // Replaces oakht.push/has_key/get (:521-603), add_kmer (:1036-1047), build_dbg (:1052-1093),
 // seq2dbg_jit_ (:1202-1230), build_rdbg_jit_ (:1292-1309).
+#include <stdlib.h>
 #include "kmer_core.cuh"
 #include "table_dev.cuh"
 
@@ -250,7 +251,14 @@ extern "C" int pg_table_clear(const pg_table *t, pg_stream_t stream_) {
     int rc = check_table(t, "pg_table_clear"); if (rc) return rc;
     pg_tune_once();
     cudaStream_t stream = (cudaStream_t)stream_;
-    k_table_clear<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(reinterpret_cast<uint4 *>(t->d_slots), t->capacity, t->d_stats);
+    // The clear is pure DRAM writes and usually runs on a side stream next to K1/K2a (ALU bound): a full-occupancy
+    // grid would fill every SM's thread slots and make those kernels queue behind it, so it takes 2 CTAs per SM
+    // (stores are fire-and-forget: 16 warps per SM keep HBM busy) and leaves the rest of the SM to its neighbours.
+    static int per_sm = -1;
+    if (per_sm < 0) { const char *e = getenv("PG_CLEAR_CTAS_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 1; }
+    int64_t want = (t->capacity + 255) / 256, cap_grid = (int64_t)pg_num_sms() * per_sm;
+    int grid = (int)(want < cap_grid ? want : cap_grid);
+    k_table_clear<<<grid, 256, 0, stream>>>(reinterpret_cast<uint4 *>(t->d_slots), t->capacity, t->d_stats);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
