@@ -512,22 +512,37 @@ def bench(args, world, rank, local, ClockSampler=None):
     stage = torch.tensor([avg("build"), avg("k2a_all_chunks"), avg("until_exchange_done"), avg("k3")], dtype=torch.float64, device="cuda")
     dist.all_reduce(stage, op=dist.ReduceOp.MAX)
 
-    # end to end: pinned host bytes -> H2D -> build -> D2H of the table statistics
-    def step_e2e():
-        if hasattr(builder, "begin"):
-            builder.begin()
-        d = host.to("cuda", non_blocking=True)
-        p = engine.PackedSeqs(d)
-        tt = builder.build(p, n_rec)
-        return tt.stats_host()
-    for _ in range(2):
-        step_e2e()
+    # end to end: every step uploads its own copy of the shard from pinned host memory (double-buffered on a
+    # copy stream: the upload of step i+1 is issued before step i's result is awaited), builds, and reads the
+    # table statistics back
+    copy_stream = torch.cuda.Stream()
+    dev_in = [torch.empty_like(d_fasta) for _ in range(2)]
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            dev_in[i % 2].copy_(host, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        return done
+
+    def run_e2e(n):
+        nxt = upload(0)
+        for i in range(n):
+            cur = nxt
+            if i + 1 < n:
+                nxt = upload(i + 1)
+            if hasattr(builder, "begin"):
+                builder.begin()
+            stream.wait_event(cur)
+            p = engine.PackedSeqs(dev_in[i % 2])
+            tt = builder.build(p, n_rec)
+            tt.stats_host()
+    run_e2e(2)
     dist.barrier()
     torch.cuda.synchronize()
     g0, g1 = ev(), ev()
     g0.record(stream)
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     g1.record(stream)
     dist.barrier()
     torch.cuda.synchronize()
