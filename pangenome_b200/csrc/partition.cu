@@ -278,24 +278,22 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
 // inserts into region b after cleared[b] and cleared[b+1] (linear probing may spill over the region's end) are
 // complete.  All CTAs must be co-resident (the launcher sizes the grid from the occupancy calculator); the spin
 // is bounded and raises PG_STAT_OVERFLOW instead of hanging.
-constexpr int K3_LAG = 4;
-// the CTA's share of region r is cleared by ONE of its warps (they take turns: warp r mod 8), so the
-// hand-shake costs one global atomicAdd per CTA per region instead of one per warp
-__device__ __forceinline__ void k3_clear_share(const TableView &t, int64_t slots_per_region, int r, int lane) {
+constexpr int K3_LAG = 3;
+__device__ __forceinline__ void k3_clear_region(const TableView &t, int64_t slots_per_region, int r, int64_t warp_id, int64_t n_warps, int lane) {
     uint4 *base = reinterpret_cast<uint4 *>(t.slots) + (int64_t)r * slots_per_region;
     const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-    for (int64_t i = (int64_t)blockIdx.x * 32 + lane; i < slots_per_region; i += (int64_t)gridDim.x * 32) base[i] = e;   // 512-byte pieces: whole lines
+    // contiguous 512-byte pieces per warp so that whole 128-byte lines are written by one instruction
+    for (int64_t i = warp_id * 32 + lane; i < slots_per_region; i += n_warps * 32) base[i] = e;
 }
-__device__ __forceinline__ int k3_peek(const int *ctr) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr));
-    return v;
-}
-__device__ __forceinline__ bool k3_wait(const int *ctr, int seen, int want, int lane) {
+__device__ __forceinline__ bool k3_wait(const int *ctr, int want, int lane) {
     bool ok = true;
     if (lane == 0) {
-        int v = seen, spins = 0;
-        while (v < want && ++spins < (1 << 22)) { __nanosleep(32); v = k3_peek(ctr); }
+        int v, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr));
+            if (v >= want) break;
+            __nanosleep(64);
+        } while (++spins < (1 << 22));
         ok = v >= want;
     }
     return __shfl_sync(0xffffffffu, ok, 0);
@@ -305,34 +303,29 @@ k3_insert_records_fused(TableView t, const uint4 *__restrict__ records, const in
                         const int64_t *__restrict__ seg_cnt, int n_regions, int n_src, int64_t seg_cap, int *cleared) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_ctas = (int)gridDim.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_id = i0 >> 5, n_warps = stride >> 5;
     const int64_t slots_per_region = (int64_t)(t.capmask + 1) / n_regions;
     uint32_t n_claimed = 0;
     bool healthy = true;
-    auto clear_turn = [&](int r) {
-        if (r < n_regions && warp == (r & 7)) {
-            k3_clear_share(t, slots_per_region, r, lane);
-            __syncwarp();
-            if (lane == 0) { __threadfence(); atomicAdd(cleared + r, 1); }
-        }
-    };
-    for (int r = 0; r < K3_LAG; r++) clear_turn(r);        // prologue: regions 0 .. LAG-1
-    int verified = 0;                                        // regions [0, verified) are known to be cleared by every CTA
+    // prologue: regions 0 .. LAG-1
+    for (int r = 0; r < K3_LAG && r < n_regions; r++) {
+        k3_clear_region(t, slots_per_region, r, warp_id, n_warps, lane);
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicAdd(cleared + r, 1); }
+    }
     for (int b = 0; b < n_regions; b++) {
-        // region b and b+1 (linear probing may spill over the region's end) must be clear; b was verified last turn
-        const int need = b + 2 < n_regions ? b + 2 : n_regions;
-        int seen = 0;
-        if (verified < need && lane == 0) seen = k3_peek(cleared + need - 1);     // issued early, checked after the clear turn
-        clear_turn(b + K3_LAG);
-        if (verified < need) {
-            for (int r = verified; r < need - 1; r++) healthy = k3_wait(cleared + r, 0, n_ctas, lane) && healthy;
-            healthy = k3_wait(cleared + need - 1, seen, n_ctas, lane) && healthy;
-            verified = need;
-        }
+        healthy = k3_wait(cleared + b, (int)n_warps, lane) && healthy;
+        if (b + 1 < n_regions) healthy = k3_wait(cleared + b + 1, (int)n_warps, lane) && healthy;
         uint4 r;
         for (int64_t i = i0; k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b, i, r); i += stride)
             table_upsert(t, (uint64_t)r.x | ((uint64_t)r.y << 32), r.z, r.w, n_claimed);
+        const int rc = b + K3_LAG;
+        if (rc < n_regions) {
+            k3_clear_region(t, slots_per_region, rc, warp_id, n_warps, lane);
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicAdd(cleared + rc, 1); }
+        }
     }
     if (!healthy && lane == 0) atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 2ull);
     publish_claims(t, n_claimed);
