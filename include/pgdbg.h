@@ -144,15 +144,6 @@ int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *
                       int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
                       uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts,
                       uint64_t *d_sample_keys, int64_t sample_cap, int64_t *d_sample_count, pg_stream_t stream);
-/* K3 with the table clear fused in (clear-ahead): regions are cleared in L2 a few regions ahead of the insert
- * sweep, so the table is never cleared in a separate pass and never filled from HBM.  Call pg_table_reset
- * (statistics only) instead of pg_table_clear, then pg_count_short*, then this.  n_regions = the number of
- * hash-prefix regions the records were bucketed into (power of two, divides the capacity); d_cleared =
- * n_regions int32 of workspace.  If the inter-warp hand-shake ever times out PG_STAT_OVERFLOW is set to 2. */
-int pg_table_reset(const pg_table *t, pg_stream_t stream);
-int pg_insert_records_fused(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
-                            const int64_t *d_seg_cnt, int n_regions, int n_src, int64_t seg_cap, int32_t *d_cleared,
-                            pg_stream_t stream);
 /* Fused extraction + exchange over NVLink peer memory: like pg_kmer_partition, but bucket
  * (owner, sub) is stored straight into rank `owner`'s receive buffer (d_peer_bases[owner], a
  * peer-mapped pointer; the own rank's entry is its own buffer) at slice

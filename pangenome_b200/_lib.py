@@ -48,8 +48,6 @@ SIGNATURES = {
     "pg_peer_free": (c_int, [c_vp]),
     "pg_kmer_partition_dev": (c_int, [PT, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
     "pg_count_short_dev": (c_int, [PT, c_vp, c_vp, c_i64, c_vp]),
-    "pg_table_reset": (c_int, [PT, c_vp]),
-    "pg_insert_records_fused": (c_int, [PT, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp]),
     "pg_insert_records": (c_int, [PT, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "pg_table_count": (c_int, [PT, c_vp]),
     "pg_table_export": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),

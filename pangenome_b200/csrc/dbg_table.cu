@@ -263,13 +263,6 @@ extern "C" int pg_table_clear(const pg_table *t, pg_stream_t stream_) {
     return PG_OK;
 }
 
-// zero the statistics of a table whose slots will be cleared by pg_insert_records_fused itself
-extern "C" int pg_table_reset(const pg_table *t, pg_stream_t stream_) {
-    int rc = check_table(t, "pg_table_reset"); if (rc) return rc;
-    PG_CUDA(cudaMemsetAsync(t->d_stats, 0, PG_STAT_WORDS * sizeof(int64_t), (cudaStream_t)stream_));
-    return PG_OK;
-}
-
 extern "C" int pg_count_short(const pg_table *t, const int64_t *d_seq_off, int64_t n_rec, int64_t g_begin, int64_t g_end,
                               pg_stream_t stream_) {
     int rc = check_table(t, "pg_count_short"); if (rc) return rc;

@@ -269,68 +269,6 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
     publish_claims(t, n_claimed);
 }
 
-// K3 with the table clear fused in ("clear-ahead").  Instead of a separate pass that writes EMPTY over the whole
-// table to HBM and a K3 that later pulls every touched line back in (ncu: 1.5 GB of fills for 0.5 GB of useful
-// sectors), every warp clears its share of region b+LAG right after it finished inserting into region b: the
-// cleared lines are born in L2 (whole-line writes need no fill) and are still there when the grid reaches that
-// region, so slot probes hit L2 and each table line travels to HBM exactly once, as a write-back.
-// Ordering without grid-wide barriers: cleared[r] counts the warps that finished clearing region r; a warp only
-// inserts into region b after cleared[b] and cleared[b+1] (linear probing may spill over the region's end) are
-// complete.  All CTAs must be co-resident (the launcher sizes the grid from the occupancy calculator); the spin
-// is bounded and raises PG_STAT_OVERFLOW instead of hanging.
-constexpr int K3_LAG = 3;
-__device__ __forceinline__ void k3_clear_region(const TableView &t, int64_t slots_per_region, int r, int64_t warp_id, int64_t n_warps, int lane) {
-    uint4 *base = reinterpret_cast<uint4 *>(t.slots) + (int64_t)r * slots_per_region;
-    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-    // contiguous 512-byte pieces per warp so that whole 128-byte lines are written by one instruction
-    for (int64_t i = warp_id * 32 + lane; i < slots_per_region; i += n_warps * 32) base[i] = e;
-}
-__device__ __forceinline__ bool k3_wait(const int *ctr, int want, int lane) {
-    bool ok = true;
-    if (lane == 0) {
-        int v, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr));
-            if (v >= want) break;
-            __nanosleep(64);
-        } while (++spins < (1 << 22));
-        ok = v >= want;
-    }
-    return __shfl_sync(0xffffffffu, ok, 0);
-}
-__global__ void __launch_bounds__(256)
-k3_insert_records_fused(TableView t, const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
-                        const int64_t *__restrict__ seg_cnt, int n_regions, int n_src, int64_t seg_cap, int *cleared) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp_id = i0 >> 5, n_warps = stride >> 5;
-    const int64_t slots_per_region = (int64_t)(t.capmask + 1) / n_regions;
-    uint32_t n_claimed = 0;
-    bool healthy = true;
-    // prologue: regions 0 .. LAG-1
-    for (int r = 0; r < K3_LAG && r < n_regions; r++) {
-        k3_clear_region(t, slots_per_region, r, warp_id, n_warps, lane);
-        __syncwarp();
-        if (lane == 0) { __threadfence(); atomicAdd(cleared + r, 1); }
-    }
-    for (int b = 0; b < n_regions; b++) {
-        healthy = k3_wait(cleared + b, (int)n_warps, lane) && healthy;
-        if (b + 1 < n_regions) healthy = k3_wait(cleared + b + 1, (int)n_warps, lane) && healthy;
-        uint4 r;
-        for (int64_t i = i0; k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b, i, r); i += stride)
-            table_upsert(t, (uint64_t)r.x | ((uint64_t)r.y << 32), r.z, r.w, n_claimed);
-        const int rc = b + K3_LAG;
-        if (rc < n_regions) {
-            k3_clear_region(t, slots_per_region, rc, warp_id, n_warps, lane);
-            __syncwarp();
-            if (lane == 0) { __threadfence(); atomicAdd(cleared + rc, 1); }
-        }
-    }
-    if (!healthy && lane == 0) atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 2ull);
-    publish_claims(t, n_claimed);
-}
-
 int part_smem_bytes(int mode, int n_parts, int threads) {
     int maxr = (mode == PG_MODE_LITERAL_RC ? 2 : 1) * threads * KP_G;
     return maxr * 16 + maxr * 2 * 2 + (3 * n_parts + (n_parts & 1)) * 4 + n_parts * 8 + 16;
@@ -469,33 +407,6 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
         k3_insert_records<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap);
     else
         k3_insert_records<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap);
-    PG_CUDA(cudaGetLastError());
-    return PG_OK;
-}
-
-// K3 with the clear fused in: the table must NOT be cleared beforehand (pg_table_reset zeroes its statistics);
-// d_cleared = n_regions ints of workspace (zeroed here).  n_regions must divide the capacity.
-extern "C" int pg_insert_records_fused(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
-                                       const int64_t *d_seg_cnt, int n_regions, int n_src, int64_t seg_cap, int32_t *d_cleared,
-                                       pg_stream_t stream_) {
-    if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)))
-        return pg_fail(PG_ERR_INVALID, "pg_insert_records_fused: bad table");
-    if (n_regions < 1 || (n_regions & (n_regions - 1)) || n_regions > t->capacity || n_src < 1 || n_src > K3_MAX_SRC || !d_records ||
-        !d_seg_off || !d_seg_cnt || !d_cleared)
-        return pg_fail(PG_ERR_INVALID, "pg_insert_records_fused: bad arguments (n_regions: power of two <= capacity, n_src 1..%d)", K3_MAX_SRC);
-    if (seg_cap <= 0) seg_cap = INT64_MAX;
-    if (reinterpret_cast<uintptr_t>(d_records) & 15) return pg_fail(PG_ERR_INVALID, "pg_insert_records_fused: records must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream_;
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        int n = 0;
-        PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k3_insert_records_fused, 256, 0));
-        per_sm = n < 1 ? 1 : n;
-    }
-    PG_CUDA(cudaMemsetAsync(d_cleared, 0, (size_t)n_regions * sizeof(int32_t), st));
-    int grid = pg_num_sms() * per_sm;          // every CTA resident: the clear-ahead counters are waited on
-    k3_insert_records_fused<<<grid, 256, 0, st>>>(make_view(t), reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt,
-                                                  n_regions, n_src, seg_cap, d_cleared);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

@@ -392,8 +392,7 @@ class TwoPhaseBuilder:
     (which also samples the key space), sizes the table from the estimate - a small D2H - then clears
     just that much of the buffer and runs K3."""
 
-    def __init__(self, k, mode, n_positions, device="cuda", capacity=None, sub_bytes=8 << 20, owner_bits=0, estimate=None,
-                 fused_clear=None):
+    def __init__(self, k, mode, n_positions, device="cuda", capacity=None, sub_bytes=8 << 20, owner_bits=0, estimate=None):
         self.L = _lib.load()
         self.k, self.mode = int(min(max(1, k), 27)), int(mode)
         per_pos = 2 if mode == _lib.PG_MODE_LITERAL_RC else 1
@@ -412,28 +411,14 @@ class TwoPhaseBuilder:
             free = torch.cuda.mem_get_info(device)[0] if torch.cuda.is_available() else 0
             estimate = cap * 16 > 0.35 * free
         self.sampler = KeySampler(n_positions * per_pos, device) if (estimate and not capacity) else None
-        # fused_clear: K3 clears each table region in L2 a few regions ahead of its insert sweep
-        # (pg_insert_records_fused) - no separate clear pass, no HBM fills of the table lines
-        import os
-        self.fused = (os.environ.get("PG_FUSED_CLEAR", "1") != "0") if fused_clear is None else bool(fused_clear)
-        self.cleared = torch.zeros(n_parts, dtype=torch.int32, device=device)
-        self.launches_per_build = 3 if self.fused else 4     # k2a_partition, [clear,] count_short, k3_insert_records
+        self.launches_per_build = 4          # k2a_partition, clear, count_short, k3_insert_records
         self.side = torch.cuda.Stream(device=device)
         self.last_estimate = None
-
-    def _insert(self, t, b):
-        L = self.L
-        if self.fused:
-            check(L.pg_insert_records_fused(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1,
-                                            b.part_cap, _ptr(self.cleared), _stream()), "pg_insert_records_fused")
-        else:
-            check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, b.part_cap,
-                                      _stream()), "pg_insert_records")
 
     def begin(self):
         """Without the estimator the (full) table clear can start early on the side stream, e.g. before
         the H2D copy of the next input; with it the capacity is only known after K2a."""
-        if self.sampler is not None or self.fused:
+        if self.sampler is not None:
             return
         st = torch.cuda.current_stream()
         self.side.wait_stream(st)            # whoever still reads the previous table finishes first
@@ -446,12 +431,12 @@ class TwoPhaseBuilder:
         around the kernels."""
         t, b, L = self.table, self.buckets, self.L
         st = torch.cuda.current_stream()
-        if self.sampler is None and not self.fused and not getattr(self, "_begun", False):
+        if self.sampler is None and not getattr(self, "_begun", False):
             self.begin()
         self._begun = False
         if n_rec == 0:
             st.wait_stream(self.side)
-            if self.sampler is not None or self.fused:
+            if self.sampler is not None:
                 t.clear()
             return t
         g_begin, g_end = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
@@ -464,17 +449,15 @@ class TwoPhaseBuilder:
             e[1].record(st)
         if self.sampler is not None:
             self.last_estimate = self.sampler.estimate()            # 8-byte D2H, synchronises
-            t.set_capacity(max(capacity_for(self.last_estimate, self.cap_max), b.n_parts))
-        if self.fused:
-            check(L.pg_table_reset(ctypes.byref(t.c), _stream()), "pg_table_reset")
-        elif self.sampler is not None:
+            t.set_capacity(capacity_for(self.last_estimate, self.cap_max))
             t.clear()
         else:
             st.wait_stream(self.side)        # K3 needs the cleared table
         check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
         if ev is not None:
             e[2].record(st)
-        self._insert(t, b)
+        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, b.part_cap, _stream()),
+              "pg_insert_records")
         if ev is not None:
             e[3].record(st)
             ev.setdefault("partition", []).append((e[0], e[1]))
@@ -491,7 +474,7 @@ class TwoPhaseBuilder:
             raise PgError("build_async sizes the table before K2a: construct the builder with estimate=False")
         t, b, L = self.table, self.buckets, self.L
         st = torch.cuda.current_stream()
-        if not self.fused and not getattr(self, "_begun", False):
+        if not getattr(self, "_begun", False):
             self.begin()
         self._begun = False
         if ev is not None:
@@ -501,15 +484,13 @@ class TwoPhaseBuilder:
         check(L.pg_kmer_partition_dev(ctypes.byref(desc), _ptr(packed.pk2), _ptr(packed.amb), _ptr(packed.d_seq_off),
                                       _ptr(packed.d_counts), packed.cap_records, packed.nbytes, self.owner_bits, self.sub_bits,
                                       _ptr(b.records), b.part_cap, _ptr(b.counts), _stream()), "pg_kmer_partition_dev")
-        if self.fused:
-            check(L.pg_table_reset(ctypes.byref(t.c), _stream()), "pg_table_reset")
-        else:
-            st.wait_stream(self.side)        # K3 needs the cleared table
+        st.wait_stream(self.side)            # K3 needs the cleared table
         check(L.pg_count_short_dev(ctypes.byref(t.c), _ptr(packed.d_seq_off), _ptr(packed.d_counts), packed.cap_records, _stream()),
               "pg_count_short_dev")
         if ev is not None:
             e[1].record(st)
-        self._insert(t, b)
+        check(L.pg_insert_records(ctypes.byref(t.c), _ptr(b.records), _ptr(b.seg_off), _ptr(b.counts), b.n_parts, 1, b.part_cap, _stream()),
+              "pg_insert_records")
         if ev is not None:
             e[2].record(st)
             ev.setdefault("partition", []).append((e[0], e[1]))

@@ -125,21 +125,3 @@ def test_async_build_device_args(eng):
     with _pt.raises(_lib.PgError):
         b.verify()
     assert p.n_rec == 40                                             # fetching re-packs with a larger index
-
-
-def test_fused_clear_matches_separate_clear(eng):
-    """pg_insert_records_fused (clear-ahead inside K3) on a table full of stale data == clear + K3."""
-    from pangenome_b200 import _lib
-    import torch
-    for data, k in ((pangenome(6, 400_000), 27), (pangenome(3, 50_000, seed=4), 15), (b">a\nACGTTGCAAGGCTTAACCGGATAGGCTTA\n", 11)):
-        packed = eng.PackedSeqs(eng.to_device_bytes(data))
-        ref_t, _ = eng.build_dbg(packed, k)
-        for sub_bytes in (8 << 20, 1 << 16, 1 << 12):
-            b = eng.TwoPhaseBuilder(k, _lib.PG_MODE_CANONICAL, max(packed.n_positions(k), 64), sub_bytes=sub_bytes, estimate=False,
-                                    fused_clear=True)
-            b.table.slots.random_(-2 ** 62, 2 ** 62)            # stale garbage: the fused clear must wipe all of it
-            for _ in range(2):
-                t = b.build(packed, packed.n_rec)
-            b.verify()
-            assert t.checksum() == ref_t.checksum(), (k, sub_bytes)
-            assert t.n_keys() == ref_t.n_keys()
