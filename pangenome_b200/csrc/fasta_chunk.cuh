@@ -232,3 +232,35 @@ PG_HD uint32_t pext16_1bit(uint32_t bits, uint32_t mask) {
     }
     return out;
 }
+
+// ---- single-pass K1 helpers ---------------------------------------------------------------------
+// The line state of a chunk follows from the LAST newline before it: the line starts right after it,
+// and the line is a header iff its first byte is '>'.  gt_masks[c] = '>' mask of chunk c of the tile.
+PG_HD uint32_t chunk_entry_state(int prev_nl, int chunk_off, const uint16_t *gt_masks, uint32_t fallback) {
+    if (prev_nl < 0) return fallback;                    // no newline in the tile before this chunk
+    const int ls = prev_nl + 1;
+    if (ls == chunk_off) return ST_LINE_START;
+    return ((gt_masks[ls >> 4] >> (ls & 15)) & 1u) ? ST_HEADER : ST_SEQ;
+}
+PG_HD int chunk_last_nl(uint32_t nl, int chunk_off) { return nl ? chunk_off + pg_msb(nl & 0xFFFFu) : -1; }
+PG_HD int chunk_first_nl(uint32_t nl, int chunk_off) { return nl ? chunk_off + pg_ctz(nl & 0xFFFFu) : 0x7FFFFFFF; }
+
+// What a whole tile does for each entry state, from quantities that do not depend on the entry state:
+// bases / headers after the tile's first newline, the position of the first and last newline, and
+// whether the tile's first byte is '>'.
+struct TileLocal { uint32_t post_seq, post_hdr; int first_nl, last_nl; uint32_t first_gt, gt_after_last; int tile_len; };
+PG_HD Sum3 tile_sum3(const TileLocal &t) {
+    const bool has_nl = t.last_nl >= 0;
+    const uint32_t pre = has_nl ? (uint32_t)t.first_nl : (uint32_t)t.tile_len;      // bytes before the first newline (none of them is one)
+    const uint32_t exit_local = !has_nl ? 0u : (t.last_nl == t.tile_len - 1 ? (uint32_t)ST_LINE_START : (t.gt_after_last ? (uint32_t)ST_HEADER : (uint32_t)ST_SEQ));
+    Sum3 s;
+#pragma unroll
+    for (uint32_t e = 0; e < 3; e++) {
+        const bool pre_hdr = (e == ST_HEADER) || (e == ST_LINE_START && t.first_gt && pre > 0);
+        const uint32_t seq = t.post_seq + (pre_hdr ? 0u : pre);
+        const uint32_t hdr = t.post_hdr + ((e == ST_LINE_START && t.first_gt && pre > 0) ? 1u : 0u);
+        const uint32_t ex = has_nl ? exit_local : (pre == 0 ? e : (pre_hdr ? (uint32_t)ST_HEADER : (uint32_t)ST_SEQ));
+        s.v[e] = SV_MAKE(ex, hdr, seq);
+    }
+    return s;
+}

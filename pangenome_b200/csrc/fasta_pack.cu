@@ -12,6 +12,7 @@
 //                         writes 0.375 B/base]
 // HBM-bound streaming work: 128-bit coalesced loads, SWAR byte classification (no per-byte loops),
 // shuffle scans, shared-memory staging so global stores are full words.
+#include <stdlib.h>
 #include "fasta_chunk.cuh"
 
 namespace {
@@ -274,6 +275,268 @@ k1_tile_pack(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles,
     }
 }
 
+// =================================================================================================
+// Single-pass K1: one launch reads the file ONCE.
+// Tiles are handed out by an atomic ticket (so every earlier tile is already running or done), and
+// the prefix a tile needs - entry line state, base rank, record rank - comes from a decoupled
+// look-back over the tiles before it: each tile first publishes what it does for each of the three
+// entry states (tile_sum3: built from quantities that do not depend on the entry state), later its
+// inclusive prefix.  Inside a tile the line state of every 16-byte chunk follows from a max-scan of
+// "position of the last newline" (one word per chunk) and the base ranks from a plain sum scan - no
+// 3-variant composition in the per-chunk scans any more.
+struct K1Pref { unsigned long long seq, hdr, nl; uint32_t state, pad; };
+struct K1Entry { unsigned long long seq, hdr, nl; uint32_t state; };
+
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// executed by warp 0: the inclusive prefix of tiles [0, tile), or ok = false if a predecessor never showed up
+__device__ __forceinline__ K1Entry k1_look_back(int64_t tile, const uint4 *agg, const uint32_t *tile_nl, const K1Pref *pref,
+                                                const uint32_t *pflag, bool &ok) {
+    const int lane = threadIdx.x & 31;
+    // composite of the tiles between the window and `tile`: state map + counts per entry state
+    uint32_t gst[3] = {0, 1, 2}; unsigned long long gseq[3] = {0, 0, 0}, ghdr[3] = {0, 0, 0}, gnl = 0;
+    K1Entry e; e.seq = e.hdr = e.nl = 0; e.state = ST_LINE_START;
+    ok = true;
+    int64_t j = tile - 1;
+    while (j >= 0) {
+        const int64_t idx = j - lane;
+        uint32_t pf = 0; uint4 a = make_uint4(0, 0, 0, 0); uint32_t nl = 0;
+        int spins = 0;
+        unsigned need;
+        for (;;) {
+            if (idx >= 0) {
+                pf = ld_acquire_u32(pflag + idx);
+                if (pf != 2) a = ld_volatile_u4(agg + idx);
+            }
+            const unsigned has_pref = __ballot_sync(0xffffffffu, idx >= 0 && pf == 2);
+            const unsigned has_agg = __ballot_sync(0xffffffffu, idx < 0 || pf == 2 || a.w == 1);
+            const int first_pref = has_pref ? __ffs(has_pref) - 1 : 32;
+            need = first_pref >= 32 ? 0xffffffffu : ((1u << first_pref) - 1u);       // lanes nearer than the first prefix must show an aggregate
+            if ((has_agg & need) == need) break;
+            if (++spins > (1 << 20)) { ok = false; return e; }
+            __nanosleep(20);
+        }
+        if (idx >= 0 && pf != 2) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(nl) : "l"(tile_nl + idx));   // never through a stale L1 line
+        const unsigned has_pref = __ballot_sync(0xffffffffu, idx >= 0 && pf == 2);
+        const int first_pref = has_pref ? __ffs(has_pref) - 1 : 32;
+        const int n_agg = first_pref < 32 ? first_pref : (int)((j + 1 < 32) ? j + 1 : 32);
+        for (int l = 0; l < n_agg; l++) {          // nearest tile first: new composite = (tile j-l) then (old composite)
+            const uint32_t v0 = __shfl_sync(0xffffffffu, a.x, l), v1 = __shfl_sync(0xffffffffu, a.y, l), v2 = __shfl_sync(0xffffffffu, a.z, l);
+            const uint32_t tnl = __shfl_sync(0xffffffffu, nl, l);
+            uint32_t nst[3]; unsigned long long nseq[3], nhdr[3];
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const uint32_t x = s == 0 ? v0 : (s == 1 ? v1 : v2);
+                const uint32_t mid = SV_STATE(x);
+                nst[s] = mid == 0 ? gst[0] : (mid == 1 ? gst[1] : gst[2]);
+                nseq[s] = SV_SEQ(x) + (mid == 0 ? gseq[0] : (mid == 1 ? gseq[1] : gseq[2]));
+                nhdr[s] = SV_HDR(x) + (mid == 0 ? ghdr[0] : (mid == 1 ? ghdr[1] : ghdr[2]));
+            }
+#pragma unroll
+            for (int s = 0; s < 3; s++) { gst[s] = nst[s]; gseq[s] = nseq[s]; ghdr[s] = nhdr[s]; }
+            gnl += tnl;
+        }
+        if (first_pref < 32) {
+            K1Pref p;
+            const K1Pref *pp = pref + (j - first_pref);
+            asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(p.seq), "=l"(p.hdr) : "l"(pp));
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(p.nl) : "l"(&pp->nl));
+            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(p.state) : "l"(&pp->state));
+            e.state = p.state == 0 ? gst[0] : (p.state == 1 ? gst[1] : gst[2]);
+            e.seq = p.seq + (p.state == 0 ? gseq[0] : (p.state == 1 ? gseq[1] : gseq[2]));
+            e.hdr = p.hdr + (p.state == 0 ? ghdr[0] : (p.state == 1 ? ghdr[1] : ghdr[2]));
+            e.nl = p.nl + gnl;
+            return e;
+        }
+        j -= 32;
+    }
+    e.state = gst[ST_LINE_START]; e.seq = gseq[ST_LINE_START]; e.hdr = ghdr[ST_LINE_START]; e.nl = gnl;   // start of file
+    return e;
+}
+
+__global__ void __launch_bounds__(K1_THREADS)
+k1_fused_pack(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles, unsigned int *ticket, uint4 *agg, uint32_t *tile_nl,
+              K1Pref *pref, uint32_t *pflag, uint32_t *__restrict__ pk2, uint32_t *__restrict__ amb,
+              int64_t *__restrict__ hdr_off, int64_t *__restrict__ seq_off, int64_t cap_records, int64_t *__restrict__ counts) {
+    constexpr int NW = K1_THREADS / 32, NAGG = K1_NSUB * NW;
+    __shared__ uint16_t s_gt[K1_TILE / 16];
+    __shared__ int s_imax[NAGG + 1];
+    __shared__ uint32_t s_add[NAGG + 1];
+    __shared__ uint32_t s_pk[K1_PKW], s_am[K1_AMW];
+    __shared__ int s_first_nl; __shared__ uint32_t s_post_seq, s_post_hdr, s_real_nl;
+    __shared__ long long s_tile; __shared__ K1Entry s_entry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) { s_tile = (long long)atomicAdd(ticket, 1u); s_first_nl = 0x7FFFFFFF; s_post_seq = s_post_hdr = s_real_nl = 0; }
+        for (int i = threadIdx.x; i < K1_PKW; i += K1_THREADS) s_pk[i] = 0;
+        for (int i = threadIdx.x; i < K1_AMW; i += K1_THREADS) s_am[i] = 0;
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= ntiles) break;
+        const int64_t tile_off = tile * K1_TILE;
+        // ---- S1: load + classify (four 128-bit loads in flight per thread)
+        ChunkCls c[K1_NSUB];
+        load_classify4<false>(fasta, nbytes, tile_off, c);
+        int off[K1_NSUB], prev[K1_NSUB];
+        // ---- S2: max-scan of the last newline position, tile-wide first newline, real newline count
+        int my_first = 0x7FFFFFFF; uint32_t my_nl = 0;
+        int inc[K1_NSUB];
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++) {
+            off[i] = (i * K1_THREADS + threadIdx.x) * 16;
+            s_gt[off[i] >> 4] = (uint16_t)c[i].gt;
+            inc[i] = chunk_last_nl(c[i].nl, off[i]);
+            int f = chunk_first_nl(c[i].nl, off[i]); my_first = f < my_first ? f : my_first;
+            my_nl += c[i].real_nl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc[i], o); if (lane >= o && y > inc[i]) inc[i] = y; }
+            if (lane == 31) s_imax[i * NW + warp] = inc[i];
+        }
+        my_first = __reduce_min_sync(0xffffffffu, my_first);
+        my_nl = __reduce_add_sync(0xffffffffu, my_nl);
+        if (lane == 0) { atomicMin(&s_first_nl, my_first); if (my_nl) atomicAdd(&s_real_nl, my_nl); }
+        __syncthreads();
+        if (warp == 0) {       // exclusive max-scan of the 32 (sub-tile, warp) aggregates; total in slot NAGG
+            int v = s_imax[lane], x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o && y > x) x = y; }
+            int ex = __shfl_up_sync(0xffffffffu, x, 1);
+            __syncwarp();
+            s_imax[lane] = lane == 0 ? -1 : ex;
+            if (lane == 31) s_imax[NAGG] = x;
+        }
+        __syncthreads();
+        const int last_nl = s_imax[NAGG], first_nl = s_first_nl;
+        // ---- S3/S4: chunk states where they do not depend on the tile's entry state; entry-independent sums
+        ChunkRun run[K1_NSUB];
+        uint32_t psum_seq = 0, psum_hdr = 0;
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++) {
+            int ex = __shfl_up_sync(0xffffffffu, inc[i], 1);
+            int wp = s_imax[i * NW + warp];
+            prev[i] = lane == 0 ? wp : (ex > wp ? ex : wp);
+            run[i] = chunk_run(c[i], chunk_entry_state(prev[i], off[i], s_gt, ST_HEADER));
+            psum_seq += pg_popc(run[i].seqmask); psum_hdr += pg_popc(run[i].hs);
+        }
+        psum_seq = __reduce_add_sync(0xffffffffu, psum_seq); psum_hdr = __reduce_add_sync(0xffffffffu, psum_hdr);
+        if (lane == 0) { if (psum_seq) atomicAdd(&s_post_seq, psum_seq); if (psum_hdr) atomicAdd(&s_post_hdr, psum_hdr); }
+        __syncthreads();
+        // ---- S5: publish the tile summary, look back, publish the inclusive prefix (warp 0)
+        if (warp == 0) {
+            TileLocal tl; tl.post_seq = s_post_seq; tl.post_hdr = s_post_hdr; tl.first_nl = first_nl; tl.last_nl = last_nl; tl.tile_len = K1_TILE;
+            tl.first_gt = s_gt[0] & 1u;
+            tl.gt_after_last = (last_nl >= 0 && last_nl + 1 < K1_TILE) ? ((s_gt[(last_nl + 1) >> 4] >> ((last_nl + 1) & 15)) & 1u) : 0u;
+            const Sum3 sm = tile_sum3(tl);
+            if (lane == 0) {
+                tile_nl[tile] = s_real_nl;
+                __threadfence();
+                asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(agg + tile), "r"(sm.v[0]), "r"(sm.v[1]), "r"(sm.v[2]), "r"(1u) : "memory");
+            }
+            bool ok;
+            K1Entry e = k1_look_back(tile, agg, tile_nl, pref, pflag, ok);
+            if (lane == 0) {
+                const uint32_t y = sum3_sel(sm, e.state);
+                K1Pref p; p.seq = e.seq + SV_SEQ(y); p.hdr = e.hdr + SV_HDR(y); p.nl = e.nl + s_real_nl; p.state = SV_STATE(y); p.pad = 0;
+                pref[tile] = p;
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(pflag + tile), "r"(2u) : "memory");
+                s_entry = e;
+                if (tile == ntiles - 1) {       // whole-file totals
+                    const bool dead = (p.nl == 0) || !ok;     // a file without any real newline yields no line (readline_jit_ :129-132)
+                    counts[0] = dead ? 0 : (int64_t)p.hdr; counts[1] = dead ? 0 : (int64_t)p.seq; counts[2] = (int64_t)p.nl;
+                    counts[3] = !ok ? 2 : (dead ? 1 : 0);
+                    if (dead) seq_off[0] = 0;
+                    else if ((int64_t)p.hdr <= cap_records) seq_off[p.hdr] = (int64_t)p.seq;
+                }
+            }
+        }
+        __syncthreads();
+        const K1Entry e = s_entry;
+        // ---- S6: final chunk states, ranks by a plain sum scan (bases | headers << 16)
+        const uint32_t fallback = e.state == ST_LINE_START ? ((s_gt[0] & 1u) ? (uint32_t)ST_HEADER : (uint32_t)ST_SEQ) : e.state;
+        uint32_t cnt[K1_NSUB], ainc[K1_NSUB];
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++) {
+            if (prev[i] < 0) {
+                const uint32_t st = (off[i] == 0 && e.state == ST_LINE_START) ? (uint32_t)ST_LINE_START : fallback;
+                run[i] = chunk_run(c[i], st);
+            }
+            cnt[i] = pg_popc(run[i].seqmask) | (pg_popc(run[i].hs) << 16);
+            ainc[i] = cnt[i];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, ainc[i], o); if (lane >= o) ainc[i] += y; }
+            if (lane == 31) s_add[i * NW + warp] = ainc[i];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = s_add[lane], x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            s_add[lane] = x - v;
+            if (lane == 31) s_add[NAGG] = x;
+        }
+        __syncthreads();
+        // ---- S7: pack into shared memory, record index, coalesced write-out
+        const uint32_t a0 = (uint32_t)(e.seq & 31);
+#pragma unroll
+        for (int i = 0; i < K1_NSUB; i++) {
+            const uint32_t excl = s_add[i * NW + warp] + ainc[i] - cnt[i];
+            const uint32_t rank = excl & 0xFFFFu, hrank = excl >> 16;
+            const uint32_t n = cnt[i] & 0xFFFFu;
+            if (n) {
+                uint32_t d = pext16_2bit(c[i].dig, run[i].seqmask);
+                uint32_t m = pext16_1bit(c[i].amb, run[i].seqmask);
+                if (n < 16) d &= (1u << (2 * n)) - 1u;
+                const uint32_t q = a0 + rank, sh = 2 * (q & 15);
+                atomicOr(&s_pk[q >> 4], d << sh);
+                if (sh && (d >> (32 - sh))) atomicOr(&s_pk[(q >> 4) + 1], d >> (32 - sh));
+                if (m) {
+                    const uint32_t sh1 = q & 31;
+                    atomicOr(&s_am[q >> 5], m << sh1);
+                    if (sh1 > 16 && (m >> (32 - sh1))) atomicOr(&s_am[(q >> 5) + 1], m >> (32 - sh1));
+                }
+            }
+            if (run[i].hs) {
+                uint32_t hs = run[i].hs; unsigned long long idx = e.hdr + hrank;
+                while (hs) {
+                    const int j = pg_ctz(hs); hs &= hs - 1;
+                    if ((int64_t)idx < cap_records) {
+                        hdr_off[idx] = tile_off + off[i] + j;
+                        seq_off[idx] = (int64_t)(e.seq + rank + pg_popc(run[i].seqmask & ((1u << j) - 1u)));
+                    }
+                    idx++;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t tot = s_add[NAGG] & 0xFFFFu;            // bases of this tile (<= 16384 fits 16 bits? 16384 = 0x4000: yes)
+        const uint32_t end = a0 + tot;
+        uint32_t *gpk = pk2 + ((e.seq >> 5) << 1);
+        uint32_t *gam = amb + (e.seq >> 5);
+        const uint32_t npk = (end + 15) >> 4, nam = (end + 31) >> 5;
+        for (uint32_t w = threadIdx.x; w < npk; w += K1_THREADS) {
+            const uint32_t v = s_pk[w];
+            if (16 * w >= a0 && 16 * (w + 1) <= end) gpk[w] = v;
+            else if (v) atomicOr(&gpk[w], v);                      // word shared with a neighbouring tile (buffers are pre-zeroed)
+        }
+        for (uint32_t w = threadIdx.x; w < nam; w += K1_THREADS) {
+            const uint32_t v = s_am[w];
+            if (32 * w >= a0 && 32 * (w + 1) <= end) gam[w] = v;
+            else if (v) atomicOr(&gam[w], v);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t pg_pack_words(int64_t cap_bases) { return (cap_bases < 0 ? 0 : cap_bases) / 16 + 32; }
@@ -281,7 +544,9 @@ extern "C" int64_t pg_pack_words(int64_t cap_bases) { return (cap_bases < 0 ? 0 
 extern "C" int64_t pg_fasta_workspace_bytes(int64_t nbytes) {
     int64_t ntiles = (nbytes + K1_TILE - 1) / K1_TILE;
     if (ntiles < 1) ntiles = 1;
-    return ntiles * (int64_t)(sizeof(TileSum) + sizeof(TileEntry)) + 256;
+    int64_t legacy = ntiles * (int64_t)(sizeof(TileSum) + sizeof(TileEntry)) + 256;
+    int64_t fused = 256 + ntiles * (int64_t)(sizeof(uint4) + sizeof(K1Pref) + 2 * sizeof(uint32_t)) + 64;
+    return legacy > fused ? legacy : fused;
 }
 
 extern "C" int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes, uint32_t *d_pk2, uint32_t *d_amb,
@@ -299,6 +564,32 @@ extern "C" int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes, uint32
     if ((reinterpret_cast<uintptr_t>(d_fasta) & 15) != 0)
         return pg_fail(PG_ERR_INVALID, "pg_fasta_scan_pack: d_fasta must be 16-byte aligned");
     int64_t ntiles = (nbytes + K1_TILE - 1) / K1_TILE;
+    static int legacy = -1;
+    if (legacy < 0) { const char *e = getenv("PG_K1_LEGACY"); legacy = e ? atoi(e) : 0; }
+    if (!legacy) {
+        // single pass: zero the output planes (tiles OR into the words they share) and the look-back state
+        PG_CUDA(cudaMemsetAsync(d_pk2, 0, (size_t)pg_pack_words(cap_bases) * 4, stream));
+        PG_CUDA(cudaMemsetAsync(d_amb, 0, (size_t)pg_pack_words(cap_bases) * 4, stream));
+        if (ntiles == 0) {
+            PG_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int64_t), stream));
+            PG_CUDA(cudaMemsetAsync(d_seq_off, 0, sizeof(int64_t), stream));
+            return PG_OK;
+        }
+        char *w = reinterpret_cast<char *>(d_ws);
+        size_t used = 256 + (size_t)ntiles * (sizeof(uint4) + sizeof(K1Pref) + 2 * sizeof(uint32_t));
+        PG_CUDA(cudaMemsetAsync(d_ws, 0, used, stream));
+        unsigned int *ticket = reinterpret_cast<unsigned int *>(w);
+        uint4 *agg = reinterpret_cast<uint4 *>(w + 256);
+        K1Pref *pref = reinterpret_cast<K1Pref *>(w + 256 + (size_t)ntiles * sizeof(uint4));
+        uint32_t *tile_nl = reinterpret_cast<uint32_t *>(w + 256 + (size_t)ntiles * (sizeof(uint4) + sizeof(K1Pref)));
+        uint32_t *pflag = tile_nl + ntiles;
+        int64_t maxg = (int64_t)pg_num_sms() * 5;
+        int grid1 = (int)(ntiles < maxg ? ntiles : maxg);
+        k1_fused_pack<<<grid1, K1_THREADS, 0, stream>>>(d_fasta, nbytes, ntiles, ticket, agg, tile_nl, pref, pflag, d_pk2, d_amb,
+                                                        d_hdr_off, d_seq_off, cap_records, d_counts);
+        PG_CUDA(cudaGetLastError());
+        return PG_OK;
+    }
     TileSum *sums = reinterpret_cast<TileSum *>(d_ws);
     TileEntry *entries = reinterpret_cast<TileEntry *>(reinterpret_cast<char *>(d_ws) + ((ntiles < 1 ? 1 : ntiles) * sizeof(TileSum) + 15) / 16 * 16);
     int sms = pg_num_sms();

@@ -145,3 +145,70 @@ extern "C" int64_t emul_dbg(const uint32_t *pk2_32, const uint32_t *amb, int64_t
     *n_rdbg = nr;
     return n;
 }
+
+
+// mirrors k1_fused_pack: per tile, states from a max-scan of the last newline, tile summary from
+// entry-independent quantities (tile_sum3), then ranks from a plain prefix sum
+extern "C" int64_t emul_pack2(const uint8_t *fasta, int64_t nbytes, uint32_t *pk2, uint32_t *amb, int64_t n_words,
+                              int64_t *hdr_off, int64_t *seq_off, int64_t cap_rec, int64_t *counts) {
+    memset(pk2, 0, (size_t)n_words * 4); memset(amb, 0, (size_t)n_words * 4);
+    const int NCH = TILE / 16;
+    int64_t ntiles = (nbytes + TILE - 1) / TILE;
+    uint64_t seq = 0, hdr = 0, real_nl = 0; uint32_t state = ST_LINE_START;
+    for (int64_t t = 0; t < ntiles; t++) {
+        std::vector<ChunkCls> cls(NCH); std::vector<uint16_t> gt(NCH); std::vector<int> prev(NCH);
+        int run = -1, first_nl = 0x7FFFFFFF, last_nl = -1;
+        for (int c = 0; c < NCH; c++) {
+            cls[c] = load_cls(fasta, nbytes, t * TILE + c * 16);
+            gt[c] = (uint16_t)cls[c].gt; real_nl += cls[c].real_nl;
+            prev[c] = run;
+            int l = chunk_last_nl(cls[c].nl, c * 16); if (l > run) run = l;
+            int f = chunk_first_nl(cls[c].nl, c * 16); if (f < first_nl) first_nl = f;
+        }
+        last_nl = run;
+        TileLocal tl; tl.post_seq = tl.post_hdr = 0; tl.first_nl = first_nl; tl.last_nl = last_nl; tl.tile_len = TILE;
+        tl.first_gt = gt[0] & 1u;
+        tl.gt_after_last = (last_nl >= 0 && last_nl + 1 < TILE) ? ((gt[(last_nl + 1) >> 4] >> ((last_nl + 1) & 15)) & 1u) : 0u;
+        for (int c = 0; c < NCH; c++) {
+            ChunkRun r = chunk_run(cls[c], chunk_entry_state(prev[c], c * 16, gt.data(), ST_HEADER));
+            tl.post_seq += pg_popc(r.seqmask); tl.post_hdr += pg_popc(r.hs);
+        }
+        Sum3 agg = tile_sum3(tl);
+        // ---- entry known (sequential emulation of the look-back): final states, ranks, pack
+        const uint32_t fallback = state == ST_LINE_START ? (tl.first_gt ? (uint32_t)ST_HEADER : (uint32_t)ST_SEQ) : state;
+        uint32_t rank = 0, hrank = 0;
+        for (int c = 0; c < NCH; c++) {
+            int64_t off = t * TILE + c * 16;
+            uint32_t st = (prev[c] < 0 && c == 0 && state == ST_LINE_START) ? (uint32_t)ST_LINE_START
+                                                                             : chunk_entry_state(prev[c], c * 16, gt.data(), fallback);
+            ChunkRun r = chunk_run(cls[c], st);
+            uint32_t cnt = pg_popc(r.seqmask);
+            if (cnt) {
+                uint32_t d = pext16_2bit(cls[c].dig, r.seqmask), m = pext16_1bit(cls[c].amb, r.seqmask);
+                if (cnt < 16) d &= (1u << (2 * cnt)) - 1u;
+                uint64_t g = seq + rank;
+                uint32_t sh = 2 * (g & 15);
+                pk2[g >> 4] |= d << sh;
+                if (sh && (d >> (32 - sh))) pk2[(g >> 4) + 1] |= d >> (32 - sh);
+                uint32_t sh1 = g & 31;
+                amb[g >> 5] |= m << sh1;
+                if (sh1 > 16 && (m >> (32 - sh1))) amb[(g >> 5) + 1] |= m >> (32 - sh1);
+            }
+            uint32_t hs = r.hs; uint64_t idx = hdr + hrank;
+            while (hs) {
+                int j = pg_ctz(hs); hs &= hs - 1;
+                if ((int64_t)idx < cap_rec) { hdr_off[idx] = off + j; seq_off[idx] = (int64_t)(seq + rank + pg_popc(r.seqmask & ((1u << j) - 1u))); }
+                idx++;
+            }
+            rank += cnt; hrank += pg_popc(r.hs);
+        }
+        uint32_t y = sum3_sel(agg, state);
+        if (SV_SEQ(y) != rank || SV_HDR(y) != hrank) return -1000 - t;       // the summary must agree with the final pass
+        seq += rank; hdr += hrank; state = SV_STATE(y);
+    }
+    bool dead = real_nl == 0;
+    counts[0] = dead ? 0 : (int64_t)hdr; counts[1] = dead ? 0 : (int64_t)seq; counts[2] = (int64_t)real_nl;
+    if (!dead && (int64_t)hdr <= cap_rec) seq_off[hdr] = (int64_t)seq;
+    if (dead) seq_off[0] = 0;
+    return counts[1];
+}

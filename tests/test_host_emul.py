@@ -25,6 +25,7 @@ def emul():
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-o", _SO, src])
     L = ctypes.CDLL(_SO)
     L.emul_pack.restype = ctypes.c_int64
+    L.emul_pack2.restype = ctypes.c_int64
     L.emul_dbg.restype = ctypes.c_int64
     return L
 
@@ -33,7 +34,7 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_pack(L, data):
+def run_pack(L, data, fn="emul_pack"):
     n = len(data)
     buf = np.frombuffer(data, dtype=np.uint8) if n else np.zeros(1, np.uint8)
     nw = n // 16 + 64
@@ -43,8 +44,9 @@ def run_pack(L, data):
     hdr = np.zeros(cap + 1, np.int64)
     so = np.zeros(cap + 2, np.int64)
     counts = np.zeros(4, np.int64)
-    L.emul_pack(_p(buf), ctypes.c_int64(n), _p(pk2), _p(amb), ctypes.c_int64(nw), _p(hdr), _p(so),
-                ctypes.c_int64(cap), _p(counts))
+    rc = getattr(L, fn)(_p(buf), ctypes.c_int64(n), _p(pk2), _p(amb), ctypes.c_int64(nw), _p(hdr), _p(so),
+                        ctypes.c_int64(cap), _p(counts))
+    assert rc >= 0, "tile summary disagrees with the final pass in tile %d" % (-rc - 1000)
     nrec = int(counts[0])
     return pk2, amb, hdr[:nrec], so[:nrec + 1], counts
 
@@ -124,3 +126,30 @@ def test_emul_big(emul, big_facts):
     assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
     assert np.array_equal(rk, ref["rdbg"])
     assert oracle.table_checksum(ks, vs, cs) == oracle.table_checksum(*ref["dbg"])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_emul_single_pass_pack_matches_golden(emul, case):
+    """the single-pass K1 formulation (states from the last newline, tile_sum3) == the oracle's parse"""
+    data = case["input_latin1"].encode("latin-1")
+    ref = oracle.run(data, case["k"], c=case["c"], stages=1)
+    pk2, amb, hdr, so, counts = run_pack(emul, data, "emul_pack2")
+    assert so.tolist() == ref["seq_off"].tolist()
+    assert hdr.tolist() == ref["hdr_off"].tolist()
+    assert unpack_syms(pk2, amb, int(counts[1])).tolist() == syms_of_bytes(ref["seq"]).tolist()
+
+
+def test_emul_single_pass_pack_hostile_layouts(emul):
+    rng = np.random.default_rng(5)
+    alph = np.frombuffer(b"ACGTNacgtRY>\n\n\r", dtype=np.uint8)
+    for it in range(300):
+        n = int(rng.integers(0, 70000 if it % 10 == 0 else 3000))
+        body = bytes(rng.choice(alph, size=n, p=[.2, .2, .2, .2, .02, .01, .01, .01, .01, .01, .01, .03, .04, .03, .02]).tolist())
+        data = (b">h\n" if it % 3 else b"") + body
+        ref = oracle.run(data, 5, stages=1)
+        a = run_pack(emul, data, "emul_pack")
+        b = run_pack(emul, data, "emul_pack2")
+        assert (a[3] - a[3][0]).tolist() == ref["seq_off"].tolist(), data[:80]      # bases before the first header stay in the stream
+        assert a[3].tolist() == b[3].tolist() and a[2].tolist() == b[2].tolist() and a[4][:3].tolist() == b[4][:3].tolist()
+        nb = int(a[4][1])
+        assert np.array_equal(unpack_syms(a[0], a[1], nb), unpack_syms(b[0], b[1], nb))
