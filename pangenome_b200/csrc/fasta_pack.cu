@@ -564,9 +564,14 @@ extern "C" int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes, uint32
     if ((reinterpret_cast<uintptr_t>(d_fasta) & 15) != 0)
         return pg_fail(PG_ERR_INVALID, "pg_fasta_scan_pack: d_fasta must be 16-byte aligned");
     int64_t ntiles = (nbytes + K1_TILE - 1) / K1_TILE;
-    static int legacy = -1;
-    if (legacy < 0) { const char *e = getenv("PG_K1_LEGACY"); legacy = e ? atoi(e) : 0; }
-    if (!legacy) {
+    // PG_K1_SINGLE_PASS=1 selects the one-launch kernel below.  It reads the file once (no second pass, 67 M
+    // instead of 112 M warp instructions) and is bit-exact, but measured 267 us against 189 us for the three
+    // launches on the 50 MB config-2 file: at 100 registers only two CTAs fit an SM and seven of a CTA's eight
+    // warps sit at the barrier while warp 0 looks back (ncu: barrier stall 8.5).  It becomes the default once the
+    // look-back runs on a helper warp under the digit classification (round-2 work).
+    static int single_pass = -1;
+    if (single_pass < 0) { const char *e = getenv("PG_K1_SINGLE_PASS"); single_pass = e ? atoi(e) : 0; }
+    if (single_pass) {
         // single pass: zero the output planes (tiles OR into the words they share) and the look-back state
         PG_CUDA(cudaMemsetAsync(d_pk2, 0, (size_t)pg_pack_words(cap_bases) * 4, stream));
         PG_CUDA(cudaMemsetAsync(d_amb, 0, (size_t)pg_pack_words(cap_bases) * 4, stream));

@@ -140,3 +140,30 @@ def test_config2_scaled_checksum(eng):
         ref = oracle.run(data, k, stages=1)
         t, _ = eng.build_dbg(packed, k)
         assert t.checksum() == oracle.table_checksum(*ref["dbg"]), k
+
+
+def test_single_pass_k1_matches(eng):
+    """PG_K1_SINGLE_PASS=1 (one launch, decoupled look-back) packs exactly like the default three launches.
+    The switch is read once per process, so the variant runs in a subprocess."""
+    import os, subprocess, sys, textwrap
+    from conftest import ROOT
+    code = textwrap.dedent("""
+        import sys, hashlib, numpy as np
+        sys.path.insert(0, %r)
+        from pangenome_b200 import engine
+        from pangenome_b200.synth import pangenome
+        out = []
+        for data in (pangenome(3, 300_000), b">a desc\\nACGTNNacgtRY\\nAC\\n\\n>b\\n>c\\nGGGTT", b"junk\\n>x\\n" + b"ACGT" * 9000, b""):
+            p = engine.PackedSeqs(engine.to_device_bytes(data))
+            nw = p.n_bases // 16 + 1
+            out.append((p.n_rec, p.n_bases, p.seq_off.tolist(), p.hdr_off.tolist(),
+                        hashlib.sha256(p.pk2[:nw].cpu().numpy().tobytes() + p.amb[:nw // 2 + 1].cpu().numpy().tobytes()).hexdigest()))
+        print(repr(out))
+    """ % ROOT)
+    res = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, PG_K1_SINGLE_PASS=flag)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[flag] = r.stdout.strip().splitlines()[-1]
+    assert res["0"] == res["1"]
