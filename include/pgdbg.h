@@ -55,14 +55,19 @@ extern "C" {
 typedef void *pg_stream_t;
 
 /* An open-addressing table: `capacity` (power of two) 16-byte slots
- * {uint64 key, uint32 masks, uint32 count}.  Replaces class oakht
- * (kmer_numba.py:340-679) and init_dict (:1097-1122). */
+ * {uint64 key, uint32 masks, uint32 count:22 | generation tag:10}.  A slot is live
+ * only while its tag equals `epoch`, which makes emptying the table O(1)
+ * (pg_table_reset).  Replaces class oakht (kmer_numba.py:340-679) and init_dict
+ * (:1097-1122).  Life cycle: allocate, set epoch = 1, pg_table_clear once;
+ * before every further build pg_table_reset. */
 typedef struct pg_table {
     uint64_t *d_slots;   /* device, 2 * capacity uint64 */
     int64_t capacity;    /* power of two */
     int64_t *d_stats;    /* device, PG_STAT_WORDS int64 */
     int32_t mode;        /* PG_MODE_* */
     int32_t k;           /* k-mer length, 1..27 */
+    int32_t epoch;       /* 1..1023: generation of the live slots (host side; pg_table_reset advances it) */
+    int32_t reserved;
 } pg_table;
 
 const char *pg_last_error(void);
@@ -99,7 +104,10 @@ int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes,
                        int64_t *d_counts, void *d_ws, int64_t ws_bytes, pg_stream_t stream);
 
 /* ---- K2+K3: k-mer extraction fused with table insertion ---------------------
- * pg_table_clear  : all slots empty, stats zero       (oakht.__init__ :341-352)
+ * pg_table_clear  : all slots empty (for every epoch), stats zero: 16 B/slot of HBM writes
+ *                   (oakht.__init__ :341-352)
+ * pg_table_reset  : the same effect between builds without touching the slots: ++t->epoch, stats
+ *                   zero (falls back to pg_table_clear when the 10-bit tag wraps)
  * pg_kmer_insert  : for every k-mer occurrence of records [0, n_rec) whose
  *                   start lies in stream range [g_begin, g_end): key/val as
  *                   build_dbg + add_kmer (:1036-1093), both strands unless
@@ -110,6 +118,7 @@ int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes,
  */
 int64_t pg_table_bytes(int64_t capacity);
 int pg_table_clear(const pg_table *t, pg_stream_t stream);
+int pg_table_reset(pg_table *t, pg_stream_t stream);
 /* adds (strands x records of [0,n_rec) shorter than k whose offset lies in [g_begin, g_end]) to PG_STAT_SHORT;
  * pg_kmer_insert calls it itself, the two-phase path (pg_kmer_partition) does not */
 int pg_count_short(const pg_table *t, const int64_t *d_seq_off, int64_t n_rec, int64_t g_begin, int64_t g_end,

@@ -14,7 +14,7 @@ c_i64, c_int, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
 
 class PgTable(ctypes.Structure):
     _fields_ = [("d_slots", c_vp), ("capacity", c_i64), ("d_stats", c_vp), ("mode", ctypes.c_int32),
-                ("k", ctypes.c_int32)]
+                ("k", ctypes.c_int32), ("epoch", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 PT = ctypes.POINTER(PgTable)
@@ -38,6 +38,7 @@ SIGNATURES = {
     "pg_fasta_scan_pack": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "pg_table_bytes": (c_i64, [c_i64]),
     "pg_table_clear": (c_int, [PT, c_vp]),
+    "pg_table_reset": (c_int, [PT, c_vp]),
     "pg_kmer_insert": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "pg_count_short": (c_int, [PT, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "pg_kmer_partition": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),

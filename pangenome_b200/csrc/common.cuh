@@ -6,6 +6,14 @@
 #include "../../include/pgdbg.h"
 
 #define PG_EMPTY 0xFFFFFFFFFFFFFFFFull
+// Slot value word: masks [0,32) | count or rdBG flags [32,54) | generation tag [54,64).  A slot is live only
+// while its tag equals the table's epoch, so "clearing" a table is epoch += 1 (pg_table_reset): no HBM traffic.
+// pg_table_clear writes tag 0 everywhere; epochs 1..PG_EPOCH_MAX are the live ones.  The count field saturates
+// at 255 by "skip the add once >= 255 was seen"; 22 bits leave room for every add that can be in flight before
+// a thread sees the saturated value (<= 2 per resident thread).
+#define PG_TAG_SHIFT 54
+#define PG_VAL_MASK ((1ull << PG_TAG_SHIFT) - 1ull)
+#define PG_EPOCH_MAX 1023
 #define PG_HD __host__ __device__ __forceinline__
 
 extern thread_local char pg_err_buf[512];
@@ -108,9 +116,18 @@ __device__ __forceinline__ uint4 pg_ld_stream(const uint4 *p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-// 16-byte table-slot load at L2 (slots are mutated by atomics, never trust L1)
-__device__ __forceinline__ void pg_ld_slot(const uint64_t *p, uint64_t &key, uint64_t &val) {
-    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(key), "=l"(val) : "l"(p));
+// 16-byte table-slot load at L2 (slots are mutated by atomics, never trust L1).  One .b128 access: the
+// key and the value word (which carries the generation tag) are observed together, like atom.cas.b128 writes them.
+__device__ __forceinline__ void pg_ld_slot_raw(const uint64_t *p, uint64_t &lo, uint64_t &hi) {
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));
+}
+// The slot as the current generation sees it: anything written under another tag reads as EMPTY.
+__device__ __forceinline__ void pg_ld_slot(const uint64_t *p, uint64_t tag, uint64_t &key, uint64_t &val) {
+    uint64_t lo, hi;
+    pg_ld_slot_raw(p, lo, hi);
+    const bool live = (hi & ~PG_VAL_MASK) == tag;
+    key = live ? lo : PG_EMPTY;
+    val = live ? (hi & PG_VAL_MASK) : 0ull;
 }
 // read-once streams (update records): keep them from displacing the table region in L2
 __device__ __forceinline__ uint64_t pg_policy_evict_first() {

@@ -2,9 +2,11 @@
 // K4 (reduced-dBG selection).
 //
 // Table = open addressing, linear probing, power-of-two capacity, 16-byte slots
-//   { u64 key | u32 masks | u32 count }      EMPTY key = 2^64-1
-// so that one probe touches one 32-byte sector.  A slot is claimed with a 64-bit atomicCAS on the key;
-// masks are merged with red.or.b32 and occurrences counted with red.add.u32 (no return value needed:
+//   { u64 key | u32 masks | count:22 tag:10 }
+// so that one probe touches one 32-byte sector.  A slot is live while its tag equals the table's epoch
+// (common.cuh), so a rebuild starts with epoch += 1 instead of rewriting the table.  A free slot is claimed
+// with ONE 128-bit CAS (key + first masks + first count + tag) against the contents just loaded; later
+// occurrences merge masks with red.or.b32 and count with red.add.u32 (no return value needed:
 // "fire and forget" reductions resolved in L2).  Both are skipped when the 16-byte slot load already
 // shows the bits set / the count saturated (>= 255; the reference clamps there, kmer_numba.py:551) -
 // repeats therefore cost one sector read and no atomic.
@@ -101,10 +103,10 @@ __global__ void k_table_clear(uint4 *slots, int64_t n_slots, int64_t *stats) {
 }
 
 // ---- read-out ----------------------------------------------------------------------------------
-__global__ void k_table_count(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k, uint64_t pow5_mid, int64_t *stats) {
+__global__ void k_table_count(const uint64_t *__restrict__ slots, int64_t cap, uint64_t tag, int mode, int k, uint64_t pow5_mid, int64_t *stats) {
     unsigned long long used = 0, ents = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t key = slots[2 * i];                       // streaming 8 of every 16 bytes; the value word is not needed
+        uint64_t key, v; pg_ld_slot(slots + 2 * i, tag, key, v);
         if (key == PG_EMPTY) continue;
         int n = 1;
         if (mode == PG_MODE_CANONICAL) n = (pg_maybe_palindrome(key, k, pow5_mid) && pg_rc_code(key, k) == key) ? 1 : 2;
@@ -120,7 +122,7 @@ __global__ void k_count_finish(int64_t *stats) {   // the short-record sentinel 
     if (stats[PG_STAT_SHORT] > 0) stats[PG_STAT_ENTRIES] += 1;
 }
 
-__global__ void k_table_export(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k,
+__global__ void k_table_export(const uint64_t *__restrict__ slots, int64_t cap, uint64_t tag, int mode, int k,
                                const int64_t *__restrict__ stats, uint64_t *keys, uint16_t *vals, uint8_t *cnts,
                                int64_t out_cap, unsigned long long *n_out) {
     const int lane = threadIdx.x & 31;
@@ -129,7 +131,7 @@ __global__ void k_table_export(const uint64_t *__restrict__ slots, int64_t cap, 
     for (int64_t base = i0 - lane; base < cap; base += stride) {   // whole warps iterate together
         int64_t i = base + lane;
         PgEntry e[2]; int n = 0;
-        if (i < cap) { uint64_t key, v; pg_ld_slot(slots + 2 * i, key, v); n = pg_slot_entries(key, v, mode, k, e); }
+        if (i < cap) { uint64_t key, v; pg_ld_slot(slots + 2 * i, tag, key, v); n = pg_slot_entries(key, v, mode, k, e); }
         // warp-aggregated append: one atomicAdd per warp
         unsigned tot = n;
         unsigned pre = n;
@@ -153,12 +155,12 @@ __global__ void k_table_export(const uint64_t *__restrict__ slots, int64_t cap, 
     }
 }
 
-__global__ void k_table_checksum(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k,
+__global__ void k_table_checksum(const uint64_t *__restrict__ slots, int64_t cap, uint64_t tag, int mode, int k,
                                  const int64_t *__restrict__ stats, unsigned long long *out) {
     unsigned long long n = 0, sum = 0, x = 0;
     int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t i = i0; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t key, v; pg_ld_slot(slots + 2 * i, key, v);
+        uint64_t key, v; pg_ld_slot(slots + 2 * i, tag, key, v);
         PgEntry e[2];
         int m = pg_slot_entries(key, v, mode, k, e);
         for (int q = 0; q < m; q++) { uint64_t h = pg_entry_mix(e[q].key, e[q].val, e[q].cnt); n++; sum += h; x ^= h; }
@@ -174,12 +176,12 @@ __global__ void k_table_checksum(const uint64_t *__restrict__ slots, int64_t cap
 }
 
 // ---- K4: reduced dBG -----------------------------------------------------------------------------
-__global__ void k4_rdbg_count(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k, uint64_t pow5_mid,
+__global__ void k4_rdbg_count(const uint64_t *__restrict__ slots, int64_t cap, uint64_t tag, int mode, int k, uint64_t pow5_mid,
                               const int64_t *__restrict__ stats, unsigned long long *out) {
     unsigned long long ns = 0, nm = 0;
     int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t i = i0; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t key, v; pg_ld_slot(slots + 2 * i, key, v);
+        uint64_t key, v; pg_ld_slot(slots + 2 * i, tag, key, v);
         uint32_t f = pg_rdbg_flags_fast(key, v, mode, k, pow5_mid);
         ns += f != 0; nm += (f & 1u) + ((f >> 1) & 1u);
     }
@@ -188,33 +190,24 @@ __global__ void k4_rdbg_count(const uint64_t *__restrict__ slots, int64_t cap, i
     if ((threadIdx.x & 31) == 0) { if (ns) atomicAdd(out, ns); if (nm) atomicAdd(out + 1, nm); }
 }
 
-__global__ void k4_rdbg_select(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k, uint64_t pow5_mid,
+__global__ void k4_rdbg_select(const uint64_t *__restrict__ slots, int64_t cap, uint64_t tag, int mode, int k, uint64_t pow5_mid,
                                const int64_t *__restrict__ stats, TableView rd) {
     int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t i = i0; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t key, v; pg_ld_slot(slots + 2 * i, key, v);
+        uint64_t key, v; pg_ld_slot(slots + 2 * i, tag, key, v);
         uint32_t f = pg_rdbg_flags_fast(key, v, mode, k, pow5_mid);
         if (!f) continue;
-        // every key arrives exactly once: claim with CAS, then plain stores of masks + flags
-        uint64_t s = tv_home(rd, key);
-        bool done = false;
-        for (uint32_t probe = 0; probe < PG_MAX_PROBE && !done; probe++) {
-            uint64_t *p = rd.slots + 2 * s;
-            uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)PG_EMPTY, (unsigned long long)key);
-            if (old == PG_EMPTY) { p[1] = (uint64_t)(uint32_t)v | ((uint64_t)f << 32); done = true; }
-            else s = (s + 1) & rd.capmask;
-        }
-        if (!done) atomicExch(reinterpret_cast<unsigned long long *>(rd.stats + PG_STAT_OVERFLOW), 1ull);
+        table_put_or(rd, key, (uint64_t)(uint32_t)v | ((uint64_t)f << 32));     // every key arrives exactly once
     }
     if (i0 == 0) rd.stats[PG_STAT_SHORT] = stats[PG_STAT_SHORT];
 }
 
-__global__ void k4_rdbg_export(const uint64_t *__restrict__ slots, int64_t cap, int mode, int k,
+__global__ void k4_rdbg_export(const uint64_t *__restrict__ slots, int64_t cap, uint64_t tag, int mode, int k,
                                const int64_t *__restrict__ stats, uint64_t *keys, uint16_t *vals, int64_t out_cap,
                                unsigned long long *n_out) {
     int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t i = i0; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t key, v; pg_ld_slot(slots + 2 * i, key, v);
+        uint64_t key, v; pg_ld_slot(slots + 2 * i, tag, key, v);
         if (key == PG_EMPTY) continue;
         uint32_t masks = (uint32_t)v, f = (uint32_t)(v >> 32);
         int n = (f & 1u) + ((f >> 1) & 1u);
@@ -234,6 +227,8 @@ int check_table(const pg_table *t, const char *who) {
     if (t->capacity < 2 || (t->capacity & (t->capacity - 1))) return pg_fail(PG_ERR_INVALID, "%s: capacity %lld is not a power of two >= 2", who, (long long)t->capacity);
     if (t->k < 1 || t->k > 27) return pg_fail(PG_ERR_INVALID, "%s: k=%d outside 1..27", who, t->k);
     if (t->mode < 0 || t->mode > 2) return pg_fail(PG_ERR_INVALID, "%s: bad mode %d", who, t->mode);
+    if (t->epoch < 1 || t->epoch > PG_EPOCH_MAX)
+        return pg_fail(PG_ERR_INVALID, "%s: epoch %d outside 1..%d (set 1 and call pg_table_clear once, then pg_table_reset)", who, t->epoch, PG_EPOCH_MAX);
     return PG_OK;
 }
 
@@ -251,15 +246,26 @@ extern "C" int pg_table_clear(const pg_table *t, pg_stream_t stream_) {
     int rc = check_table(t, "pg_table_clear"); if (rc) return rc;
     pg_tune_once();
     cudaStream_t stream = (cudaStream_t)stream_;
-    // The clear is pure DRAM writes and usually runs on a side stream next to K1/K2a (ALU bound): a full-occupancy
-    // grid would fill every SM's thread slots and make those kernels queue behind it, so it takes 2 CTAs per SM
-    // (stores are fire-and-forget: 16 warps per SM keep HBM busy) and leaves the rest of the SM to its neighbours.
+    // Full clear: 16 B/slot of DRAM writes (tag 0 everywhere = free under every epoch).  Needed once for a fresh
+    // allocation and when the epoch wraps; between builds pg_table_reset does the same job without touching HBM.
+    // 2 CTAs per SM: stores are fire-and-forget, 16 warps per SM keep HBM busy.
     static int per_sm = -1;
     if (per_sm < 0) { const char *e = getenv("PG_CLEAR_CTAS_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 1; }
     int64_t want = (t->capacity + 255) / 256, cap_grid = (int64_t)pg_num_sms() * per_sm;
     int grid = (int)(want < cap_grid ? want : cap_grid);
     k_table_clear<<<grid, 256, 0, stream>>>(reinterpret_cast<uint4 *>(t->d_slots), t->capacity, t->d_stats);
     PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_table_reset(pg_table *t, pg_stream_t stream_) {
+    int rc = check_table(t, "pg_table_reset"); if (rc) return rc;
+    if (t->epoch >= PG_EPOCH_MAX) {           // tags would repeat: rewrite the slots and start over
+        t->epoch = 1;
+        return pg_table_clear(t, stream_);
+    }
+    t->epoch += 1;                            // every slot written so far now reads as free
+    PG_CUDA(cudaMemsetAsync(t->d_stats, 0, PG_STAT_WORDS * sizeof(int64_t), (cudaStream_t)stream_));
     return PG_OK;
 }
 
@@ -320,7 +326,7 @@ extern "C" int pg_table_count(const pg_table *t, pg_stream_t stream_) {
     int rc = check_table(t, "pg_table_count"); if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(t->d_stats + PG_STAT_USED, 0, 2 * sizeof(int64_t), stream));
-    k_table_count<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(t->d_slots, t->capacity, t->mode, t->k, pg_pow5(t->k / 2), t->d_stats);
+    k_table_count<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(t->d_slots, t->capacity, pg_tag(t), t->mode, t->k, pg_pow5(t->k / 2), t->d_stats);
     k_count_finish<<<1, 1, 0, stream>>>(t->d_stats);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
@@ -332,7 +338,7 @@ extern "C" int pg_table_export(const pg_table *t, uint64_t *d_keys, uint16_t *d_
     if (!d_keys || !d_n || cap < 0) return pg_fail(PG_ERR_INVALID, "pg_table_export: bad arguments");
     cudaStream_t stream = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(d_n, 0, sizeof(int64_t), stream));
-    k_table_export<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(t->d_slots, t->capacity, t->mode, t->k, t->d_stats, d_keys, d_vals, d_cnts, cap,
+    k_table_export<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(t->d_slots, t->capacity, pg_tag(t), t->mode, t->k, t->d_stats, d_keys, d_vals, d_cnts, cap,
                                                                   reinterpret_cast<unsigned long long *>(d_n));
     PG_CUDA(cudaGetLastError());
     return PG_OK;
@@ -343,7 +349,7 @@ extern "C" int pg_table_checksum(const pg_table *t, uint64_t *d_out, pg_stream_t
     if (!d_out) return pg_fail(PG_ERR_INVALID, "pg_table_checksum: null output");
     cudaStream_t stream = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(d_out, 0, 3 * sizeof(uint64_t), stream));
-    k_table_checksum<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(t->d_slots, t->capacity, t->mode, t->k, t->d_stats,
+    k_table_checksum<<<scan_grid(t->capacity, 256), 256, 0, stream>>>(t->d_slots, t->capacity, pg_tag(t), t->mode, t->k, t->d_stats,
                                                                     reinterpret_cast<unsigned long long *>(d_out));
     PG_CUDA(cudaGetLastError());
     return PG_OK;
@@ -354,7 +360,7 @@ extern "C" int pg_rdbg_count(const pg_table *dbg, int64_t *d_out, pg_stream_t st
     if (!d_out) return pg_fail(PG_ERR_INVALID, "pg_rdbg_count: null output");
     cudaStream_t stream = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(int64_t), stream));
-    k4_rdbg_count<<<scan_grid(dbg->capacity, 256), 256, 0, stream>>>(dbg->d_slots, dbg->capacity, dbg->mode, dbg->k, pg_pow5(dbg->k / 2), dbg->d_stats,
+    k4_rdbg_count<<<scan_grid(dbg->capacity, 256), 256, 0, stream>>>(dbg->d_slots, dbg->capacity, pg_tag(dbg), dbg->mode, dbg->k, pg_pow5(dbg->k / 2), dbg->d_stats,
                                                                    reinterpret_cast<unsigned long long *>(d_out));
     PG_CUDA(cudaGetLastError());
     return PG_OK;
@@ -366,7 +372,7 @@ extern "C" int pg_rdbg_select(const pg_table *dbg, const pg_table *rdbg, pg_stre
     if (dbg->mode != rdbg->mode || dbg->k != rdbg->k) return pg_fail(PG_ERR_INVALID, "pg_rdbg_select: mode/k mismatch");
     cudaStream_t stream = (cudaStream_t)stream_;
     TableView rd = make_view(rdbg);
-    k4_rdbg_select<<<scan_grid(dbg->capacity, 256), 256, 0, stream>>>(dbg->d_slots, dbg->capacity, dbg->mode, dbg->k, pg_pow5(dbg->k / 2), dbg->d_stats, rd);
+    k4_rdbg_select<<<scan_grid(dbg->capacity, 256), 256, 0, stream>>>(dbg->d_slots, dbg->capacity, pg_tag(dbg), dbg->mode, dbg->k, pg_pow5(dbg->k / 2), dbg->d_stats, rd);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
@@ -377,7 +383,7 @@ extern "C" int pg_rdbg_export(const pg_table *rdbg, uint64_t *d_keys, uint16_t *
     if (!d_keys || !d_n || cap < 0) return pg_fail(PG_ERR_INVALID, "pg_rdbg_export: bad arguments");
     cudaStream_t stream = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(d_n, 0, sizeof(int64_t), stream));
-    k4_rdbg_export<<<scan_grid(rdbg->capacity, 256), 256, 0, stream>>>(rdbg->d_slots, rdbg->capacity, rdbg->mode, rdbg->k, rdbg->d_stats, d_keys, d_vals, cap,
+    k4_rdbg_export<<<scan_grid(rdbg->capacity, 256), 256, 0, stream>>>(rdbg->d_slots, rdbg->capacity, pg_tag(rdbg), rdbg->mode, rdbg->k, rdbg->d_stats, d_keys, d_vals, cap,
                                                                      reinterpret_cast<unsigned long long *>(d_n));
     PG_CUDA(cudaGetLastError());
     return PG_OK;

@@ -81,16 +81,21 @@ PG_HD bool pg_is_interior(const PgWindow &w, int64_t g0, int G, int k, int64_t r
                           int64_t g_begin, int64_t g_end) {
     return !w.any_amb() && have_rec && g0 - 2 >= rs && g0 + G + k + 1 <= re && g0 >= g_begin && g0 + G <= g_end;
 }
+template <bool NARROW> struct PgView { typedef uint64_t type; };
+template <> struct PgView<true> { typedef uint32_t type; };
 // Visit G consecutive interior positions (window index j0 .. j0+G-1, j0 + G <= 32): f(q, F, R, vf, vr).
 // Every digit is a constant-shift field of three 64-bit views; codes roll with one multiply each.
 template <int G, class Fn>
 PG_HD void pg_interior_visit(const PgWindow &w, int j0, int k, uint64_t pow5km1, Fn &&f) {
-    const uint64_t dprev_w = pg_win64(w, j0 - 1), dout_w = pg_win64(w, j0), din_w = pg_win64(w, j0 + k);
+    const uint64_t dout64 = pg_win64(w, j0);
     uint64_t F = 0, R = 0, p5 = 1;
     for (int i = 0; i < k; i++) {
-        uint32_t d = (uint32_t)(dout_w >> (2 * i)) & 3u;      // k <= 27 digits: all inside the 64-bit view
+        uint32_t d = (uint32_t)(dout64 >> (2 * i)) & 3u;      // k <= 27 digits: all inside the 64-bit view
         F += (uint64_t)d * p5; R = R * 5 + (3u - d); p5 *= 5;
     }
+    // the G per-position digit fields: 32-bit views are enough (and half the shift work) for G <= 16
+    using view_t = typename PgView<(G <= 16)>::type;
+    const view_t dprev_w = (view_t)pg_win64(w, j0 - 1), dout_w = (view_t)dout64, din_w = (view_t)pg_win64(w, j0 + k);
 #pragma unroll
     for (int q = 0; q < G; q++) {
         const uint32_t dp = (uint32_t)(dprev_w >> (2 * q)) & 3u, dout = (uint32_t)(dout_w >> (2 * q)) & 3u,

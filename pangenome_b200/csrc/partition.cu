@@ -92,7 +92,9 @@ k2a_partition(PartArgs a) {
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_perm + MAXR);          // n_parts
     uint32_t *s_off = s_hist + a.n_parts;                                    // n_parts: exclusive offsets
     uint32_t *s_tick = s_off + a.n_parts;                                    // n_parts: tickets
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_tick + a.n_parts + (a.n_parts & 1));
+    uint32_t *s_room = s_tick + a.n_parts;                                   // n_parts: records of this tile the bucket can still take
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_room + a.n_parts);
+    uint4 **s_dst = reinterpret_cast<uint4 **>(s_base + a.n_parts);          // n_parts: address of sorted position 0
     __shared__ uint32_t s_nrec;
     __shared__ uint32_t s_chunk[32];
     const uint64_t pol = pg_policy_evict_first();
@@ -189,7 +191,24 @@ k2a_partition(PartArgs a) {
             if (threadIdx.x == 31) s_nrec = inc;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < a.n_parts; i += KP_THREADS) s_off[i] += s_chunk[i >> 5];
+        // final offsets, and per bucket the address its sorted position 0 would map to: record at sorted
+        // position o goes to s_dst[pid][o] (its run in the bucket starts at s_base, its run in the tile at s_off)
+        for (int i = threadIdx.x; i < a.n_parts; i += KP_THREADS) {
+            const uint32_t off = s_off[i] + s_chunk[i >> 5];
+            s_off[i] = off;
+            uint4 *bucket;
+            if (a.peers) {     // [source rank][sub][part_cap] in the owner's memory: the layout an all-to-all would produce
+                const uint32_t owner = (uint32_t)i >> a.sub_bits, sub = (uint32_t)i & ((1u << a.sub_bits) - 1u);
+                bucket = a.peers[owner] + (((int64_t)a.my_rank << a.sub_bits) + sub) * a.part_cap;
+            } else {
+                bucket = a.records + (int64_t)i * a.part_cap;
+            }
+            const unsigned long long base = s_base[i];
+            s_dst[i] = bucket + ((int64_t)base - (int64_t)off);
+            // records of this tile that still fit the bucket (the host sees the overflow in part_counts)
+            const int64_t room = a.part_cap - (int64_t)base;
+            s_room[i] = room <= 0 ? 0u : (room > 0xFFFF ? 0xFFFFu : (uint32_t)room);
+        }
         __syncthreads();
         const uint32_t nrec = s_nrec;
         if (nrec == 0) continue;
@@ -197,24 +216,29 @@ k2a_partition(PartArgs a) {
         for (uint32_t i = threadIdx.x; i < (uint32_t)MAXR; i += KP_THREADS) {
             uint32_t pid = s_pid[i];
             if (pid == NOREC) continue;
-            uint32_t o = s_off[pid] + atomicAdd(&s_tick[pid], 1u);
-            s_perm[o] = (uint16_t)i;
+            const uint32_t rank = atomicAdd(&s_tick[pid], 1u);
+            s_perm[s_off[pid] + rank] = rank < s_room[pid] ? (uint16_t)i : NOREC;
         }
         __syncthreads();
-        // ---- 4. coalesced write-out: consecutive threads write consecutive records of one bucket ----
-        for (uint32_t o = threadIdx.x; o < nrec; o += KP_THREADS) {
-            uint32_t i = s_perm[o];
-            uint32_t pid = s_pid[i];
-            unsigned long long dst = s_base[pid] + (o - s_off[pid]);
-            if ((int64_t)dst < a.part_cap) {
-                if (a.peers) {     // [source rank][sub][part_cap] in the owner's memory: the layout an all-to-all would produce
-                    const uint32_t owner = pid >> a.sub_bits, sub = pid & ((1u << a.sub_bits) - 1u);
-                    uint4 *base = a.peers[owner];
-                    base[(((int64_t)a.my_rank << a.sub_bits) + sub) * a.part_cap + (int64_t)dst] = s_rec[i];
-                } else {
-                    pg_st_stream_l2first(a.records + (int64_t)pid * a.part_cap + (int64_t)dst, s_rec[i], pol);
-                }
+        // ---- 4. coalesced write-out: consecutive threads write consecutive records of one bucket; four
+        // independent chains (perm -> bucket id -> address, record) per thread hide the shared-memory latency
+        const bool remote = a.peers != nullptr;
+        for (uint32_t o0 = threadIdx.x; o0 < nrec; o0 += 4 * KP_THREADS) {
+            uint32_t idx[4]; uint4 *dst[4]; uint4 rec[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t o = o0 + j * KP_THREADS;
+                idx[j] = o < nrec ? (uint32_t)s_perm[o] : (uint32_t)NOREC;
             }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (idx[j] != NOREC) { dst[j] = s_dst[s_pid[idx[j]]] + (o0 + j * KP_THREADS); rec[j] = s_rec[idx[j]]; }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (idx[j] != NOREC) {
+                    if (remote) *dst[j] = rec[j];
+                    else pg_st_stream_l2first(dst[j], rec[j], pol);
+                }
         }
     }
 }
@@ -239,12 +263,13 @@ __device__ __forceinline__ bool k3_fetch(const uint4 *__restrict__ records, cons
     }
     return false;
 }
-template <bool PREFETCH>
-__global__ void __launch_bounds__(256)
+template <bool PREFETCH, int MINB, bool ROTATE>
+__global__ void __launch_bounds__(256, MINB)
 k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
                   const int64_t *__restrict__ seg_cnt, int n_regions, int n_src, int64_t seg_cap) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t rot = ROTATE ? (int64_t)((gridDim.x * 618u) / 1000u) * blockDim.x : 0;
     uint32_t n_claimed = 0;
     if (PREFETCH) {
         uint4 r;
@@ -260,10 +285,16 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
             if (b + 1 < n_regions) have = k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b + 1, i0, r);
         }
     } else {
+        // A region holds a non-integral number of grid strides of records, so the threads with the lowest
+        // start index do one more record than the rest.  The start index is rotated from region to region
+        // (whole CTAs, golden-ratio steps) so that the extra record falls on different threads each time
+        // and every thread ends up with the same total instead of the low ones carrying all the excess.
+        int64_t start = i0;
         for (int b = 0; b < n_regions; b++) {
             uint4 r;
-            for (int64_t i = i0; k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b, i, r); i += stride)
+            for (int64_t i = start; k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b, i, r); i += stride)
                 table_upsert(t, (uint64_t)r.x | ((uint64_t)r.y << 32), r.z, r.w, n_claimed);
+            start += rot; if (start >= stride) start -= stride;
         }
     }
     publish_claims(t, n_claimed);
@@ -271,7 +302,7 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
 
 int part_smem_bytes(int mode, int n_parts, int threads) {
     int maxr = (mode == PG_MODE_LITERAL_RC ? 2 : 1) * threads * KP_G;
-    return maxr * 16 + maxr * 2 * 2 + (3 * n_parts + (n_parts & 1)) * 4 + n_parts * 8 + 16;
+    return maxr * 16 + maxr * 2 * 2 + 4 * n_parts * 4 + 2 * n_parts * 8 + 16;
 }
 
 }  // namespace
@@ -297,7 +328,7 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
     a.seq_off = d_seq_off; a.n_rec = n_rec; a.g_begin = g_begin; a.g_end = g_end; a.k = t->k; a.pow5km1 = pg_pow5(t->k - 1);
     static int thr_env = -1;
     if (thr_env < 0) { const char *e = getenv("PG_K2A_THREADS"); thr_env = e ? atoi(e) : 0; }
-    const int threads = (thr_env == 128 || thr_env == 256 || thr_env == 512) ? thr_env : (d_peers ? (t->mode == PG_MODE_LITERAL_RC ? 256 : 512) : 128);
+    const int threads = (thr_env == 128 || thr_env == 256 || thr_env == 512) ? thr_env : (d_peers ? (t->mode == PG_MODE_LITERAL_RC ? 256 : 512) : 256);
     const int tile = threads * KP_G;
     a.t_first = g_begin / tile; a.n_tiles = (g_end + tile - 1) / tile - a.t_first;
     a.sub_bits = sub_bits; a.owner_bits = owner_bits; a.n_parts = n_parts;
@@ -313,7 +344,7 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
         a.sample_count = reinterpret_cast<unsigned long long *>(d_sample_count);
     }
     int smem = part_smem_bytes(t->mode, n_parts, threads);
-    int per_sm = 200 * 1024 / smem; if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
+    int per_sm = 227 * 1024 / (smem + 1024);      // 227 KB usable per SM, 1 KB reserved per CTA if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
     int64_t maxg = (int64_t)pg_num_sms() * per_sm;
     int grid = (int)(a.n_tiles < maxg ? a.n_tiles : maxg);
 #define K2A_LAUNCH(M, T)                                                                                            \
@@ -389,7 +420,7 @@ extern "C" int pg_peer_free(void *d_ptr) { PG_CUDA(cudaFree(d_ptr)); return PG_O
 
 extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
                                  const int64_t *d_seg_cnt, int n_regions, int n_src, int64_t seg_cap, pg_stream_t stream_) {
-    if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)))
+    if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)) || t->epoch < 1 || t->epoch > PG_EPOCH_MAX)
         return pg_fail(PG_ERR_INVALID, "pg_insert_records: bad table");
     if (n_regions < 0 || n_src < 1 || n_src > K3_MAX_SRC || (n_regions > 0 && (!d_records || !d_seg_off || !d_seg_cnt)))
         return pg_fail(PG_ERR_INVALID, "pg_insert_records: bad arguments (n_src must be 1..%d)", K3_MAX_SRC);
@@ -397,16 +428,22 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
     if (seg_cap <= 0) seg_cap = INT64_MAX;
     if (reinterpret_cast<uintptr_t>(d_records) & 15) return pg_fail(PG_ERR_INVALID, "pg_insert_records: records must be 16-byte aligned");
     TableView tv = make_view(t);
-    static int gmul = -1, prefetch = -1;
+    static int gmul = -1, prefetch = -1, rotate = 1;
     if (gmul < 0) {
-        const char *e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 8;
+        const char *e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 5;
         e = getenv("PG_K3_PREFETCH"); prefetch = e ? atoi(e) : 0;
+        e = getenv("PG_K3_ROTATE"); rotate = e ? atoi(e) : 1;
     }
+    // the grid is exactly the resident CTAs (a region sweep must not leave a second wave behind): 8 per SM caps the
+    // kernel at 32 registers, which costs it a few stack slots; 6 per SM runs it spill-free at 38
     int grid = pg_num_sms() * gmul;
-    if (prefetch)
-        k3_insert_records<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap);
-    else
-        k3_insert_records<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(tv, reinterpret_cast<const uint4 *>(d_records), d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap);
+    const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
+    cudaStream_t st = (cudaStream_t)stream_;
+#define K3_LAUNCH(P, M, R) k3_insert_records<P, M, R><<<grid, 256, 0, st>>>(tv, recs, d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap)
+    if (prefetch) K3_LAUNCH(true, 8, false);
+    else if (gmul >= 7) { if (rotate) K3_LAUNCH(false, 8, true); else K3_LAUNCH(false, 8, false); }
+    else { if (rotate) K3_LAUNCH(false, 6, true); else K3_LAUNCH(false, 6, false); }
+#undef K3_LAUNCH
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

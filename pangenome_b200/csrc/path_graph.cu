@@ -98,7 +98,7 @@ __device__ __forceinline__ bool rdbg_hit(const TableView &rd, int mode, uint64_t
     uint64_t s = tv_home(rd, key);
     for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
         uint64_t ck, cv;
-        pg_ld_slot(rd.slots + 2 * s, ck, cv);
+        pg_ld_slot(rd.slots + 2 * s, rd.tag, ck, cv);
         if (ck == key) {
             uint32_t f = (uint32_t)(cv >> 32);
             slot_o = (s << 1) | o;
@@ -429,26 +429,20 @@ __global__ void k8_rows(const uint32_t *__restrict__ flag, const int64_t *__rest
 }
 
 // ---- raw slot transfer + rank-independent hits (multi-GPU path stages) --------------------------
-__global__ void k_export_raw(const uint64_t *__restrict__ slots, int64_t cap, uint64_t *keys, uint64_t *vals, int64_t out_cap,
+__global__ void k_export_raw(const uint64_t *__restrict__ slots, int64_t cap, uint64_t tag, uint64_t *keys, uint64_t *vals, int64_t out_cap,
                              unsigned long long *n_out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= cap) return;
-    uint64_t k = slots[2 * i];
+    uint64_t k, v;
+    pg_ld_slot(slots + 2 * i, tag, k, v);              // v comes back without the generation tag
     if (k == PG_EMPTY) return;
     unsigned long long at = atomicAdd(n_out, 1ull);
-    if ((int64_t)at < out_cap) { keys[at] = k; vals[at] = slots[2 * i + 1]; }
+    if ((int64_t)at < out_cap) { keys[at] = k; vals[at] = v; }
 }
 __global__ void k_insert_raw(TableView t, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t key = keys[i], s = tv_home(t, key);
-    for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
-        uint64_t *p = t.slots + 2 * s;
-        uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)PG_EMPTY, (unsigned long long)key);
-        if (old == PG_EMPTY || old == key) { atomicOr(reinterpret_cast<unsigned long long *>(p + 1), (unsigned long long)vals[i]); return; }
-        s = (s + 1) & t.capmask;
-    }
-    atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
+    table_put_or(t, keys[i], vals[i]);
 }
 // node key (local rdBG slot, orientation, v5) -> the reference's literal code: what another rank can re-key
 __global__ void k_hits_decode(const uint64_t *__restrict__ hit_node, int64_t n, const uint64_t *__restrict__ rd_slots, int64_t rd_cap,
@@ -482,7 +476,8 @@ int check_graph(const pg_graph *g, const char *who) {
 }
 
 int check_tab(const pg_table *t, const char *who) {
-    if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)) || t->k < 1 || t->k > 27)
+    if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)) || t->k < 1 || t->k > 27 ||
+        t->epoch < 1 || t->epoch > PG_EPOCH_MAX)
         return pg_fail(PG_ERR_INVALID, "%s: bad table", who);
     return PG_OK;
 }
@@ -649,7 +644,7 @@ extern "C" int pg_table_export_raw(const pg_table *t, uint64_t *d_keys, uint64_t
     if (!d_keys || !d_vals || !d_n || cap < 0) return pg_fail(PG_ERR_INVALID, "pg_table_export_raw: bad arguments");
     cudaStream_t st = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(d_n, 0, 8, st));
-    k_export_raw<<<blocks_for(t->capacity, 256), 256, 0, st>>>(t->d_slots, t->capacity, d_keys, d_vals, cap, reinterpret_cast<unsigned long long *>(d_n));
+    k_export_raw<<<blocks_for(t->capacity, 256), 256, 0, st>>>(t->d_slots, t->capacity, pg_tag(t), d_keys, d_vals, cap, reinterpret_cast<unsigned long long *>(d_n));
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

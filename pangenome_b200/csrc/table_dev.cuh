@@ -10,11 +10,12 @@ constexpr uint32_t PG_MAX_PROBE = 1u << 16;
 // Home slot = TOP bits of the 64-bit mix: the high bits of a slot index are then hash bits too, so
 // "region of the table" == "hash prefix" for every capacity (K2a buckets records by that prefix before
 // the table is even sized); the owner rank of the multi-GPU split comes from the LOW bits instead.
-struct TableView { uint64_t *slots; uint64_t capmask; int64_t *stats; int shift; };
+struct TableView { uint64_t *slots; uint64_t capmask; int64_t *stats; int shift; uint64_t tag; };
+inline uint64_t pg_tag(const pg_table *t) { return (uint64_t)(uint32_t)t->epoch << PG_TAG_SHIFT; }
 __host__ __device__ __forceinline__ uint64_t tv_home(const TableView &t, uint64_t key) { return pg_mix64(key) >> t.shift; }
 inline TableView make_view(const pg_table *t) {
     int bits = 0; while ((1ll << bits) < t->capacity) bits++;
-    return TableView{t->d_slots, (uint64_t)t->capacity - 1, t->d_stats, 64 - bits};
+    return TableView{t->d_slots, (uint64_t)t->capacity - 1, t->d_stats, 64 - bits, pg_tag(t)};
 }
 
 // Merge one update into a slot whose key already matches; cv = the value word last seen.
@@ -23,28 +24,54 @@ __device__ __forceinline__ void slot_merge(uint64_t *p, uint64_t cv, uint32_t ma
     if (((uint32_t)cv & masks) != masks) pg_red_or32(v, masks);
     if ((uint32_t)(cv >> 32) < 255u) pg_red_add32(v + 1, inc);       // counts clamp at 255 upstream (:551)
 }
-// Continue an upsert from slot s whose contents (ck, cv) were already loaded.
+// Continue an upsert from slot s whose raw contents (lo, hi) were already loaded.
 // returns the slot index the key lives in (claimed if absent), or -1 when probing gives up
-__device__ __forceinline__ int64_t table_upsert_from(const TableView &t, uint64_t s, uint64_t ck, uint64_t cv, uint64_t key,
+__device__ __forceinline__ int64_t table_upsert_from(const TableView &t, uint64_t s, uint64_t lo, uint64_t hi, uint64_t key,
                                                      uint32_t masks, uint32_t inc, uint32_t &n_claimed) {
     for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
         uint64_t *p = t.slots + 2 * s;
-        if (probe) pg_ld_slot(p, ck, cv);
-        if (ck == PG_EMPTY) {
-            // empty slots always hold {EMPTY, 0}: claim key + first masks + first count at once
-            pg_cas128(p, PG_EMPTY, 0ull, key, (uint64_t)masks | ((uint64_t)inc << 32), ck, cv);
-            if (ck == PG_EMPTY) { n_claimed++; return (int64_t)s; }
+        if (probe) pg_ld_slot_raw(p, lo, hi);
+        if ((hi & ~PG_VAL_MASK) != t.tag) {
+            // not of this generation = free: replace whatever it holds by key + first masks + first count + tag
+            // in ONE 128-bit CAS against the contents just seen
+            uint64_t olo, ohi;
+            pg_cas128(p, lo, hi, key, (uint64_t)masks | ((uint64_t)inc << 32) | t.tag, olo, ohi);
+            if (olo == lo && ohi == hi) { n_claimed++; return (int64_t)s; }
+            lo = olo; hi = ohi;              // lost the race: the slot is live now, look at its key
         }
-        if (ck == key) { slot_merge(p, cv, masks, inc); return (int64_t)s; }
+        if (lo == key) { slot_merge(p, hi & PG_VAL_MASK, masks, inc); return (int64_t)s; }
         s = (s + 1) & t.capmask;
     }
     atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
     return -1;
 }
 __device__ __forceinline__ int64_t table_upsert(const TableView &t, uint64_t key, uint32_t masks, uint32_t inc, uint32_t &n_claimed) {
-    uint64_t s = tv_home(t, key), ck, cv;
-    pg_ld_slot(t.slots + 2 * s, ck, cv);
-    return table_upsert_from(t, s, ck, cv, key, masks, inc, n_claimed);
+    uint64_t s = tv_home(t, key), lo, hi;
+    pg_ld_slot_raw(t.slots + 2 * s, lo, hi);
+    return table_upsert_from(t, s, lo, hi, key, masks, inc, n_claimed);
+}
+// Store {key, val} whole (no masks/count semantics): claims a free slot, or ORs val into the slot that already
+// holds the key.  Used where every key arrives once (K4) or arrives with its final value (gathered tables).
+__device__ __forceinline__ bool table_put_or(const TableView &t, uint64_t key, uint64_t val) {
+    uint64_t s = tv_home(t, key);
+    for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
+        uint64_t *p = t.slots + 2 * s, lo, hi;
+        pg_ld_slot_raw(p, lo, hi);
+        if ((hi & ~PG_VAL_MASK) != t.tag) {
+            uint64_t olo, ohi;
+            pg_cas128(p, lo, hi, key, (val & PG_VAL_MASK) | t.tag, olo, ohi);
+            if (olo == lo && ohi == hi) return true;
+            lo = olo; hi = ohi;
+        }
+        if (lo == key) {
+            if ((hi & val & PG_VAL_MASK) != (val & PG_VAL_MASK))
+                atomicOr(reinterpret_cast<unsigned long long *>(p + 1), (unsigned long long)(val & PG_VAL_MASK));
+            return true;
+        }
+        s = (s + 1) & t.capmask;
+    }
+    atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
+    return false;
 }
 // one atomicAdd per warp: slots claimed by this kernel -> PG_STAT_USED (distinct keys, kept by the inserts)
 __device__ __forceinline__ void publish_claims(const TableView &t, uint32_t n_claimed) {

@@ -7,6 +7,7 @@ sequence data is a kernel of libpgdbg.so.  No CPU fallback: constructing any of
 these objects without CUDA raises.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -156,11 +157,14 @@ class DbgTable:
         self.mode = int(mode)
         self.slots = torch.empty(2 * self.capacity, dtype=torch.int64, device=device)
         self.stats = torch.zeros(_lib.PG_STAT_WORDS, dtype=torch.int64, device=device)
-        self.c = PgTable(self.slots.data_ptr(), self.capacity, self.stats.data_ptr(), self.mode, self.k)
-        self.clear()
+        self.c = PgTable(self.slots.data_ptr(), self.capacity, self.stats.data_ptr(), self.mode, self.k, 1, 0)
+        # a fresh allocation holds arbitrary tags: write every slot once; from then on clear() is an epoch bump
+        check(self.L.pg_table_clear(ctypes.byref(self.c), _stream()), "pg_table_clear")
 
     def clear(self):
-        check(self.L.pg_table_clear(ctypes.byref(self.c), _stream()), "pg_table_clear")
+        """Empty the table: the epoch advances and every slot written so far reads as free - no HBM traffic
+        (pg_table_reset rewrites the slots only when the 10-bit generation tag wraps)."""
+        check(self.L.pg_table_reset(ctypes.byref(self.c), _stream()), "pg_table_reset")
 
     def set_capacity(self, capacity):
         """Use only the first ``capacity`` (power of two) slots of the allocated buffer."""
@@ -329,7 +333,7 @@ def partition_kmers(packed, k, mode, n_rec, owner_bits, sub_bits, g_begin=None, 
     part_cap = int((g_end - g_begin) * per_pos / n_parts * slack) + 4096
     if buckets is None or buckets.n_parts != n_parts or buckets.part_cap < part_cap:
         buckets = RecordBuckets(n_parts, part_cap, packed.pk2.device)
-    desc = PgTable(None, 2, None, mode, k)          # only mode and k are read by K2a
+    desc = PgTable(None, 2, None, mode, k, 1, 0)    # only mode and k are read by K2a
     if sampler is not None:
         sampler.reset()
     check(L.pg_kmer_partition(ctypes.byref(desc), _ptr(packed.pk2), _ptr(packed.amb), _ptr(packed.d_seq_off), n_rec,
@@ -405,25 +409,21 @@ class TwoPhaseBuilder:
         part_cap = int(n_positions * per_pos / n_parts * 1.25) + 4096
         self.buckets = RecordBuckets(n_parts, part_cap, device)
         # K3 is fastest on a sparse table (measured on config 2: load 0.125 -> 1.02 ms, 0.25 -> 1.10 ms, 0.5 -> 1.33 ms)
-        # and the clear overlaps K1/K2a, so the positions upper bound is used while it is affordable; the
+        # and emptying a table costs nothing (epoch bump), so the positions upper bound is used while it is affordable; the
         # estimator takes over when that table would eat a large part of the free HBM (config-5 scale)
         if estimate is None:
             free = torch.cuda.mem_get_info(device)[0] if torch.cuda.is_available() else 0
             estimate = cap * 16 > 0.35 * free
         self.sampler = KeySampler(n_positions * per_pos, device) if (estimate and not capacity) else None
-        self.launches_per_build = 4          # k2a_partition, clear, count_short, k3_insert_records
-        self.side = torch.cuda.Stream(device=device)
+        self.launches_per_build = 3          # k2a_partition, count_short, k3_insert_records (the reset is a 64-byte memset)
         self.last_estimate = None
 
     def begin(self):
-        """Without the estimator the (full) table clear can start early on the side stream, e.g. before
-        the H2D copy of the next input; with it the capacity is only known after K2a."""
+        """Empty the table for the next build (an epoch bump, DbgTable.clear).  With the estimator the
+        capacity is only known after K2a, so build() resets there instead."""
         if self.sampler is not None:
             return
-        st = torch.cuda.current_stream()
-        self.side.wait_stream(st)            # whoever still reads the previous table finishes first
-        with torch.cuda.stream(self.side):
-            self.table.clear()
+        self.table.clear()
         self._begun = True
 
     def build(self, packed, n_rec, ev=None):
@@ -435,7 +435,6 @@ class TwoPhaseBuilder:
             self.begin()
         self._begun = False
         if n_rec == 0:
-            st.wait_stream(self.side)
             if self.sampler is not None:
                 t.clear()
             return t
@@ -451,8 +450,6 @@ class TwoPhaseBuilder:
             self.last_estimate = self.sampler.estimate()            # 8-byte D2H, synchronises
             t.set_capacity(capacity_for(self.last_estimate, self.cap_max))
             t.clear()
-        else:
-            st.wait_stream(self.side)        # K3 needs the cleared table
         check(L.pg_count_short(ctypes.byref(t.c), _ptr(packed.d_seq_off), n_rec, g_begin, g_end, _stream()), "pg_count_short")
         if ev is not None:
             e[2].record(st)
@@ -480,11 +477,10 @@ class TwoPhaseBuilder:
         if ev is not None:
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record(st)
-        desc = PgTable(None, 2, None, self.mode, self.k)
+        desc = PgTable(None, 2, None, self.mode, self.k, 1, 0)
         check(L.pg_kmer_partition_dev(ctypes.byref(desc), _ptr(packed.pk2), _ptr(packed.amb), _ptr(packed.d_seq_off),
                                       _ptr(packed.d_counts), packed.cap_records, packed.nbytes, self.owner_bits, self.sub_bits,
                                       _ptr(b.records), b.part_cap, _ptr(b.counts), _stream()), "pg_kmer_partition_dev")
-        st.wait_stream(self.side)            # K3 needs the cleared table
         check(L.pg_count_short_dev(ctypes.byref(t.c), _ptr(packed.d_seq_off), _ptr(packed.d_counts), packed.cap_records, _stream()),
               "pg_count_short_dev")
         if ev is not None:

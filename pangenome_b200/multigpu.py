@@ -127,7 +127,7 @@ class DistributedBuilder:
         g_end = int(packed.seq_off[n_rec]) if n_rec > 0 else 0
         span = g_end - g_begin
         step = ((span + C - 1) // C + 2047) // 2048 * 2048 if span > 0 else 0
-        desc = _lib.PgTable(None, 2, None, _lib.PG_MODE_CANONICAL, self.k)
+        desc = _lib.PgTable(None, 2, None, _lib.PG_MODE_CANONICAL, self.k, 1, 0)
         for c in range(C):
             lo = min(g_begin + c * step, g_end)
             hi = min(lo + step, g_end)
@@ -261,7 +261,7 @@ class PeerBuilder:
         g_end = int(packed.seq_off[n_rec]) if n_rec > 0 else 0
         buf = self.parity
         self.parity ^= 1
-        desc = _lib.PgTable(None, 2, None, _lib.PG_MODE_CANONICAL, self.k)
+        desc = _lib.PgTable(None, 2, None, _lib.PG_MODE_CANONICAL, self.k, 1, 0)
         eng.check(L.pg_kmer_partition_p2p(ctypes.byref(desc), eng._ptr(packed.pk2), eng._ptr(packed.amb),
                                           eng._ptr(packed.d_seq_off), n_rec, g_begin, g_end, self.owner_bits, self.sub_bits,
                                           eng._ptr(self.peer_tables[buf]), self.rank, self.part_cap,

@@ -167,3 +167,41 @@ def test_single_pass_k1_matches(eng):
         assert r.returncode == 0, r.stderr[-2000:]
         res[flag] = r.stdout.strip().splitlines()[-1]
     assert res["0"] == res["1"]
+
+
+def test_table_generations_and_wrap(eng):
+    """DbgTable.clear() is an epoch bump (pg_table_reset): slots written by earlier builds must read as
+    free in every later one - also across the wrap of the 10-bit generation tag, where the slots are
+    rewritten - and in all three table modes.  Two different inputs alternate so that a stale slot
+    leaking through would change the table."""
+    from pangenome_b200 import _lib
+    inputs = [b">a\nACGTTGCAAGGCTTAACCGGATAGGCTTACGATCGGANCTTAGGA\n>b\nTTGACGGTCATTG\n",
+              b">x\nGGGGGGGGGGGGGGGGGGGACGTACGTACGTTTTTTTTTTTTTTTTTTT\n>s\nAC\n"]
+    for mode, rc in ((_lib.PG_MODE_CANONICAL, True), (_lib.PG_MODE_LITERAL_RC, True), (_lib.PG_MODE_LITERAL, False)):
+        packs = [eng.PackedSeqs(eng.to_device_bytes(d)) for d in inputs]
+        want = []
+        for d in inputs:
+            r = oracle.run(d, 7, c=3 if rc else 0, stages=1)
+            want.append(oracle.table_checksum(*r["dbg"]))
+        t = eng.DbgTable(256, 7, mode)
+        assert t.c.epoch == 1
+        seen_wrap = False
+        for it in range(1100):
+            i = (it * 7 + it // 3) & 1
+            t.clear()
+            seen_wrap |= t.c.epoch == 1
+            t.insert(packs[i])
+            if it % 97 == 0 or it > 1015:
+                assert t.checksum() == want[i], (mode, it, t.c.epoch)
+                assert t.n_keys() == t.count()[0]
+        assert seen_wrap and 1 <= t.c.epoch <= 1023
+
+
+def test_bad_epoch_is_rejected(eng):
+    import ctypes
+    from pangenome_b200 import _lib
+    t = eng.DbgTable(64, 5, _lib.PG_MODE_CANONICAL)
+    for bad in (0, 1024, -3):
+        c = _lib.PgTable(t.c.d_slots, t.c.capacity, t.c.d_stats, t.c.mode, t.c.k, bad, 0)
+        assert _lib.load().pg_table_count(ctypes.byref(c), None) != 0
+        assert b"epoch" in _lib.load().pg_last_error()
