@@ -176,6 +176,10 @@ int pg_peer_free(void *d_ptr);
 int pg_kmer_partition_dev(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                           const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
                           uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream);
+int pg_kmer_partition_p2p_dev(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                              const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
+                              uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
+                              pg_stream_t stream);
 int pg_count_short_dev(const pg_table *t, const int64_t *d_seq_off, const int64_t *d_counts, int64_t cap_records,
                        pg_stream_t stream);
 int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,

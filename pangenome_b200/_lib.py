@@ -47,6 +47,7 @@ SIGNATURES = {
     "pg_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "pg_peer_close": (c_int, [c_vp]),
     "pg_peer_free": (c_int, [c_vp]),
+    "pg_kmer_partition_p2p_dev": (c_int, [PT, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_int, c_i64, c_vp, c_vp]),
     "pg_kmer_partition_dev": (c_int, [PT, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
     "pg_count_short_dev": (c_int, [PT, c_vp, c_vp, c_i64, c_vp]),
     "pg_insert_records": (c_int, [PT, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),

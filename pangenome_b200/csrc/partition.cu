@@ -105,14 +105,16 @@ k2a_partition(PartArgs a) {
         s_pid[slot] = (uint16_t)pid;
         atomicAdd(&s_hist[pid], 1u);
     };
+    // staging slot of this thread's q-th position: consecutive lanes take consecutive slots, so the 16-byte
+    // record stores of a warp fall into distinct banks (a [thread][q] layout costs 8 wavefronts per store)
     auto emit_pos = [&](int q, uint64_t F, uint64_t R, uint32_t vf, uint32_t vr) {
-        const int slot = (threadIdx.x * KP_G + q) * RPP;
+        const int slot = q * KP_THREADS + threadIdx.x;
         if (MODE == PG_MODE_CANONICAL) {
             PgUpdate u = pg_canonical_update(F, R, vf, vr);
             emit(slot, u.key, u.masks, u.inc);
         } else {
             emit(slot, F, vf, 1u);
-            if (MODE == PG_MODE_LITERAL_RC) emit(slot + 1, R, vr, 1u);
+            if (MODE == PG_MODE_LITERAL_RC) emit(slot + KP_TILE, R, vr, 1u);
         }
     };
 
@@ -154,7 +156,7 @@ k2a_partition(PartArgs a) {
                         pg_occ_vals(w, j, g - rs, re - rs, k, vf, vr);
                         emit_pos(q, F, R, vf, vr);
                     } else {
-                        for (int e = 0; e < RPP; e++) s_pid[(threadIdx.x * KP_G + q) * RPP + e] = NOREC;
+                        for (int e = 0; e < RPP; e++) s_pid[e * KP_TILE + q * KP_THREADS + threadIdx.x] = NOREC;
                     }
                     pg_codes_roll(w, j, k, a.pow5km1, F, R);
                 }
@@ -162,7 +164,7 @@ k2a_partition(PartArgs a) {
             }
         }
         if (!done)
-            for (int e = 0; e < KP_G * RPP; e++) s_pid[threadIdx.x * KP_G * RPP + e] = NOREC;
+            for (int e = 0; e < KP_G * RPP; e++) s_pid[e * KP_THREADS + threadIdx.x] = NOREC;
         __syncthreads();
         // ---- 2. reserve space: one global atomicAdd per bucket per tile (all in flight at once, every
         // thread owns buckets tid, tid+128, ..) and local exclusive offsets by a block scan of the histogram
@@ -396,6 +398,18 @@ extern "C" int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, c
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p: bad peer table / rank");
     return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, owner_bits, sub_bits, nullptr, d_peer_bases, my_rank,
                             part_cap, d_part_counts, nullptr, 0, nullptr, nullptr, 0, 0, stream_);
+}
+
+// pg_kmer_partition_p2p with device-side bounds (see pg_kmer_partition_dev): the multi-GPU step without a host read-back
+extern "C" int pg_kmer_partition_p2p_dev(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                                         const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
+                                         uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
+                                         pg_stream_t stream_) {
+    if (!d_counts || cap_records < 0 || max_bases < 0) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p_dev: bad arguments");
+    if (!d_peer_bases || my_rank < 0 || my_rank >= (1 << owner_bits))
+        return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p_dev: bad peer table / rank");
+    return partition_launch(t, d_pk2, d_amb, d_seq_off, 1, 0, 1, owner_bits, sub_bits, nullptr, d_peer_bases, my_rank,
+                            part_cap, d_part_counts, nullptr, 0, nullptr, d_counts, cap_records, max_bases, stream_);
 }
 
 // ---- peer memory for the fused exchange (CUDA IPC; one process per GPU) ------------------------

@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import PgError, PgTable, check
 
-_DEFAULT_LOAD = 0.5
+_DEFAULT_LOAD = float(os.environ.get("PG_TABLE_LOAD", "0.5"))     # positions (upper bound of keys) per slot when sizing a table
 
 
 def _require_cuda():

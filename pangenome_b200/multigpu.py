@@ -172,7 +172,7 @@ class DistributedBuilder:
 
     def verify(self):
         if int(self.send_counts.max().item()) > self.part_cap:
-            raise _lib.PgError("record bucket overflow on rank %d" % self.rank)
+            raise _lib.PgError("record bucket overflow or truncated record index on rank %d" % self.rank)
         if self.table.overflowed():
             raise _lib.PgError("dBG table overflow on rank %d" % self.rank)
 
@@ -289,9 +289,52 @@ class PeerBuilder:
             ev.setdefault("k3", []).append((e[2], e[3]))
         return t
 
+    def build_async(self, packed, ev=None):
+        """build() over ALL records of ``packed`` without reading K1's record index back: K2a and the
+        short-record count take their bounds from the device (PackedSeqs(lazy=True)), so a step is
+        K1 -> K2a+exchange -> counts all-to-all -> K3 enqueued back to back.  verify() reports a
+        truncated record index or an overflow afterwards."""
+        eng, L, t = self.engine, self.L, self.table
+        W, n_sub = self.world, self.n_sub
+        st = torch.cuda.current_stream()
+        if not getattr(self, "_begun", False):
+            self.begin()
+        self._begun = False
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if ev is not None else None
+        if e:
+            e[0].record(st)
+        buf = self.parity
+        self.parity ^= 1
+        desc = _lib.PgTable(None, 2, None, _lib.PG_MODE_CANONICAL, self.k, 1, 0)
+        eng.check(L.pg_kmer_partition_p2p_dev(ctypes.byref(desc), eng._ptr(packed.pk2), eng._ptr(packed.amb),
+                                              eng._ptr(packed.d_seq_off), eng._ptr(packed.d_counts), packed.cap_records, packed.nbytes,
+                                              self.owner_bits, self.sub_bits, eng._ptr(self.peer_tables[buf]), self.rank,
+                                              self.part_cap, eng._ptr(self.send_counts), eng._stream()), "pg_kmer_partition_p2p_dev")
+        if e:
+            e[1].record(st)
+        if W > 1:
+            dist.all_to_all_single(self.recv_counts, self.send_counts)
+        else:
+            self.recv_counts.copy_(self.send_counts)
+        if e:
+            e[2].record(st)
+        st.wait_stream(self.side)
+        eng.check(L.pg_count_short_dev(ctypes.byref(t.c), eng._ptr(packed.d_seq_off), eng._ptr(packed.d_counts), packed.cap_records,
+                                       eng._stream()), "pg_count_short_dev")
+        self.seg_cnt.copy_(self.recv_counts.view(W, n_sub).t().reshape(-1))
+        eng.check(L.pg_insert_records(ctypes.byref(t.c), self.own[buf], eng._ptr(self.seg_off), eng._ptr(self.seg_cnt),
+                                      n_sub, W, self.part_cap, eng._stream()), "pg_insert_records")
+        if e:
+            e[3].record(st)
+            ev.setdefault("build", []).append((e[0], e[3]))
+            ev.setdefault("k2a_all_chunks", []).append((e[0], e[1]))
+            ev.setdefault("until_exchange_done", []).append((e[0], e[2]))
+            ev.setdefault("k3", []).append((e[2], e[3]))
+        return t
+
     def verify(self):
         if int(self.send_counts.max().item()) > self.part_cap:
-            raise _lib.PgError("record bucket overflow on rank %d" % self.rank)
+            raise _lib.PgError("record bucket overflow or truncated record index on rank %d" % self.rank)
         if self.table.overflowed():
             raise _lib.PgError("dBG table overflow on rank %d" % self.rank)
 
@@ -479,7 +522,9 @@ def bench(args, world, rank, local, ClockSampler=None):
 
     def step(record=False):
         if hasattr(builder, "begin"):
-            builder.begin()                 # table clear overlaps K1 and K2a
+            builder.begin()                 # empty the table (epoch bump)
+        if hasattr(builder, "build_async"):   # no host read-back inside a step: bounds stay on the device
+            return builder.build_async(engine.PackedSeqs(d_fasta, lazy=True), ev=kev if record else None)
         p = engine.PackedSeqs(d_fasta)
         return builder.build(p, n_rec, ev=kev if record else None)
 
@@ -534,8 +579,10 @@ def bench(args, world, rank, local, ClockSampler=None):
             if hasattr(builder, "begin"):
                 builder.begin()
             stream.wait_event(cur)
-            p = engine.PackedSeqs(dev_in[i % 2])
-            tt = builder.build(p, n_rec)
+            if hasattr(builder, "build_async"):
+                tt = builder.build_async(engine.PackedSeqs(dev_in[i % 2], lazy=True))
+            else:
+                tt = builder.build(engine.PackedSeqs(dev_in[i % 2]), n_rec)
             tt.stats_host()
     run_e2e(2)
     dist.barrier()
