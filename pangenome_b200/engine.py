@@ -144,6 +144,15 @@ class PackedSeqs:
         return int(np.maximum(lens - k + 1, 1).sum()) * (2 if rc else 1)
 
 
+class _StatsFuture:
+    def __init__(self, pinned, event):
+        self.pinned, self.event = pinned, event
+
+    def wait(self):
+        self.event.synchronize()
+        return self.pinned.numpy().copy()
+
+
 class DbgTable:
     """Device hash table behind the C-ABI ``pg_table`` struct (replaces oakht,
     kmer_numba.py:340-679).  ``mode``: 0 literal one strand, 1 literal both
@@ -185,6 +194,17 @@ class DbgTable:
 
     def stats_host(self):
         return self.stats.cpu().numpy()
+
+    def stats_async(self, slot=0):
+        """Enqueue the D2H copy of the statistics words into pinned host memory (two slots, so a loop can
+        read step i-1's result while step i runs) and return a handle whose ``wait()`` yields them."""
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = torch.empty((2, _lib.PG_STAT_WORDS), dtype=torch.int64).pin_memory()
+        dst = self._pinned[slot & 1]
+        dst.copy_(self.stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return _StatsFuture(dst, ev)
 
     def n_keys(self):
         """Occupied slots as counted by the inserts themselves (one atomicAdd per warp on claim):

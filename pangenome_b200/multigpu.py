@@ -563,15 +563,21 @@ def bench(args, world, rank, local, ClockSampler=None):
     copy_stream = torch.cuda.Stream()
     dev_in = [torch.empty_like(d_fasta) for _ in range(2)]
 
+    k1_done = [None, None]
+
     def upload(i):
         with torch.cuda.stream(copy_stream):
+            if k1_done[i % 2] is not None:
+                copy_stream.wait_event(k1_done[i % 2])       # K1 of the step that last read this buffer
             dev_in[i % 2].copy_(host, non_blocking=True)
             done = torch.cuda.Event()
             done.record(copy_stream)
         return done
 
     def run_e2e(n):
+        # as in bench.py: input i+1 uploads and result i-1 (table statistics) is read while step i runs
         nxt = upload(0)
+        pending = None
         for i in range(n):
             cur = nxt
             if i + 1 < n:
@@ -580,10 +586,20 @@ def bench(args, world, rank, local, ClockSampler=None):
                 builder.begin()
             stream.wait_event(cur)
             if hasattr(builder, "build_async"):
-                tt = builder.build_async(engine.PackedSeqs(dev_in[i % 2], lazy=True))
+                p = engine.PackedSeqs(dev_in[i % 2], lazy=True)
+                k1_done[i % 2] = torch.cuda.Event()
+                k1_done[i % 2].record(stream)
+                tt = builder.build_async(p)
             else:
-                tt = builder.build(engine.PackedSeqs(dev_in[i % 2]), n_rec)
-            tt.stats_host()
+                p = engine.PackedSeqs(dev_in[i % 2])
+                k1_done[i % 2] = torch.cuda.Event()
+                k1_done[i % 2].record(stream)
+                tt = builder.build(p, n_rec)
+            fut = tt.stats_async(i)
+            if pending is not None:
+                pending.wait()
+            pending = fut
+        pending.wait()
     run_e2e(2)
     dist.barrier()
     torch.cuda.synchronize()
@@ -616,7 +632,7 @@ def bench(args, world, rank, local, ClockSampler=None):
                        "table_slots_per_gpu": builder.table.capacity, "distinct_canonical_keys": int(ent.item()),
                        "l2": "every step clears and updates a table larger than L2 on every rank"},
             "e2e": {"value": n_ins / (e2e_ms * 1e-3) / 1e9, "unit": "G k-mers/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(host.numel()) * world, "d2h_bytes_per_step": (8 * 8 + 4 * 8 + 16 * (n_rec + 1)) * world},
+                    "h2d_bytes_per_step": int(host.numel()) * world, "d2h_bytes_per_step": 8 * _lib.PG_STAT_WORDS * world},
             "gpu_launches": (3 + builder.launches_per_build) * args.steps * world,
             "clocks": clk,
             "exchange": "fused into K2a: peer stores over NVLink (CUDA IPC)" if mode == "p2p" else "NCCL all_to_all_single, %d chunks" % builder.chunks,
