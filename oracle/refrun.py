@@ -132,3 +132,30 @@ def run(fasta_bytes, k, c=2, Ns=2 ** 63, stages="all", timings=None):
         return out
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_chunked(fasta_bytes, k, c=2, Ns=2 ** 63, chunk=2 ** 33, brkpt_bytes=None):
+    """Stage 1 only, with the reference's chunk checkpoints (kmer_numba.py:1252-1266): returns
+    dict(dbg=(keys,vals,cnts), brkpt=bytes|None, offset=int|None) where ``brkpt`` is the last
+    ``<qry>_db_brkpt.npz`` the run left behind.  ``brkpt_bytes``: resume from that image (``-r``)."""
+    import numpy as np
+    mod = load()
+    tmp = tempfile.mkdtemp(prefix="pgref_")
+    try:
+        qry = os.path.join(tmp, "in.fa")
+        with open(qry, "wb") as f:
+            f.write(fasta_bytes)
+        brk = ''
+        if brkpt_bytes is not None:
+            brk = os.path.join(tmp, "resume.npz")
+            with open(brk, "wb") as f:
+                f.write(brkpt_bytes)
+        kd = mod.seq2rdbg(qry, k, 5, Ns, brkpt=brk, chunk=chunk, rc=((c >> 1) == 1))
+        out = {"dbg": table_triples(kd), "brkpt": None, "offset": None}
+        ck = qry + "_db_brkpt.npz"
+        if os.path.isfile(ck):
+            out["brkpt"] = open(ck, "rb").read()
+            out["offset"] = int(np.load(ck)["parameters"][5])
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)

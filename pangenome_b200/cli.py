@@ -63,15 +63,18 @@ def _eval_n(text):
     return int(ev(ast.parse(text, mode="eval").body))
 
 
+CHUNK = 2 ** 33      # bases (both strands counted) between dBG checkpoints, kmer_numba.py entry_point
+
+
 def entry_point(argv, out=sys.stdout):
     args, extra, flags = parse_args(argv)
     qry, kmer, Ns, rc = args['-i'], int(args['-k']), _eval_n(args['-n']), int(args['-c'])
     if not qry:
         manual_print(out)
         raise SystemExit()
-    if args['-r'] or args['-R']:
-        raise SystemExit("pangenome_b200: -r/-R (chunk breakpoints of the CPU reference) are not supported by the "
-                         "GPU path; run without them")
+    if args['-R']:
+        raise SystemExit("pangenome_b200: -R (resuming the edge-weight stage from a _rdb_brkpt.npz) is not supported by the "
+                         "GPU path; -r (dBG checkpoint) is")
     from . import stages
     p = lambda *a: print(*a, file=out)
     dbs, rdb = args['-d'], args['-D']
@@ -91,7 +94,7 @@ def entry_point(argv, out=sys.stdout):
     p('# build the dBG')
     st = time()
     rc0 = ((rc >> 1) == 1)
-    kmer_dict = stages.seq2rdbg(qry, kmer, 5, Ns, rc=rc0)
+    kmer_dict = stages.seq2rdbg(qry, kmer, 5, Ns, brkpt=args['-r'], chunk=CHUNK, rc=rc0)    # :2111
     p('# finished in', time() - st, 'seconds')
     # the reference always dumps the table to <qry>_db.npz and reloads it here (:2116-2126); the result does
     # not depend on it, so the GPU table stays resident and the file is only written on request

@@ -183,14 +183,16 @@ class DbgTable:
         self.capacity = capacity
         self.c.capacity = capacity
 
-    def insert(self, packed, n_rec=None, g_begin=None, g_end=None):
+    def insert(self, packed, n_rec=None, g_begin=None, g_end=None, rec_begin=0):
+        """Insert records [rec_begin, n_rec) (fused K2+K3).  With ``rec_begin`` the kernel is handed the record
+        index from that record on, so zero-length records at the boundary belong to exactly one call."""
         n_rec = packed.n_rec if n_rec is None else n_rec
-        if n_rec == 0:
+        if n_rec - rec_begin <= 0:
             return
-        g_begin = int(packed.seq_off[0]) if g_begin is None else g_begin
+        g_begin = int(packed.seq_off[rec_begin]) if g_begin is None else g_begin
         g_end = int(packed.seq_off[n_rec]) if g_end is None else g_end
-        check(self.L.pg_kmer_insert(ctypes.byref(self.c), _ptr(packed.pk2), _ptr(packed.amb), _ptr(packed.d_seq_off),
-                                    n_rec, g_begin, g_end, _stream()), "pg_kmer_insert")
+        check(self.L.pg_kmer_insert(ctypes.byref(self.c), _ptr(packed.pk2), _ptr(packed.amb), ctypes.c_void_p(packed.d_seq_off.data_ptr() + 8 * rec_begin),
+                                    n_rec - rec_begin, g_begin, g_end, _stream()), "pg_kmer_insert")
 
     def stats_host(self):
         return self.stats.cpu().numpy()

@@ -36,7 +36,12 @@ def seq_chk(qry):
 
 def seq2rdbg(qry, kmer=13, bits=5, Ns=1e6, chunk=2 ** 32, brkpt="./breakpoint", saved="dBG_disk", hashfunc=None,
              jit=True, rc=True, data=None):
-    """Stage 1: build the dBG (both strands when ``rc``)."""
+    """Stage 1: build the dBG (both strands when ``rc``).
+
+    Chunk checkpoints as upstream (:1252-1266): whenever a call has consumed more than ``chunk`` bases
+    (both strands counted) the table is written to ``<qry>_db_brkpt.npz`` together with the byte offset
+    of the next header line; an existing ``brkpt`` file (``-r``) is loaded and the build resumes at its
+    offset.  Inputs below ``chunk`` with no ``brkpt`` file take the one-shot two-phase build."""
     if bits != 5:
         raise ValueError("only the reference's base-5 code (bits=5) is supported")
     kmer = min(max(1, int(kmer)), 27)
@@ -46,8 +51,95 @@ def seq2rdbg(qry, kmer=13, bits=5, Ns=1e6, chunk=2 ** 32, brkpt="./breakpoint", 
         data = _read(qry)
     raw = data.tobytes() if isinstance(data, np.ndarray) else bytes(data)
     packed = engine.PackedSeqs(engine.to_device_bytes(data))
-    table, n_rec = engine.build_dbg(packed, kmer, rc=bool(rc), Ns=Ns)
-    return DbgHandle(table, packed, raw, n_rec)
+    strands = 2 if rc else 1
+    resume = bool(brkpt) and os.path.isfile(brkpt)
+    if not resume and strands * int(packed.n_bases) <= chunk:
+        table, n_rec = engine.build_dbg(packed, kmer, rc=bool(rc), Ns=Ns)
+        return DbgHandle(table, packed, raw, n_rec)
+    table = _build_chunked(qry, raw, packed, kmer, Ns, chunk, brkpt if resume else None, bool(rc))
+    return DbgHandle(table, packed, raw, packed.n_rec)
+
+
+def plan_chunks(lens, chunk, Ns):
+    """The record ranges the ``while 1`` loop of seq2rdbg (:1252-1266) hands to seq2dbg_jit_ (:1202-1230):
+    yields (first record, end record, checkpoint written afterwards?, tail?).  ``lens`` = bases per record
+    with both strands counted when rc.  ``tail`` marks the extra call upstream makes after a checkpoint that
+    fell on the last record: it parses again from the file's last line and finds no sequence.  Inside a call N and chk restart at 0 and the chunk test comes before
+    the -n test (:1224-1228); after a checkpoint the call's N joins a running total that ends the loop
+    once it exceeds Ns (:1263-1265)."""
+    n_rec, r, total = len(lens), 0, 0
+    while True:
+        N = chk = 0
+        r0, done = r, 1
+        while r < n_rec:
+            N += int(lens[r])
+            chk += int(lens[r])
+            r += 1
+            if chk > chunk:
+                done = -1
+                break
+            if N > Ns:
+                break
+        yield r0, r, done == -1, False
+        if done != -1:
+            return
+        total += N
+        if total > Ns:
+            return
+        if r >= n_rec:
+            yield r, r, False, True
+            return
+
+
+def _last_line_start(raw):
+    """Byte offset of the last line readline_jit_ (:122-132) yields."""
+    end = len(raw) - 1 if raw.endswith(b"\n") else len(raw)
+    return raw.rfind(b"\n", 0, max(end, 0)) + 1
+
+
+def _build_chunked(qry, raw, packed, kmer, Ns, chunk, brkpt, rc):
+    """The ``while 1`` loop of seq2rdbg (:1252-1266) around seq2dbg_jit_ (:1202-1230)."""
+    from . import npz
+    strands = 2 if rc else 1
+    mode = _lib.PG_MODE_LITERAL_RC if rc else _lib.PG_MODE_LITERAL      # checkpoint images hold literal keys
+    p, shift = packed, 0               # records still to insert, and what to add to their header offsets
+    if brkpt is None:
+        table = engine.DbgTable(int(strands * packed.n_positions(kmer) / 0.5) + 1024, kmer, mode, device=packed.pk2.device)
+    else:
+        offset = int(np.load(brkpt)["parameters"][5])
+        # readline_jit_ with an offset: the first "line" runs from byte 0 to the first newline at or after
+        # ``offset``; starting with '>' it is taken for a header, so the record resumes right after it
+        nl = raw.find(b"\n", offset)
+        rest = raw[nl + 1:] if nl >= 0 else None
+        if rest is None:
+            p = None
+        else:
+            pre = b">\n" if raw[:1] == b">" else b""       # a file not starting with '>': those lines belong to no record
+            p = engine.PackedSeqs(engine.to_device_bytes(pre + rest))
+            shift = nl + 1 - len(pre)
+        n_more = strands * p.n_positions(kmer) if p is not None else 0
+        _, table = npz.load(brkpt, kmer, device=packed.pk2.device, mode=mode, with_offset=True,
+                            min_capacity=int((n_more + 2 * int(np.load(brkpt)["parameters"][2])) / 0.5) + 1024)
+    if p is None or p.n_rec == 0:
+        return table
+    hdr_off, n_rec = p.hdr_off, p.n_rec
+    for r0, r, checkpoint, tail in plan_chunks(p.seq_lengths.astype(np.int64) * strands, chunk, Ns):
+        if tail:
+            # upstream re-parses from the last line: with a newline at or after it the whole file becomes a header
+            # and an EMPTY record follows (one short-record sentinel hit per strand); without one nothing does
+            ptr = _last_line_start(raw)
+            if raw.find(b"\n", ptr) >= 0 and raw[:1] == b">":
+                table.stats[_lib.PG_STAT_SHORT] += strands
+            break
+        if r > r0:
+            table.insert(p, n_rec=r, rec_begin=r0)
+            if table.overflowed():
+                raise _lib.PgError("dBG table overflow in the chunked build")
+        if not checkpoint:
+            break
+        ptr = int(hdr_off[r]) + shift if r < n_rec else _last_line_start(raw)
+        npz.dump(table, qry + "_db_brkpt", offset=ptr)
+    return table
 
 
 def dump(kmer_dict, fn):

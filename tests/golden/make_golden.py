@@ -205,13 +205,81 @@ def main_big():
     print(json.dumps({k: v for k, v in facts.items() if "sha" not in k}))
 
 
+def main_chunk():
+    """Chunk checkpoints of the dBG stage (kmer_numba.py:1252-1266): the reference's
+    ``seq2rdbg`` with a small ``chunk``.  Stored per case: the final dBG, the offset and the live
+    entries of the last ``<qry>_db_brkpt.npz`` it left behind, and that file itself (base64) so the
+    GPU path can resume from the reference's own image."""
+    import base64
+    import io
+    rng = np.random.default_rng(20260)
+    cases = []
+    tiny = (b">a\nACGTTGCAAGGCTTAACCGGATAGGCTTACGATCGGA\nGGCTTAACCAGT\n>b\nTTGACGGTCATTGACCAGTA\n>c\nAC\n"
+            b">d\nGGGATTTACCCAGATTTAGGACCA\n")
+    # (a file without a final newline is left out: when the checkpoint falls on its last record the reference
+    # re-parses from the last line, finds no newline at all and segfaults)
+    inputs = [("tiny", tiny, 5),
+              ("nasty_k7", no_ub(lambda r: fasta(r, width=30), nasty(7), 7), 7),
+              ("nasty_crlf_k11", no_ub(lambda r: fasta(r, width=25, crlf=True), nasty(11), 11), 11)]
+    for i in range(4):
+        k = int(rng.choice([5, 9, 15, 27]))
+        import oracle
+        for _ in range(20):       # needs a final newline (see above) and still no record of length k+1 (Q2)
+            data = rand_case(rng, k)
+            if not data.endswith(b"\n"):
+                data += b"\n"
+            if (k + 1) not in np.diff(oracle.run(data, k, stages=1)["seq_off"]).tolist():
+                break
+        else:
+            raise RuntimeError("no usable random case")
+        inputs.append(("rand%d_k%d" % (i, k), data, k))
+    # every -n 2**63 case first: numba dispatches the python int 2**63 onto an int64 signature compiled for a
+    # small -n and raises OverflowError (same reason main_small/main_big are separate processes)
+    todo = []
+    for name, data, k in inputs:
+        total = 2 * sum(len(x) for x in data.split(b"\n") if not x.startswith(b">"))
+        for c in (2, 0):
+            for chunk in sorted({10, max(20, total // 5), max(30, total // 2), total + 1000}):
+                for Ns in ((2 ** 63, 150) if (name.startswith("tiny") and chunk < 100) else (2 ** 63,)):
+                    todo.append((Ns != 2 ** 63, len(todo), name, data, k, c, chunk, Ns))
+    for _, _, name, data, k, c, chunk, Ns in sorted(todo):
+        if True:
+            if True:
+                if True:
+                    r = refrun.run_chunked(data, k, c=c, Ns=Ns, chunk=chunk)
+                    case = {"name": "%s_c%d_chunk%d%s" % (name, c, chunk, "" if Ns == 2 ** 63 else "_n%d" % Ns),
+                            "input_latin1": data.decode("latin-1"), "k": k, "c": c, "chunk": chunk, "Ns": Ns,
+                            "dbg": [[int(a), int(b), int(d)] for a, b, d in zip(*[x.tolist() for x in r["dbg"]])],
+                            "offset": r["offset"], "brkpt_b64": None, "brkpt_live": None}
+                    if r["brkpt"] is not None:
+                        z = np.load(io.BytesIO(r["brkpt"]))
+                        live = z["counts"] > 0
+                        o = np.argsort(z["keys"][live], kind="stable")
+                        case["brkpt_live"] = [[int(a), int(b), int(d)] for a, b, d in
+                                              zip(z["keys"][live][o].tolist(), z["values"][live][o].tolist(), z["counts"][live][o].tolist())]
+                        case["brkpt_b64"] = base64.b64encode(r["brkpt"]).decode()
+                        # what ``-r <that file>`` gives (same -n, the CLI's chunk); without a -n cap it must be
+                        # the final table again
+                        rr = refrun.run_chunked(data, k, c=c, Ns=Ns, brkpt_bytes=r["brkpt"])
+                        case["resume_dbg"] = [[int(a), int(b), int(d)] for a, b, d in zip(*[x.tolist() for x in rr["dbg"]])]
+                        if Ns == 2 ** 63:
+                            assert case["resume_dbg"] == case["dbg"], case["name"]
+                    cases.append(case)
+                    print(case["name"], len(case["dbg"]), case["offset"], flush=True)
+    with open(os.path.join(HERE, "chunk_cases.json"), "w") as f:
+        json.dump(cases, f)
+    print("wrote", len(cases), "chunk cases")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which == "all":
         import subprocess
-        for w in ("small", "big"):
+        for w in ("small", "big", "chunk"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), w])
     elif which == "small":
         main_small()
+    elif which == "chunk":
+        main_chunk()
     else:
         main_big()
