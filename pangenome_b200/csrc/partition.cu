@@ -8,7 +8,7 @@
 // owner rank).  K3 then walks the buckets in order, so at any moment the CTAs of the grid hammer one
 // table region that fits the 126 MB L2: atomicCAS / red.or / red.add resolve in L2 and every table
 // line is written back to HBM once.  The bucketed records are also exactly what the multi-GPU path
-// exchanges with an all-to-all (owner = top hash bits, disjoint from the slot bits).
+// exchanges (owner = low hash bits, disjoint from the slot bits, which are the top ones).
 //
 // Record emission inside a CTA tile is a counting sort in shared memory (histogram, one global
 // atomicAdd per bucket per tile to reserve space, reorder through an index permutation) so global
@@ -20,9 +20,9 @@
 namespace {
 
 constexpr int KP_G = 16;                               // positions per thread
-// CTA tile = THREADS x 16 positions: 128 threads (2048 positions, 40 KB of smem, 5 CTAs/SM) for the
-// single-GPU path; 512 threads (8192 positions, one CTA per SM) when buckets are peer memory - four
-// times the run length per bucket on NVLink (8 GPUs: 254 -> 268 G k-mers/s over 256-thread tiles)
+// CTA tile = THREADS x 16 positions: 256 threads (4096 positions, 88 KB of smem, 2 CTAs/SM) for the
+// single-GPU path; 512 threads (8192 positions, one CTA per SM) when buckets are peer memory - twice
+// the run length per bucket on NVLink (2 GPUs: K2a + exchange 0.85 ms against 0.92 ms with 256 threads)
 constexpr int KP_MAX_PARTS = 1024;
 
 struct PartArgs {
@@ -249,8 +249,8 @@ k2a_partition(PartArgs a) {
 // segments (one per source rank / pipeline chunk): seg_off/seg_cnt are [n_regions][n_src] in
 // region-major order and the threads of the whole grid stride over the CONCATENATION of a region's
 // segments, so a region is swept once with every thread busy while its 8 MB of slots sit in L2.
-// The record of the next iteration is loaded before the current one is processed (the record
-// stream comes from HBM, the slots from L2: the two latencies overlap instead of adding up).
+// (Loading the next record before the current one is merged, or pipelining record / slot / CAS three deep,
+// measured no faster: the kernel waits on random DRAM sectors, not on its own dependency chain.)
 constexpr int K3_MAX_SRC = 64;
 // record i of region b's concatenated segments (false past the end).  No shared memory and no
 // barriers: every warp walks the regions at its own pace, the segment table is read through L1.
@@ -265,7 +265,7 @@ __device__ __forceinline__ bool k3_fetch(const uint4 *__restrict__ records, cons
     }
     return false;
 }
-template <bool PREFETCH, int MINB, bool ROTATE>
+template <int MINB, bool ROTATE>
 __global__ void __launch_bounds__(256, MINB)
 k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
                   const int64_t *__restrict__ seg_cnt, int n_regions, int n_src, int64_t seg_cap) {
@@ -273,31 +273,16 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
     const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t rot = ROTATE ? (int64_t)((gridDim.x * 618u) / 1000u) * blockDim.x : 0;
     uint32_t n_claimed = 0;
-    if (PREFETCH) {
+    // A region holds a non-integral number of grid strides of records, so the threads with the lowest
+    // start index do one more record than the rest.  The start index is rotated from region to region
+    // (whole CTAs, golden-ratio steps) so that the extra record falls on different threads each time
+    // and every thread ends up with the same total instead of the low ones carrying all the excess.
+    int64_t start = i0;
+    for (int b = 0; b < n_regions; b++) {
         uint4 r;
-        bool have = k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, 0, i0, r);
-        for (int b = 0; b < n_regions; b++) {
-            int64_t i = i0;
-            while (have) {
-                const uint4 cur = r;
-                i += stride;
-                have = k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b, i, r);
-                table_upsert(t, (uint64_t)cur.x | ((uint64_t)cur.y << 32), cur.z, cur.w, n_claimed);
-            }
-            if (b + 1 < n_regions) have = k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b + 1, i0, r);
-        }
-    } else {
-        // A region holds a non-integral number of grid strides of records, so the threads with the lowest
-        // start index do one more record than the rest.  The start index is rotated from region to region
-        // (whole CTAs, golden-ratio steps) so that the extra record falls on different threads each time
-        // and every thread ends up with the same total instead of the low ones carrying all the excess.
-        int64_t start = i0;
-        for (int b = 0; b < n_regions; b++) {
-            uint4 r;
-            for (int64_t i = start; k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b, i, r); i += stride)
-                table_upsert(t, (uint64_t)r.x | ((uint64_t)r.y << 32), r.z, r.w, n_claimed);
-            start += rot; if (start >= stride) start -= stride;
-        }
+        for (int64_t i = start; k3_fetch(records, seg_off, seg_cnt, n_src, seg_cap, b, i, r); i += stride)
+            table_upsert(t, (uint64_t)r.x | ((uint64_t)r.y << 32), r.z, r.w, n_claimed);
+        start += rot; if (start >= stride) start -= stride;
     }
     publish_claims(t, n_claimed);
 }
@@ -442,10 +427,9 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
     if (seg_cap <= 0) seg_cap = INT64_MAX;
     if (reinterpret_cast<uintptr_t>(d_records) & 15) return pg_fail(PG_ERR_INVALID, "pg_insert_records: records must be 16-byte aligned");
     TableView tv = make_view(t);
-    static int gmul = -1, prefetch = -1, rotate = 1;
+    static int gmul = -1, rotate = 1;
     if (gmul < 0) {
         const char *e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 5;
-        e = getenv("PG_K3_PREFETCH"); prefetch = e ? atoi(e) : 0;
         e = getenv("PG_K3_ROTATE"); rotate = e ? atoi(e) : 1;
     }
     // the grid is exactly the resident CTAs (a region sweep must not leave a second wave behind): 8 per SM caps the
@@ -453,10 +437,9 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
     int grid = pg_num_sms() * gmul;
     const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
     cudaStream_t st = (cudaStream_t)stream_;
-#define K3_LAUNCH(P, M, R) k3_insert_records<P, M, R><<<grid, 256, 0, st>>>(tv, recs, d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap)
-    if (prefetch) K3_LAUNCH(true, 8, false);
-    else if (gmul >= 7) { if (rotate) K3_LAUNCH(false, 8, true); else K3_LAUNCH(false, 8, false); }
-    else { if (rotate) K3_LAUNCH(false, 6, true); else K3_LAUNCH(false, 6, false); }
+#define K3_LAUNCH(M, R) k3_insert_records<M, R><<<grid, 256, 0, st>>>(tv, recs, d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap)
+    if (gmul >= 7) { if (rotate) K3_LAUNCH(8, true); else K3_LAUNCH(8, false); }
+    else { if (rotate) K3_LAUNCH(6, true); else K3_LAUNCH(6, false); }
 #undef K3_LAUNCH
     PG_CUDA(cudaGetLastError());
     return PG_OK;

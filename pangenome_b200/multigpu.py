@@ -109,17 +109,14 @@ class DistributedBuilder:
         self.seg_off = (((c_i * world + s_i) * n_sub + b_i) * pc).reshape(-1).contiguous()
         self.seg_cnt = torch.zeros(n_sub * C * world, dtype=torch.int64, device=device)
         self.comm = torch.cuda.Stream(device=device)
-        self.side = torch.cuda.Stream(device=device)
-        self.launches_per_build = 3 + self.chunks      # clear, count_short, chunks x K2a, K3
+        self.launches_per_build = 2 + self.chunks      # count_short, chunks x K2a, K3 (the table reset is a 64-byte memset)
 
     def build(self, packed, n_rec, ev=None):
         eng, L, t = self.engine, self.L, self.table
         C, W, n_sub = self.chunks, self.world, self.n_sub
         st = torch.cuda.current_stream()
-        self.side.wait_stream(st)
         self.comm.wait_stream(st)
-        with torch.cuda.stream(self.side):
-            t.clear()
+        t.clear()                            # epoch bump: nothing to overlap
         e = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if ev is not None else None
         if e:
             e[0].record(st)
@@ -152,7 +149,6 @@ class DistributedBuilder:
             e_part = torch.cuda.Event(enable_timing=True); e_part.record(st)
             e_comm = torch.cuda.Event(enable_timing=True); e_comm.record(self.comm)
         st.wait_stream(self.comm)
-        st.wait_stream(self.side)            # K3 needs the cleared table
         if e:
             e_k3 = torch.cuda.Event(enable_timing=True); e_k3.record(st)
         if n_rec > 0:
@@ -232,19 +228,15 @@ class PeerBuilder:
         b_i = torch.arange(n_sub, dtype=torch.int64, device=device).view(n_sub, 1)
         self.seg_off = ((s_i * n_sub + b_i) * pc).reshape(-1).contiguous()        # region-major over sources
         self.seg_cnt = torch.zeros(n_sub * world, dtype=torch.int64, device=device)
-        self.side = torch.cuda.Stream(device=device)
         self.parity = 0
         self.chunks = 1
-        self.launches_per_build = 4          # clear, count_short, k2a (fused exchange), k3
+        self.launches_per_build = 3          # count_short, k2a (fused exchange), k3 (the table reset is a 64-byte memset)
         if world > 1:
             dist.barrier()
 
     def begin(self):
-        """Start clearing the table on the side stream (call before K1 / the H2D copy)."""
-        st = torch.cuda.current_stream()
-        self.side.wait_stream(st)
-        with torch.cuda.stream(self.side):
-            self.table.clear()
+        """Empty the table for the next build (epoch bump, DbgTable.clear)."""
+        self.table.clear()
         self._begun = True
 
     def build(self, packed, n_rec, ev=None):
@@ -274,7 +266,6 @@ class PeerBuilder:
             self.recv_counts.copy_(self.send_counts)
         if e:
             e[2].record(st)
-        st.wait_stream(self.side)
         if n_rec > 0:
             eng.check(L.pg_count_short(ctypes.byref(t.c), eng._ptr(packed.d_seq_off), n_rec, g_begin, g_end, eng._stream()),
                       "pg_count_short")
@@ -318,7 +309,6 @@ class PeerBuilder:
             self.recv_counts.copy_(self.send_counts)
         if e:
             e[2].record(st)
-        st.wait_stream(self.side)
         eng.check(L.pg_count_short_dev(ctypes.byref(t.c), eng._ptr(packed.d_seq_off), eng._ptr(packed.d_counts), packed.cap_records,
                                        eng._stream()), "pg_count_short_dev")
         self.seg_cnt.copy_(self.recv_counts.view(W, n_sub).t().reshape(-1))
