@@ -114,10 +114,13 @@ struct PgUpdate { uint64_t key; uint32_t masks; uint32_t inc; };
 // orientation 0 being the one whose literal code equals the slot key.  Palindromes (F == R, only
 // possible with ambiguity digits or even k) fold both strands into orientation 0 and count twice.
 PG_HD PgUpdate pg_canonical_update(uint64_t F, uint64_t R, uint32_t vf, uint32_t vr) {
+    // selects, not branches: the three cases are spread at random over the lanes of a warp
     PgUpdate u;
-    if (F < R) { u.key = F; u.masks = vf | (vr << 16); u.inc = 1; }
-    else if (R < F) { u.key = R; u.masks = vr | (vf << 16); u.inc = 1; }
-    else { u.key = F; u.masks = vf | vr; u.inc = 2; }
+    const bool lt = F < R, eq = F == R;
+    const uint32_t v0 = lt ? vf : vr, v1 = lt ? vr : vf;       // orientation 0 = the strand whose code is the key
+    u.key = lt ? F : R;
+    u.masks = eq ? (vf | vr) : (v0 | (v1 << 16));
+    u.inc = eq ? 2u : 1u;
     return u;
 }
 

@@ -57,15 +57,18 @@ __device__ __forceinline__ void sample_key(const PartArgs &a, uint64_t key, uint
     atomicAdd(a.sample_count, 1ull << 40);     // set full: poison the estimate so the host falls back to the upper bound
 }
 
+// GENERAL = key-space sampling and/or an owner rank in the bucket id; the plain single-GPU build needs neither
+template <bool GENERAL>
 __device__ __forceinline__ uint32_t part_of(const PartArgs &a, uint64_t key) {
     uint64_t h = pg_mix64(key);
-    if (a.sample_keys && ((h >> 8) & 0xFFu) == 0) sample_key(a, key, h);
     uint32_t sub = a.sub_bits ? (uint32_t)(h >> (64 - a.sub_bits)) : 0u;      // hash prefix = table region (tv_home)
+    if (!GENERAL) return sub;
+    if (a.sample_keys && ((h >> 8) & 0xFFu) == 0) sample_key(a, key, h);
     uint32_t owner = a.owner_bits ? (uint32_t)(h & ((1u << a.owner_bits) - 1u)) : 0u;   // low bits: disjoint from the slot bits
     return (owner << a.sub_bits) | sub;
 }
 
-template <int MODE, int KP_THREADS>
+template <int MODE, int KP_THREADS, bool GENERAL>
 __global__ void __launch_bounds__(KP_THREADS)
 k2a_partition(PartArgs a) {
     constexpr int KP_TILE = KP_THREADS * KP_G;
@@ -100,7 +103,7 @@ k2a_partition(PartArgs a) {
     const uint64_t pol = pg_policy_evict_first();
 
     auto emit = [&](int slot, uint64_t key, uint32_t masks, uint32_t inc) {
-        uint32_t pid = part_of(a, key);
+        uint32_t pid = part_of<GENERAL>(a, key);
         s_rec[slot] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), masks, inc);
         s_pid[slot] = (uint16_t)pid;
         atomicAdd(&s_hist[pid], 1u);
@@ -334,10 +337,16 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
     int per_sm = 227 * 1024 / (smem + 1024);      // 227 KB usable per SM, 1 KB reserved per CTA if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
     int64_t maxg = (int64_t)pg_num_sms() * per_sm;
     int grid = (int)(a.n_tiles < maxg ? a.n_tiles : maxg);
-#define K2A_LAUNCH(M, T)                                                                                            \
-    do {                                                                                                            \
-        PG_CUDA(cudaFuncSetAttribute(k2a_partition<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-        k2a_partition<M, T><<<grid, T, smem, st>>>(a);                                                              \
+    const bool general = a.sample_keys != nullptr || owner_bits > 0;
+#define K2A_LAUNCH(M, T)                                                                                                    \
+    do {                                                                                                                    \
+        if (general) {                                                                                                      \
+            PG_CUDA(cudaFuncSetAttribute(k2a_partition<M, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
+            k2a_partition<M, T, true><<<grid, T, smem, st>>>(a);                                                            \
+        } else {                                                                                                            \
+            PG_CUDA(cudaFuncSetAttribute(k2a_partition<M, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
+            k2a_partition<M, T, false><<<grid, T, smem, st>>>(a);                                                           \
+        }                                                                                                                   \
     } while (0)
     if (threads == 128) {
         if (t->mode == PG_MODE_LITERAL) K2A_LAUNCH(PG_MODE_LITERAL, 128);
