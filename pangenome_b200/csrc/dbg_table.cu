@@ -25,6 +25,8 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
                uint64_t pow5km1, int64_t w_first, int64_t n_tiles) {
     __shared__ __align__(16) uint64_t s_pk[K2_TILE_WORDS + 4];
     __shared__ __align__(16) uint32_t s_am[K2_TILE_WORDS + 8];
+    __shared__ uint32_t s_vlut[16];
+    if (threadIdx.x < 16) s_vlut[threadIdx.x] = pg_vlut_entry(threadIdx.x);      // visible after the tile loop's first barrier
     uint32_t n_claimed = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t w0 = w_first + tile * K2_TILE_WORDS;
@@ -38,17 +40,17 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
         w.aprv = s_am[threadIdx.x + 3]; w.acur = s_am[threadIdx.x + 4]; w.anxt = s_am[threadIdx.x + 5];
         int64_t r = find_record(seq_off, n_rec, g0);
         int64_t rs = r >= 0 ? __ldg(seq_off + r) : 0, re = __ldg(seq_off + r + 1);
-        auto upsert_pos = [&](int, uint64_t F, uint64_t R, uint32_t vf, uint32_t vr) {
+        auto upsert_pos = [&](int, uint64_t F, uint64_t R, uint32_t vw) {      // vw = vf | vr << 16
             if (MODE == PG_MODE_CANONICAL) {
-                PgUpdate u = pg_canonical_update(F, R, vf, vr);
+                PgUpdate u = pg_canonical_update_w(F, R, vw);
                 table_upsert(t, u.key, u.masks, u.inc, n_claimed);
             } else {
-                table_upsert(t, F, vf, 1, n_claimed);
-                if (MODE == PG_MODE_LITERAL_RC) table_upsert(t, R, vr, 1, n_claimed);
+                table_upsert(t, F, vw & 0xFFFFu, 1, n_claimed);
+                if (MODE == PG_MODE_LITERAL_RC) table_upsert(t, R, vw >> 16, 1, n_claimed);
             }
         };
         if (pg_is_interior(w, g0, 32, k, rs, re, r >= 0, g_begin, g_end)) {
-            pg_interior_visit<32>(w, 0, k, pow5km1, upsert_pos);      // fast path: no record edge, no ambiguity
+            pg_interior_visit<32>(w, 0, k, pow5km1, s_vlut, upsert_pos);      // fast path: no record edge, no ambiguity
             continue;
         }
         uint64_t F, R;
@@ -61,7 +63,7 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
             if (g >= g_begin && r >= 0 && g + k <= re) {
                 uint32_t vf, vr;
                 pg_occ_vals(w, j, g - rs, re - rs, k, vf, vr);
-                upsert_pos(j, F, R, vf, vr);
+                upsert_pos(j, F, R, vf | (vr << 16));
             }
             pg_codes_roll(w, j, k, pow5km1, F, R);
         }

@@ -83,10 +83,20 @@ PG_HD bool pg_is_interior(const PgWindow &w, int64_t g0, int G, int k, int64_t r
 }
 template <bool NARROW> struct PgView { typedef uint64_t type; };
 template <> struct PgView<true> { typedef uint32_t type; };
-// Visit G consecutive interior positions (window index j0 .. j0+G-1, j0 + G <= 32): f(q, F, R, vf, vr).
-// Every digit is a constant-shift field of three 64-bit views; codes roll with one multiply each.
+// The two 12-bit values of an interior position depend on its previous and next base only: 16 words
+// vf | vr << 16 indexed by dprev * 4 + dnext.  Kernels keep them in shared memory (one LDS per position
+// instead of four shift-table lookups); pg_fill_vlut is called by the first 16 threads of a CTA.
+PG_HD uint32_t pg_vlut_entry(uint32_t i) {
+    const uint32_t dp = i >> 2, din = i & 3u;
+    const uint32_t vf = (pg_lastc4_f(dp) << 6) | pg_lastc4_f(din);
+    const uint32_t vr = (pg_lastc4_r(din) << 6) | pg_lastc4_r(dp);
+    return vf | (vr << 16);
+}
+// Visit G consecutive interior positions (window index j0 .. j0+G-1, j0 + G <= 32): f(q, F, R, vw) with
+// vw = vf | vr << 16.  Every digit is a constant-shift field of three 64-bit views; codes roll with one
+// multiply each.  ``vlut``: the 16-word table above (shared memory), or nullptr to compute the values.
 template <int G, class Fn>
-PG_HD void pg_interior_visit(const PgWindow &w, int j0, int k, uint64_t pow5km1, Fn &&f) {
+PG_HD void pg_interior_visit(const PgWindow &w, int j0, int k, uint64_t pow5km1, const uint32_t *vlut, Fn &&f) {
     const uint64_t dout64 = pg_win64(w, j0);
     uint64_t F = 0, R = 0, p5 = 1;
     for (int i = 0; i < k; i++) {
@@ -100,9 +110,8 @@ PG_HD void pg_interior_visit(const PgWindow &w, int j0, int k, uint64_t pow5km1,
     for (int q = 0; q < G; q++) {
         const uint32_t dp = (uint32_t)(dprev_w >> (2 * q)) & 3u, dout = (uint32_t)(dout_w >> (2 * q)) & 3u,
                        din = (uint32_t)(din_w >> (2 * q)) & 3u;
-        const uint32_t vf = (pg_lastc4_f(dp) << 6) | pg_lastc4_f(din);
-        const uint32_t vr = (pg_lastc4_r(din) << 6) | pg_lastc4_r(dp);
-        f(q, F, R, vf, vr);
+        const uint32_t vw = vlut ? vlut[dp * 4 + din] : pg_vlut_entry(dp * 4 + din);
+        f(q, F, R, vw);
         F = (F - dout) * PG_INV5 + (uint64_t)din * pow5km1;
         R = (R - (uint64_t)(3u - dout) * pow5km1) * 5 + (3u - din);
     }
@@ -113,6 +122,16 @@ struct PgUpdate { uint64_t key; uint32_t masks; uint32_t inc; };
 // canonical pairing: slot key = min(F, R); masks = m(orientation 0) | m(orientation 1) << 16,
 // orientation 0 being the one whose literal code equals the slot key.  Palindromes (F == R, only
 // possible with ambiguity digits or even k) fold both strands into orientation 0 and count twice.
+// same from the packed pair vw = vf | vr << 16: orientation 0 first means "swap the halves unless F < R"
+PG_HD PgUpdate pg_canonical_update_w(uint64_t F, uint64_t R, uint32_t vw) {
+    PgUpdate u;
+    const bool lt = F < R, eq = F == R;
+    const uint32_t sw = (vw >> 16) | (vw << 16);
+    u.key = lt ? F : R;
+    u.masks = eq ? ((vw | sw) & 0xFFFFu) : (lt ? vw : sw);
+    u.inc = eq ? 2u : 1u;
+    return u;
+}
 PG_HD PgUpdate pg_canonical_update(uint64_t F, uint64_t R, uint32_t vf, uint32_t vr) {
     // selects, not branches: the three cases are spread at random over the lanes of a warp
     PgUpdate u;

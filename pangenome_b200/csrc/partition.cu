@@ -101,6 +101,8 @@ k2a_partition(PartArgs a) {
     __shared__ uint32_t s_nrec;
     __shared__ uint32_t s_chunk[32];
     const uint64_t pol = pg_policy_evict_first();
+    __shared__ uint32_t s_vlut[16];
+    if (threadIdx.x < 16) s_vlut[threadIdx.x] = pg_vlut_entry(threadIdx.x);      // visible after the tile loop's first barrier
 
     auto emit = [&](int slot, uint64_t key, uint32_t masks, uint32_t inc) {
         uint32_t pid = part_of<GENERAL>(a, key);
@@ -110,14 +112,14 @@ k2a_partition(PartArgs a) {
     };
     // staging slot of this thread's q-th position: consecutive lanes take consecutive slots, so the 16-byte
     // record stores of a warp fall into distinct banks (a [thread][q] layout costs 8 wavefronts per store)
-    auto emit_pos = [&](int q, uint64_t F, uint64_t R, uint32_t vf, uint32_t vr) {
+    auto emit_pos = [&](int q, uint64_t F, uint64_t R, uint32_t vw) {      // vw = vf | vr << 16
         const int slot = q * KP_THREADS + threadIdx.x;
         if (MODE == PG_MODE_CANONICAL) {
-            PgUpdate u = pg_canonical_update(F, R, vf, vr);
+            PgUpdate u = pg_canonical_update_w(F, R, vw);
             emit(slot, u.key, u.masks, u.inc);
         } else {
-            emit(slot, F, vf, 1u);
-            if (MODE == PG_MODE_LITERAL_RC) emit(slot + KP_TILE, R, vr, 1u);
+            emit(slot, F, vw & 0xFFFFu, 1u);
+            if (MODE == PG_MODE_LITERAL_RC) emit(slot + KP_TILE, R, vw >> 16, 1u);
         }
     };
 
@@ -139,7 +141,7 @@ k2a_partition(PartArgs a) {
             const int k = a.k;
             if (pg_is_interior(w, g0, KP_G, k, rs, re, r >= 0, a.g_begin, a.g_end)) {
                 // ---- fast path: 16 ACGT positions strictly inside one record (kmer_core.cuh)
-                pg_interior_visit<KP_G>(w, j0, k, a.pow5km1, emit_pos);
+                pg_interior_visit<KP_G>(w, j0, k, a.pow5km1, s_vlut, emit_pos);
                 done = true;
             } else {
                 // ---- generic path: record edges, ambiguity codes, range ends (all the quirks) ----
@@ -157,7 +159,7 @@ k2a_partition(PartArgs a) {
                     if (ok) {
                         uint32_t vf, vr;
                         pg_occ_vals(w, j, g - rs, re - rs, k, vf, vr);
-                        emit_pos(q, F, R, vf, vr);
+                        emit_pos(q, F, R, vf | (vr << 16));
                     } else {
                         for (int e = 0; e < RPP; e++) s_pid[e * KP_TILE + q * KP_THREADS + threadIdx.x] = NOREC;
                     }

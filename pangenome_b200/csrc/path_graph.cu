@@ -137,7 +137,7 @@ k5_mark(TableView rd, int mode, SeqArgs a, int strand, uint32_t *__restrict__ hi
             int64_t r = find_record(a.seq_off, a.n_rec, g0);
             int64_t rs = r >= 0 ? __ldg(a.seq_off + r) : 0, re = __ldg(a.seq_off + r + 1);
             if (pg_is_interior(w, g0, 32, a.k, rs, re, r >= 0, a.g_begin, a.g_end)) {
-                pg_interior_visit<32>(w, 0, a.k, a.pow5km1, [&](int q, uint64_t F, uint64_t R, uint32_t, uint32_t) {
+                pg_interior_visit<32>(w, 0, a.k, a.pow5km1, nullptr, [&](int q, uint64_t F, uint64_t R, uint32_t) {
                     uint64_t so;
                     if (rdbg_hit(rd, mode, strand ? R : F, strand ? F : R, so)) bits |= 1u << q;
                 });
