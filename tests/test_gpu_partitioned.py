@@ -125,3 +125,25 @@ def test_async_build_device_args(eng):
     with _pt.raises(_lib.PgError):
         b.verify()
     assert p.n_rec == 40                                             # fetching re-packs with a larger index
+
+
+def test_builder_reuse_alternating_inputs(eng):
+    """One TwoPhaseBuilder, two different inputs back to back without synchronising in between: the table is
+    emptied by an epoch bump only, so every slot still holds the previous build's key - each result must be its
+    own input's table (a stale slot read as live, or a live one as stale, changes the checksum)."""
+    from pangenome_b200 import _lib
+    ds, refs = [], []
+    for seed in (11, 12):
+        d = eng.to_device_bytes(pangenome(3, 150_000, seed=seed))
+        ds.append(d)
+        refs.append(eng.build_dbg(eng.PackedSeqs(d), 19)[0].checksum())
+    assert refs[0] != refs[1]
+    b = eng.TwoPhaseBuilder(19, _lib.PG_MODE_CANONICAL, 3 * 150_000 + 64, estimate=False)
+    for i in (0, 0, 1, 0, 1, 1, 0, 1):
+        b.begin()
+        t = b.build_async(eng.PackedSeqs(ds[i], lazy=True))
+        assert t.checksum() == refs[i]
+        assert t.n_keys() == t.count()[0]
+    p = eng.PackedSeqs(ds[1])
+    assert b.build(p, p.n_rec).checksum() == refs[1]       # the synchronous entry on the same builder
+    b.verify()
