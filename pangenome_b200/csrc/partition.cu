@@ -69,7 +69,7 @@ __device__ __forceinline__ uint32_t part_of(const PartArgs &a, uint64_t key) {
 }
 
 template <int MODE, int KP_THREADS, bool GENERAL>
-__global__ void __launch_bounds__(KP_THREADS)
+__global__ void __launch_bounds__(KP_THREADS, KP_THREADS == 256 ? 3 : 1)
 k2a_partition(PartArgs a) {
     constexpr int KP_TILE = KP_THREADS * KP_G;
     if (a.d_counts) {      // all records of the packed stream, bounds read from the device
@@ -89,8 +89,11 @@ k2a_partition(PartArgs a) {
     constexpr int RPP = (MODE == PG_MODE_LITERAL_RC) ? 2 : 1;               // records per position
     constexpr int MAXR = KP_TILE * RPP;
     constexpr uint16_t NOREC = 0xFFFFu;
-    uint4 *s_rec = reinterpret_cast<uint4 *>(smem);                          // MAXR records, natural order
-    uint16_t *s_pid = reinterpret_cast<uint16_t *>(s_rec + MAXR);            // MAXR bucket ids (NOREC = slot unused)
+    // MAXR staged records, 12 bytes each (shared memory is what limits the CTAs per SM): the key, and the masks
+    // with the increment (1 or 2) folded into bit 31
+    uint64_t *s_key = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *s_mi = reinterpret_cast<uint32_t *>(s_key + MAXR);
+    uint16_t *s_pid = reinterpret_cast<uint16_t *>(s_mi + MAXR);             // MAXR bucket ids (NOREC = slot unused)
     uint16_t *s_perm = s_pid + MAXR;                                         // sorted index -> natural index
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_perm + MAXR);          // n_parts
     uint32_t *s_off = s_hist + a.n_parts;                                    // n_parts: exclusive offsets
@@ -106,7 +109,8 @@ k2a_partition(PartArgs a) {
 
     auto emit = [&](int slot, uint64_t key, uint32_t masks, uint32_t inc) {
         uint32_t pid = part_of<GENERAL>(a, key);
-        s_rec[slot] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), masks, inc);
+        s_key[slot] = key;
+        s_mi[slot] = masks | ((inc - 1u) << 31);
         s_pid[slot] = (uint16_t)pid;
         atomicAdd(&s_hist[pid], 1u);
     };
@@ -239,7 +243,12 @@ k2a_partition(PartArgs a) {
             }
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if (idx[j] != NOREC) { dst[j] = s_dst[s_pid[idx[j]]] + (o0 + j * KP_THREADS); rec[j] = s_rec[idx[j]]; }
+                if (idx[j] != NOREC) {
+                    dst[j] = s_dst[s_pid[idx[j]]] + (o0 + j * KP_THREADS);
+                    const uint64_t key = s_key[idx[j]];
+                    const uint32_t mi = s_mi[idx[j]];
+                    rec[j] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), mi & 0x7FFFFFFFu, 1u + (mi >> 31));
+                }
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (idx[j] != NOREC) {
@@ -294,7 +303,7 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
 
 int part_smem_bytes(int mode, int n_parts, int threads) {
     int maxr = (mode == PG_MODE_LITERAL_RC ? 2 : 1) * threads * KP_G;
-    return maxr * 16 + maxr * 2 * 2 + 4 * n_parts * 4 + 2 * n_parts * 8 + 16;
+    return maxr * 12 + maxr * 2 * 2 + 4 * n_parts * 4 + 2 * n_parts * 8 + 16;
 }
 
 }  // namespace
