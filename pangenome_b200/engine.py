@@ -414,9 +414,10 @@ def build_dbg_partitioned(packed, k, rc=True, Ns=2 ** 63, mode=None, capacity=No
 
 class TwoPhaseBuilder:
     """Reusable buffers for repeated two-phase builds of same-sized inputs (bench / serving loop):
-    the table and the record buckets stay resident in HBM between calls.  Each build runs K2a first
-    (which also samples the key space), sizes the table from the estimate - a small D2H - then clears
-    just that much of the buffer and runs K3."""
+    the table and the record buckets stay resident in HBM between calls and the table is emptied by an
+    epoch bump.  By default the table is sized from the positions upper bound, which allows the fully
+    asynchronous build_async(); with ``estimate=True`` (or when that table would take a large part of the
+    free HBM) K2a also samples the key space and build() sizes the table from the estimate - a small D2H."""
 
     def __init__(self, k, mode, n_positions, device="cuda", capacity=None, sub_bytes=8 << 20, owner_bits=0, estimate=None):
         self.L = _lib.load()
