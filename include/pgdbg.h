@@ -50,6 +50,8 @@ extern "C" {
 #define PG_STAT_SHORT 1        /* insertions of the short-record sentinel key (Q5) */
 #define PG_STAT_USED 2         /* occupied slots: kept by the inserts, recomputed by pg_table_count */
 #define PG_STAT_ENTRIES 3      /* entries in reference convention (pg_table_count) */
+#define PG_STAT_LOST 4         /* != 0: update records were dropped before they reached the table (a bucket and its
+                                  spill overflowed, pg_buckets_plan): rebuild with smaller rounds */
 #define PG_STAT_WORDS 8
 
 typedef void *pg_stream_t;
@@ -68,6 +70,9 @@ typedef struct pg_table {
     int32_t k;           /* k-mer length, 1..27 */
     int32_t epoch;       /* 1..1023: generation of the live slots (host side; pg_table_reset advances it) */
     int32_t reserved;
+    int64_t alloc_capacity; /* slots allocated behind d_slots when `capacity` selects only a prefix of the buffer
+                               (0 = same as capacity).  When the 10-bit tag wraps, pg_table_reset rewrites ALL of
+                               them: a slot beyond `capacity` must not keep a tag of the previous cycle. */
 } pg_table;
 
 const char *pg_last_error(void);
@@ -119,7 +124,9 @@ int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes,
 int64_t pg_table_bytes(int64_t capacity);
 int pg_table_clear(const pg_table *t, pg_stream_t stream);
 int pg_table_reset(pg_table *t, pg_stream_t stream);
-/* adds (strands x records of [0,n_rec) shorter than k whose offset lies in [g_begin, g_end]) to PG_STAT_SHORT;
+/* adds (strands x records of [0,n_rec) shorter than k whose offset lies in [g_begin, g_end)) to PG_STAT_SHORT;
+ * the range that reaches the end of the stream (g_end >= d_seq_off[n_rec]) also owns records AT g_end (trailing
+ * empty records), so consecutive ranges [a,b) [b,c) never count a record twice.
  * pg_kmer_insert calls it itself, the two-phase path (pg_kmer_partition) does not */
 int pg_count_short(const pg_table *t, const int64_t *d_seq_off, int64_t n_rec, int64_t g_begin, int64_t g_end,
                    pg_stream_t stream);
@@ -182,6 +189,42 @@ int pg_kmer_partition_p2p_dev(const pg_table *t, const uint32_t *d_pk2, const ui
                               pg_stream_t stream);
 int pg_count_short_dev(const pg_table *t, const int64_t *d_seq_off, const int64_t *d_counts, int64_t cap_records,
                        pg_stream_t stream);
+
+/* ---- bucket sets: rounds, spill, receiver-side split (the streaming single- and multi-GPU builders) ----------
+ * A bucket set names where K2a (or K2b) puts its update records:
+ *   local : d_records holds 2^(owner_bits+sub_bits) buckets of part_cap records followed by ONE spill bucket of
+ *           spill_cap records.  A record whose bucket is full goes to the spill instead of being dropped, so hash
+ *           skew (one k-mer making up a visible share of the input: poly-A, satellites - BASELINE configs 4/5) is
+ *           absorbed; K3 sweeps the spill as one more region (table_upsert finds the home slot from the key, a
+ *           record does not have to sit in "its" region to be inserted correctly).
+ *   peer  : d_peer_bases[owner] = rank `owner`'s receive buffer (pg_peer_alloc/open); bucket (owner, sub) lands at
+ *           [my_rank][sub][part_cap] there.  No spill across NVLink: overflow shows in the counts.
+ * d_part_counts has 2^(owner_bits+sub_bits) + 1 counters: records PRODUCED per bucket (may exceed part_cap) and,
+ * last, records offered to the spill.
+ * pg_kmer_partition_to: K2a into a bucket set (counters zeroed first).  With d_counts != NULL the record count and
+ *   stream range are read on the device (pg_kmer_partition_dev) and [g_begin, g_end) is RELATIVE to the first
+ *   record's offset (g_end < 0 = to the end): one round of a multi-round build without any host read-back.
+ * pg_records_split (K2b): re-sort n_seg segments of records (e.g. what each source rank sent, bucketed by owner only
+ *   so the NVLink runs are long) into the 2^sub_bits hash-prefix regions of a local bucket set: 32 B of HBM traffic
+ *   per record buys L2-resident K3 regions for tables of any size.  A segment count above seg_cap (the sender's
+ *   wire bucket overflowed) is clamped and raises PG_STAT_LOST in d_table_stats (may be NULL).
+ * pg_buckets_plan: d_seg_cnt[i] = min(count, capacity) for the 2^bits buckets + the spill (what pg_insert_records
+ *   sweeps, with seg offsets i * part_cap), and PG_STAT_LOST in d_table_stats when records were dropped.
+ * Replaces oakht.resize's grow-and-rehash (kmer_numba.py:423-474) as the answer to "the table / a bucket is full". */
+typedef struct pg_bucket_set {
+    uint64_t *d_records;
+    uint64_t *const *d_peer_bases;
+    int64_t *d_part_counts;
+    int64_t part_cap, spill_cap;
+    int32_t owner_bits, sub_bits, my_rank, reserved;
+} pg_bucket_set;
+int pg_kmer_partition_to(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                         int64_t n_rec, int64_t g_begin, int64_t g_end, const int64_t *d_counts, int64_t cap_records,
+                         int64_t max_bases, const pg_bucket_set *out, uint64_t *d_sample_keys, int64_t sample_cap,
+                         int64_t *d_sample_count, pg_stream_t stream);
+int pg_records_split(const uint64_t *d_records_in, const int64_t *d_seg_off, const int64_t *d_seg_cnt, int n_seg,
+                     int64_t seg_cap, const pg_bucket_set *out, int64_t *d_table_stats, pg_stream_t stream);
+int pg_buckets_plan(const pg_bucket_set *b, int64_t *d_seg_cnt, int64_t *d_table_stats, pg_stream_t stream);
 int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
                       const int64_t *d_seg_cnt, int n_regions, int n_src, int64_t seg_cap, pg_stream_t stream);
 
@@ -311,6 +354,14 @@ int pg_host_write_mcl(const char *path, const uint64_t *code, const uint32_t *v5
 int64_t pg_host_oakht_capacity(int64_t n_entries);
 int pg_host_build_oakht(const uint64_t *keys, const uint16_t *vals, const uint8_t *cnts, int64_t n, int64_t cap,
                         uint64_t *okeys, uint16_t *ovals, uint8_t *ocnts);
+
+/* ---- measurement support ("a micro-benchmark ceiling (random atomicCAS + atomicOr into a table of the
+ * same byte size)") - not part of the hot path.  n_ops operations, each on one pseudo-random 16-byte slot; the regions
+ * (region_slots slots each) are swept in order by the whole grid like pg_insert_records does.  mode: 0 load, 1 load +
+ * red.add, 2 load + cas.b128, 3 the config-2 mix (1/3 cas, 2/3 red), 4 red only, 5 load + red.or + red.add; +8 also
+ * streams one 16-byte record per operation from d_records.  Overwrites the slots. */
+int pg_microbench_slots(uint64_t *d_slots, int64_t capacity, int64_t region_slots, int64_t n_ops, int mode, int ctas_per_sm,
+                        const uint64_t *d_records, uint64_t *d_sink, pg_stream_t stream);
 
 #ifdef __cplusplus
 }

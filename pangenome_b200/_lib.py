@@ -7,14 +7,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpgdbg.so")
 
 PG_MODE_LITERAL, PG_MODE_LITERAL_RC, PG_MODE_CANONICAL = 0, 1, 2
-PG_STAT_OVERFLOW, PG_STAT_SHORT, PG_STAT_USED, PG_STAT_ENTRIES, PG_STAT_WORDS = 0, 1, 2, 3, 8
+PG_STAT_OVERFLOW, PG_STAT_SHORT, PG_STAT_USED, PG_STAT_ENTRIES, PG_STAT_LOST, PG_STAT_WORDS = 0, 1, 2, 3, 4, 8
 
 c_i64, c_int, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
 
 
 class PgTable(ctypes.Structure):
     _fields_ = [("d_slots", c_vp), ("capacity", c_i64), ("d_stats", c_vp), ("mode", ctypes.c_int32),
-                ("k", ctypes.c_int32), ("epoch", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("k", ctypes.c_int32), ("epoch", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("alloc_capacity", c_i64)]
 
 
 PT = ctypes.POINTER(PgTable)
@@ -27,6 +28,14 @@ class PgGraph(ctypes.Structure):
 
 
 GT = ctypes.POINTER(PgGraph)
+
+
+class PgBucketSet(ctypes.Structure):
+    _fields_ = [("d_records", c_vp), ("d_peer_bases", c_vp), ("d_part_counts", c_vp), ("part_cap", c_i64), ("spill_cap", c_i64),
+                ("owner_bits", ctypes.c_int32), ("sub_bits", ctypes.c_int32), ("my_rank", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+BT = ctypes.POINTER(PgBucketSet)
 
 # name -> (restype, argtypes); every symbol include/pgdbg.h declares
 SIGNATURES = {
@@ -51,6 +60,10 @@ SIGNATURES = {
     "pg_kmer_partition_dev": (c_int, [PT, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
     "pg_count_short_dev": (c_int, [PT, c_vp, c_vp, c_i64, c_vp]),
     "pg_insert_records": (c_int, [PT, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
+    "pg_kmer_partition_to": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, BT, c_vp, c_i64, c_vp, c_vp]),
+    "pg_records_split": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, BT, c_vp, c_vp]),
+    "pg_buckets_plan": (c_int, [BT, c_vp, c_vp, c_vp]),
+    "pg_microbench_slots": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     "pg_table_count": (c_int, [PT, c_vp]),
     "pg_table_export": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "pg_table_checksum": (c_int, [PT, c_vp, c_vp]),

@@ -1,0 +1,334 @@
+"""The streaming dBG builder: one code path for a single GPU and for the hash-partitioned multi-GPU build
+(replaces oakht + seq2dbg_jit_, kmer_numba.py:340-679, 1202-1230; the split is SURVEY.md 8e).
+
+A build is cut into ROUNDS of stream positions.  Per round and rank:
+
+    stream A   K2a   k-mer extraction -> 16-byte update records
+                     world 1 : straight into the 2^sub_bits hash-prefix buckets (+ spill) of a local set
+                     world N : bucketed by OWNER only and stored into the owners' receive buffers over NVLink
+                               (CUDA IPC peer memory) - 8192-position tiles give 16 KB runs per peer
+    stream B   [N>1] all-to-all of the W record counts (NCCL) - also the barrier that orders the peer stores
+               [N>1] K2b  what arrived (one segment per source) -> hash-prefix buckets (+ spill)
+                     plan (clamped counts, PG_STAT_LOST), K3 region sweep into the table
+
+Two record buffers alternate, so K2a of round r+1 runs while K2b/K3 of round r drain the other buffer: the
+issue-bound extraction (and its NVLink write-out) overlaps the latency-bound table sweep.  Nothing is read
+back inside a build; verify() looks at the table's statistics block afterwards (overflow / lost-record flags)
+and the callers fall back to a safer configuration (more rounds, larger table) when it trips.
+
+Memory: a round holds round_len x 16 B x slack per buffer, the table 16 B per slot; both are sized for the
+HBM that is actually free (180 GB on a B200), so inputs far larger than one round stream through.
+"""
+import ctypes
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, engine
+from ._lib import PgBucketSet, PgError, check
+
+_TILE = 8192
+
+
+class LostRecords(PgError):
+    """update records were dropped (bucket + spill overflow): rebuild with more rounds"""
+
+
+class TableFull(PgError):
+    """the hash table ran out of probe room: rebuild with a larger capacity"""
+
+
+def log2_exact(n):
+    b = n.bit_length() - 1
+    if n < 1 or (1 << b) != n:
+        raise ValueError("world size must be a power of two (1, 2, 4, 8), got %d" % n)
+    return b
+
+
+class LocalBuckets:
+    """2^sub_bits buckets of ``part_cap`` update records + one spill bucket (include/pgdbg.h pg_bucket_set)."""
+
+    def __init__(self, sub_bits, part_cap, spill_cap, device):
+        self.sub_bits, self.n_parts, self.part_cap, self.spill_cap = sub_bits, 1 << sub_bits, int(part_cap), int(spill_cap)
+        n = self.n_parts
+        self.records = torch.empty(2 * (n * self.part_cap + self.spill_cap), dtype=torch.int64, device=device)
+        self.counts = torch.zeros(n + 1, dtype=torch.int64, device=device)
+        self.seg_off = torch.arange(n + 1, dtype=torch.int64, device=device) * self.part_cap      # the spill follows the last bucket
+        self.seg_cnt = torch.zeros(n + 1, dtype=torch.int64, device=device)
+        self.c = PgBucketSet(self.records.data_ptr(), None, self.counts.data_ptr(), self.part_cap, self.spill_cap, 0, sub_bits, 0, 0)
+
+    def bytes(self):
+        return self.records.numel() * 8
+
+
+def plan_rounds(n_bases_max, rounds=None, round_len=None, tile=_TILE):
+    """(n_rounds, round_len): the stream [0, n_bases_max) in equal rounds, a whole number of K2a tiles each."""
+    n_bases_max = max(1, int(n_bases_max))
+    if round_len is None:
+        rounds = max(1, int(rounds or 1))
+        round_len = (n_bases_max + rounds - 1) // rounds
+    round_len = max(tile, (int(round_len) + tile - 1) // tile * tile)
+    return (n_bases_max + round_len - 1) // round_len, round_len
+
+
+def table_capacity_for(n_keys_upper, free_bytes, load=0.5, max_fraction=0.55):
+    """Power-of-two slot count for at most ``n_keys_upper`` keys, never more than ``max_fraction`` of the free HBM."""
+    cap = engine.next_pow2(max(1024, int(n_keys_upper / load) + 1))
+    while cap > 1024 and cap * 16 > max_fraction * free_bytes:
+        cap //= 2
+    return cap
+
+
+class RoundBuilder:
+    """See the module docstring.  ``n_bases_max``: upper bound of this rank's stream length per build (the file size
+    will do).  ``rounds`` / ``round_len``: how the stream is cut (default: PG_ROUNDS or 1 round on one GPU, 4 across
+    GPUs, and never more than 2^27 positions per round)."""
+
+    MAX_ROUND = 1 << 27
+
+    def __init__(self, k, mode, n_bases_max, world=1, rank=0, device="cuda", capacity=None, rounds=None, round_len=None,
+                 sub_bytes=8 << 20, slack=1.25, spill_frac=1.0 / 16):
+        engine._require_cuda()
+        self.L = _lib.load()
+        self.k, self.mode = int(min(max(1, k), 27)), int(mode)
+        self.world, self.rank, self.device = int(world), int(rank), torch.device(device)
+        self.owner_bits = log2_exact(self.world)
+        if self.world > 1 and self.mode == _lib.PG_MODE_LITERAL_RC:
+            raise PgError("the multi-GPU build runs in PG_MODE_CANONICAL (both strands) or PG_MODE_LITERAL (one strand)")
+        per_pos = 2 if self.mode == _lib.PG_MODE_LITERAL_RC else 1
+        dev = self.device
+        n_max, n_sum = int(n_bases_max), int(n_bases_max)
+        if self.world > 1:
+            t = torch.tensor([n_max, n_max], dtype=torch.int64, device=dev)
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            n_max, n_sum = int(tm[0].item()), int(t[1].item())
+        self.n_bases_max = n_max
+        if rounds is None and round_len is None:
+            rounds = int(os.environ.get("PG_ROUNDS", "0")) or (4 if self.world > 1 else 1)
+            rounds = max(rounds, (n_max + self.MAX_ROUND - 1) // self.MAX_ROUND)
+        self.n_rounds, self.round_len = plan_rounds(n_max, rounds, round_len)
+        # ---- the table: every key lives on exactly one rank; sized for the worst case (all positions distinct, evenly
+        # spread) while that is affordable, else for what the free HBM allows (the overflow flag reports a table too small)
+        free = torch.cuda.mem_get_info(dev)[0]
+        R, W = self.round_len, self.world
+        buf_bytes = (2 if W == 1 else 3) * int(R * per_pos * 16 * slack * 1.1)
+        per_rank_keys = (n_sum * per_pos + W - 1) // W
+        cap = engine.next_pow2(capacity) if capacity else table_capacity_for(per_rank_keys, max(free - buf_bytes, 1 << 30))
+        self.table = engine.DbgTable(cap, self.k, self.mode, device=dev)
+        self.sub_bits = engine.sub_bits_for(cap, sub_bytes)
+        n_sub = 1 << self.sub_bits
+        # ---- record buffers
+        if W == 1:
+            part_cap = int(R * per_pos / n_sub * slack) + 2048
+            spill_cap = max(1 << 16, int(R * per_pos * spill_frac))
+            self.sets = [LocalBuckets(self.sub_bits, part_cap, spill_cap, dev) for _ in range(2 if self.n_rounds > 1 else 1)]
+            self.wire = None
+        else:
+            self.cap_wire = cw = int(R / W * slack) + 8192
+            self.wire_bytes = W * cw * 16
+            self.own, self._opened, self.peer_tables, self.wire_sets = [], [], [], []
+            for _ in range(2):
+                ptr = ctypes.c_void_p()
+                handle = ctypes.create_string_buffer(64)
+                check(self.L.pg_peer_alloc(self.wire_bytes, ctypes.byref(ptr), handle), "pg_peer_alloc")
+                handles = [None] * W
+                dist.all_gather_object(handles, handle.raw)
+                addrs = []
+                for r in range(W):
+                    if r == rank:
+                        addrs.append(ptr.value)
+                    else:
+                        q = ctypes.c_void_p()
+                        check(self.L.pg_peer_open(handles[r], ctypes.byref(q)), "pg_peer_open")
+                        self._opened.append(q)
+                        addrs.append(q.value)
+                self.own.append(ptr)
+                self.peer_tables.append(torch.tensor(addrs, dtype=torch.int64, device=dev))
+            self.send_counts = [torch.zeros(W + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+            self.recv_counts = [torch.zeros(W, dtype=torch.int64, device=dev) for _ in range(2)]
+            for i in range(2):      # bucket (owner) of source `rank` lands at [rank][cap_wire] of the owner's buffer
+                self.wire_sets.append(PgBucketSet(None, self.peer_tables[i].data_ptr(), self.send_counts[i].data_ptr(), cw, 0,
+                                                  self.owner_bits, 0, rank, 0))
+            self.wire_seg_off = torch.arange(W, dtype=torch.int64, device=dev) * cw
+            self.sent_total = torch.zeros(W, dtype=torch.int64, device=dev)
+            arriving = W * cw
+            part_cap = int(arriving / n_sub * slack) + 2048
+            spill_cap = max(1 << 16, int(arriving * spill_frac))
+            self.sets = [LocalBuckets(self.sub_bits, part_cap, spill_cap, dev)]
+            dist.barrier()
+        self.sA, self.sB = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self._round = 0                     # global round counter: buffer parity carries over from build to build
+        self._ev_free = [None, None]        # world 1: K3 finished reading local set i
+        self._ev_a2a = None                 # world N: the previous round's count exchange (= every peer drained buffer i)
+        self._begun = False
+        self.desc = _lib.PgTable(None, 2, None, self.mode, self.k, 1, 0, 0)      # K2a reads mode and k only
+        self.launches_per_round = 3 if W == 1 else 4      # K2a, plan, K3 (+ K2b); the count exchange is NCCL's
+        self.launches_per_build = 1 + self.n_rounds * self.launches_per_round       # + count_short
+
+    # ------------------------------------------------------------------------------------------------
+    def begin(self):
+        """Empty the table for the next build: an epoch bump (DbgTable.clear), no HBM traffic."""
+        self.table.clear()
+        self._begun = True
+
+    def build_async(self, packed, n_rec=None, ev=None):
+        """Enqueue one build of records [0, n_rec) of ``packed`` (``None``: ALL records, bounds read on the device -
+        nothing K1 produced has to reach the host, PackedSeqs(lazy=True)).  Returns the table; verify() checks it.
+        ``ev``: dict receiving (start, end) CUDA event pairs per stage."""
+        L, t, W = self.L, self.table, self.world
+        P, byref = engine._ptr, ctypes.byref
+        cur = torch.cuda.current_stream()
+        if not self._begun:
+            self.begin()
+        self._begun = False
+        A, B = self.sA, self.sB
+        A.wait_stream(cur)
+        B.wait_stream(cur)
+        dev_mode = n_rec is None
+        if dev_mode:
+            d_counts, cap_records, max_bases, g0, g1 = P(packed.d_counts), packed.cap_records, packed.nbytes, 0, None
+            n_rec_arg = 1
+        else:
+            d_counts, cap_records, max_bases = None, 0, 0
+            g0 = int(packed.seq_off[0]) if n_rec > 0 else 0
+            g1 = int(packed.seq_off[n_rec]) if n_rec > 0 else 0
+            n_rec_arg = n_rec
+        def stamp(stream):
+            if ev is None:
+                return None
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            return e
+
+        with torch.cuda.stream(B):
+            if dev_mode:
+                check(L.pg_count_short_dev(byref(t.c), P(packed.d_seq_off), d_counts, cap_records, engine._stream()), "pg_count_short_dev")
+            elif n_rec > 0:
+                check(L.pg_count_short(byref(t.c), P(packed.d_seq_off), n_rec, g0, g1, engine._stream()), "pg_count_short")
+        for r in range(self.n_rounds):
+            lo, hi = r * self.round_len, (r + 1) * self.round_len
+            if not dev_mode:
+                lo, hi = min(g0 + lo, g1), min(g0 + hi, g1)
+            i = self._round & 1
+            self._round += 1
+            # ---- stream A: extraction (+ NVLink write-out) into buffer i
+            with torch.cuda.stream(A):
+                if W == 1:
+                    si = i % len(self.sets)
+                    bs = self.sets[si]
+                    if self._ev_free[si] is not None:
+                        A.wait_event(self._ev_free[si])           # K3 of the round that last used this set has drained it
+                    out = bs.c
+                else:
+                    if self._ev_a2a is not None:
+                        A.wait_event(self._ev_a2a)          # every peer has drained buffer i (its K2b of two rounds ago)
+                    out = self.wire_sets[i]
+                e0 = stamp(A)
+                check(L.pg_kmer_partition_to(byref(self.desc), P(packed.pk2), P(packed.amb), P(packed.d_seq_off), n_rec_arg, lo, hi,
+                                             d_counts, cap_records, max_bases, byref(out), None, 0, None, engine._stream()),
+                      "pg_kmer_partition_to")
+                e1 = stamp(A)
+                if ev is not None and W > 1:
+                    self.sent_total += self.send_counts[i][:W]       # measurement only: records really sent to every owner
+                done = torch.cuda.Event()
+                done.record(A)
+            # ---- stream B: (exchange barrier, split,) plan, table sweep
+            with torch.cuda.stream(B):
+                B.wait_event(done)
+                if W > 1:
+                    bs = self.sets[0]
+                    x0 = stamp(B)
+                    dist.all_to_all_single(self.recv_counts[i], self.send_counts[i][:W])
+                    self._ev_a2a = torch.cuda.Event()
+                    self._ev_a2a.record(B)
+                    x1 = stamp(B)
+                    check(L.pg_records_split(self.own[i], P(self.wire_seg_off), P(self.recv_counts[i]), W, self.cap_wire, byref(bs.c),
+                                             P(t.stats), engine._stream()), "pg_records_split")
+                    x2 = stamp(B)
+                else:
+                    x2 = stamp(B)
+                check(L.pg_buckets_plan(byref(bs.c), P(bs.seg_cnt), P(t.stats), engine._stream()), "pg_buckets_plan")
+                check(L.pg_insert_records(byref(t.c), P(bs.records), P(bs.seg_off), P(bs.seg_cnt), bs.n_parts + 1, 1, 0, engine._stream()),
+                      "pg_insert_records")
+                x3 = stamp(B)
+                if W == 1:
+                    self._ev_free[si] = torch.cuda.Event()
+                    self._ev_free[si].record(B)
+            if ev is not None:
+                ev.setdefault("k2a", []).append((e0, e1))
+                if W > 1:
+                    ev.setdefault("count_exchange", []).append((x0, x1))
+                    ev.setdefault("k2b", []).append((x1, x2))
+                ev.setdefault("k3", []).append((x2, x3))
+        cur.wait_stream(B)
+        cur.wait_stream(A)
+        return t
+
+    # ------------------------------------------------------------------------------------------------
+    def flags(self):
+        """(table full, records lost) after a synchronise; agreed on by all ranks."""
+        s = self.table.stats_host()
+        f = torch.tensor([int(s[_lib.PG_STAT_OVERFLOW] != 0), int(s[_lib.PG_STAT_LOST] != 0)], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            # a truncated record index poisons the wire counts: the receiver flags PG_STAT_LOST, so it is covered here
+            dist.all_reduce(f, op=dist.ReduceOp.MAX)
+        f = f.cpu()
+        return bool(f[0]), bool(f[1])
+
+    def verify(self):
+        full, lost = self.flags()
+        if lost:
+            raise LostRecords("update records were dropped (bucket/spill overflow or a truncated record index) on some rank")
+        if full:
+            raise TableFull("dBG table overflow (capacity %d slots per rank)" % self.table.capacity)
+
+    def close(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            for q in self._opened:
+                self.L.pg_peer_close(q)
+            for p_ in self.own:
+                self.L.pg_peer_free(p_)
+            self._opened, self.own = [], []
+
+    def describe(self):
+        d = {"rounds": self.n_rounds, "round_len": self.round_len, "table_slots": self.table.capacity, "regions": 1 << self.sub_bits,
+             "record_buffers_bytes": sum(s.bytes() for s in self.sets) + (2 * self.wire_bytes if self.world > 1 else 0)}
+        if self.world > 1:
+            d["wire_bucket_records"] = self.cap_wire
+        return d
+
+
+def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capacity=None, rounds=None, max_attempts=4):
+    """The product's stage-1 build: RoundBuilder with automatic recovery - more rounds (smaller buckets relative
+    to their capacity) after lost records, a larger table after an overflow.  Returns (DbgTable, n_rec, builder)."""
+    k = int(min(max(1, k), 27))
+    if mode is None:
+        mode = _lib.PG_MODE_CANONICAL if rc else _lib.PG_MODE_LITERAL
+    strands = 1 if mode == _lib.PG_MODE_LITERAL else 2
+    n_rec = packed.record_prefix(Ns, strands)
+    n_bases = int(packed.seq_off[n_rec] - packed.seq_off[0]) if n_rec > 0 else 0
+    spill_frac = 1.0 / 16
+    err = None
+    for _ in range(max_attempts):
+        b = RoundBuilder(k, mode, max(n_bases, 1), world=world, rank=rank, device=packed.pk2.device, capacity=capacity, rounds=rounds,
+                         spill_frac=spill_frac)
+        b.begin()
+        b.build_async(packed, n_rec)
+        torch.cuda.synchronize()
+        try:
+            b.verify()
+            return b.table, n_rec, b
+        except LostRecords as e:
+            err = e
+            rounds, spill_frac = 4 * b.n_rounds, min(1.0, spill_frac * 4)
+        except TableFull as e:
+            err = e
+            capacity = 2 * b.table.capacity
+        b.close()
+        del b
+    raise PgError("dBG build failed after %d attempts: %s" % (max_attempts, err))

@@ -26,7 +26,9 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
     __shared__ __align__(16) uint64_t s_pk[K2_TILE_WORDS + 4];
     __shared__ __align__(16) uint32_t s_am[K2_TILE_WORDS + 8];
     __shared__ uint32_t s_vlut[16];
+    __shared__ uint16_t s_lut5[PG_LUT5_SIZE];
     if (threadIdx.x < 16) s_vlut[threadIdx.x] = pg_vlut_entry(threadIdx.x);      // visible after the tile loop's first barrier
+    for (int i = threadIdx.x; i < PG_LUT5_SIZE; i += K2_THREADS) s_lut5[i] = (uint16_t)pg_lut5_entry(i);
     uint32_t n_claimed = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t w0 = w_first + tile * K2_TILE_WORDS;
@@ -50,7 +52,7 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
             }
         };
         if (pg_is_interior(w, g0, 32, k, rs, re, r >= 0, g_begin, g_end)) {
-            pg_interior_visit<32>(w, 0, k, pow5km1, s_vlut, upsert_pos);      // fast path: no record edge, no ambiguity
+            pg_interior_visit<32>(w, 0, k, pow5km1, s_vlut, s_lut5, upsert_pos);      // fast path: no record edge, no ambiguity
             continue;
         }
         uint64_t F, R;
@@ -73,9 +75,10 @@ k2_kmer_insert(TableView t, const uint64_t *__restrict__ pk2, const uint32_t *__
 
 // records shorter than k insert the sentinel key 2^64-1 once per strand (Q5, build_dbg :1089-1090)
 __global__ void k2_count_short(const int64_t *__restrict__ seq_off, int64_t n_rec, int64_t g_begin, int64_t g_end,
-                               int64_t g_total, int k, int strands, int64_t *stats) {
+                               int k, int strands, int64_t *stats) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t mine = 0;
+    const int64_t g_total = seq_off[n_rec];      // true end of the stream: only the range that reaches it owns offset == g_end
     if (i < n_rec) {
         int64_t a = seq_off[i], b = seq_off[i + 1];
         bool owned = a >= g_begin && (a < g_end || (g_end >= g_total && a <= g_end));
@@ -207,14 +210,25 @@ __global__ void k4_rdbg_select(const uint64_t *__restrict__ slots, int64_t cap, 
 __global__ void k4_rdbg_export(const uint64_t *__restrict__ slots, int64_t cap, uint64_t tag, int mode, int k,
                                const int64_t *__restrict__ stats, uint64_t *keys, uint16_t *vals, int64_t out_cap,
                                unsigned long long *n_out) {
-    int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    for (int64_t i = i0; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t key, v; pg_ld_slot(slots + 2 * i, tag, key, v);
-        if (key == PG_EMPTY) continue;
-        uint32_t masks = (uint32_t)v, f = (uint32_t)(v >> 32);
-        int n = (f & 1u) + ((f >> 1) & 1u);
-        if (!n) continue;
-        unsigned long long at = atomicAdd(n_out, (unsigned long long)n);
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t base = i0 - lane; base < cap; base += stride) {       // whole warps iterate together
+        const int64_t i = base + lane;
+        uint64_t key = PG_EMPTY, v = 0;
+        if (i < cap) pg_ld_slot(slots + 2 * i, tag, key, v);
+        const uint32_t masks = (uint32_t)v, f = key == PG_EMPTY ? 0u : (uint32_t)(v >> 32);
+        const unsigned n = (f & 1u) + ((f >> 1) & 1u);
+        // warp-ballot stream compaction: one atomicAdd per warp reserves the run, lanes write at their prefix
+        unsigned pre = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += y; }
+        const unsigned tot = __shfl_sync(0xffffffffu, pre, 31);
+        if (tot == 0) continue;
+        pre -= n;
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(n_out, (unsigned long long)tot);
+        at = __shfl_sync(0xffffffffu, at, 0) + pre;
         if (f & 1u) { if ((int64_t)at < out_cap) { keys[at] = key; if (vals) vals[at] = (uint16_t)(masks & 0xFFFu); } at++; }
         if (f & 2u) { if ((int64_t)at < out_cap) { keys[at] = pg_rc_code(key, k); if (vals) vals[at] = (uint16_t)((masks >> 16) & 0xFFFu); } }
     }
@@ -264,7 +278,11 @@ extern "C" int pg_table_reset(pg_table *t, pg_stream_t stream_) {
     int rc = check_table(t, "pg_table_reset"); if (rc) return rc;
     if (t->epoch >= PG_EPOCH_MAX) {           // tags would repeat: rewrite the slots and start over
         t->epoch = 1;
-        return pg_table_clear(t, stream_);
+        // ALL allocated slots, not only the prefix selected by `capacity`: a slot beyond it that kept a tag of
+        // the previous cycle would read as live once the capacity grows again
+        pg_table all = *t;
+        if (all.alloc_capacity > all.capacity) all.capacity = all.alloc_capacity;
+        return pg_table_clear(&all, stream_);
     }
     t->epoch += 1;                            // every slot written so far now reads as free
     PG_CUDA(cudaMemsetAsync(t->d_stats, 0, PG_STAT_WORDS * sizeof(int64_t), (cudaStream_t)stream_));
@@ -277,8 +295,9 @@ extern "C" int pg_count_short(const pg_table *t, const int64_t *d_seq_off, int64
     if (!d_seq_off || n_rec < 0) return pg_fail(PG_ERR_INVALID, "pg_count_short: bad arguments");
     if (n_rec == 0) return PG_OK;
     int strands = t->mode == PG_MODE_LITERAL ? 1 : 2;
-    // a record is owned by the range holding its offset; the range that ends the stream also owns trailing empty records
-    k2_count_short<<<(unsigned)((n_rec + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(d_seq_off, n_rec, g_begin, g_end, g_end, t->k, strands, t->d_stats);
+    // a record is owned by the half-open range holding its offset; the range that reaches the end of the stream
+    // (d_seq_off[n_rec], read on the device) also owns the trailing empty records at that offset
+    k2_count_short<<<(unsigned)((n_rec + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(d_seq_off, n_rec, g_begin, g_end, t->k, strands, t->d_stats);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

@@ -8,6 +8,14 @@
 #include "common.cuh"
 
 namespace {
+// buffered writer that remembers a short write: a full disk must not leave a truncated side file behind a PG_OK
+struct OutFile {
+    FILE *f; bool ok;
+    explicit OutFile(const char *path) : f(fopen(path, "wb")), ok(f != nullptr) {}
+    void write(const char *p, size_t n) { if (ok && n && fwrite(p, 1, n, f) != n) ok = false; }
+    bool close() { if (f) { if (fclose(f) != 0) ok = false; f = nullptr; } return ok; }
+    ~OutFile() { if (f) fclose(f); }
+};
 inline char *put_u64(char *p, uint64_t v) {
     char tmp[24]; int n = 0;
     do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
@@ -19,35 +27,35 @@ inline char *put_u64(char *p, uint64_t v) {
 // "%d_%d\t%d_%d\t%d\n" per edge, in the order given (the caller sorts by first-insertion ordinal)
 extern "C" int pg_host_write_xyz(const char *path, const uint64_t *c0, const uint32_t *v0, const uint64_t *c1,
                                  const uint32_t *v1, const uint32_t *w, int64_t n) {
-    FILE *f = fopen(path, "wb");
-    if (!f) return pg_fail(PG_ERR_INVALID, "pg_host_write_xyz: cannot open %s", path);
+    OutFile f(path);
+    if (!f.ok) return pg_fail(PG_ERR_INVALID, "pg_host_write_xyz: cannot open %s", path);
     std::vector<char> buf(1 << 22);
     char *p = buf.data(), *end = buf.data() + buf.size() - 128;
     for (int64_t i = 0; i < n; i++) {
         p = put_u64(p, c0[i]); *p++ = '_'; p = put_u64(p, v0[i]); *p++ = '\t';
         p = put_u64(p, c1[i]); *p++ = '_'; p = put_u64(p, v1[i]); *p++ = '\t';
         p = put_u64(p, w[i]); *p++ = '\n';
-        if (p > end) { fwrite(buf.data(), 1, (size_t)(p - buf.data()), f); p = buf.data(); }
+        if (p > end) { f.write(buf.data(), (size_t)(p - buf.data())); p = buf.data(); }
     }
-    fwrite(buf.data(), 1, (size_t)(p - buf.data()), f);
-    fclose(f);
+    f.write(buf.data(), (size_t)(p - buf.data()));
+    if (!f.close()) return pg_fail(PG_ERR_INVALID, "pg_host_write_xyz: short write to %s (disk full?)", path);
     return PG_OK;
 }
 
 // one tab-separated line of node names "code_v5" per label; nodes must arrive sorted by (label, code, v5)
 extern "C" int pg_host_write_mcl(const char *path, const uint64_t *code, const uint32_t *v5, const int64_t *label, int64_t n) {
-    FILE *f = fopen(path, "wb");
-    if (!f) return pg_fail(PG_ERR_INVALID, "pg_host_write_mcl: cannot open %s", path);
+    OutFile f(path);
+    if (!f.ok) return pg_fail(PG_ERR_INVALID, "pg_host_write_mcl: cannot open %s", path);
     std::vector<char> buf(1 << 22);
     char *p = buf.data(), *end = buf.data() + buf.size() - 128;
     for (int64_t i = 0; i < n; i++) {
         if (i) *p++ = (label[i] != label[i - 1]) ? '\n' : '\t';
         p = put_u64(p, code[i]); *p++ = '_'; p = put_u64(p, v5[i]);
-        if (p > end) { fwrite(buf.data(), 1, (size_t)(p - buf.data()), f); p = buf.data(); }
+        if (p > end) { f.write(buf.data(), (size_t)(p - buf.data())); p = buf.data(); }
     }
     if (n) *p++ = '\n';
-    fwrite(buf.data(), 1, (size_t)(p - buf.data()), f);
-    fclose(f);
+    f.write(buf.data(), (size_t)(p - buf.data()));
+    if (!f.close()) return pg_fail(PG_ERR_INVALID, "pg_host_write_mcl: short write to %s (disk full?)", path);
     return PG_OK;
 }
 

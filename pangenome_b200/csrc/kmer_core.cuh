@@ -92,16 +92,58 @@ PG_HD uint32_t pg_vlut_entry(uint32_t i) {
     const uint32_t vr = (pg_lastc4_r(din) << 6) | pg_lastc4_r(dp);
     return vf | (vr << 16);
 }
+// ---- table-driven initial codes ---------------------------------------------------------------
+// base-5 value of five 2-bit digits: lut5[x] = sum_{i<5} ((x >> 2i) & 3) * 5^i, x < 1024 (2 KB as uint16).
+// Kernels keep it in shared memory (pg_fill_lut5 by the whole CTA); with it the first window's two codes
+// cost 12 look-ups and 10 multiply-adds instead of a 27-step digit loop per code.
+#define PG_LUT5_SIZE 1024
+PG_HD uint32_t pg_lut5_entry(uint32_t x) {
+    return (x & 3u) + 5u * ((x >> 2) & 3u) + 25u * ((x >> 4) & 3u) + 125u * ((x >> 6) & 3u) + 625u * ((x >> 8) & 3u);
+}
+// reverse the order of the 32 two-bit groups of a word
+PG_HD uint64_t pg_rev2(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    x = __brevll(x);
+#else
+    x = ((x >> 32) | (x << 32));
+    x = ((x & 0xFFFF0000FFFF0000ull) >> 16) | ((x & 0x0000FFFF0000FFFFull) << 16);
+    x = ((x & 0xFF00FF00FF00FF00ull) >> 8) | ((x & 0x00FF00FF00FF00FFull) << 8);
+    x = ((x & 0xF0F0F0F0F0F0F0F0ull) >> 4) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x & 0xCCCCCCCCCCCCCCCCull) >> 2) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
+#endif
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);     // bit-reversed pairs back in order
+}
+// base-5 code of the k (<= 27) two-bit digits in the low 2k bits of x (higher bits must be zero)
+PG_HD uint64_t pg_code5_of2(uint64_t x, const uint16_t *lut5) {
+    uint64_t c = lut5[(x >> 50) & 1023u];
+#pragma unroll
+    for (int g = 4; g >= 0; g--) c = c * 3125u + lut5[(x >> (10 * g)) & 1023u];
+    return c;
+}
+// forward and reverse-complement codes of the ACGT-only window whose digits start at bit 0 of `view`
+PG_HD void pg_codes_init_lut(uint64_t view, int k, const uint16_t *lut5, uint64_t &F, uint64_t &R) {
+    const uint64_t x = k < 32 ? (view & ((1ull << (2 * k)) - 1ull)) : view;
+    F = pg_code5_of2(x, lut5);
+    R = pg_code5_of2(pg_rev2(~x) >> (64 - 2 * k), lut5);      // digit i of the rc strand = 3 - d[k-1-i]
+}
+
 // Visit G consecutive interior positions (window index j0 .. j0+G-1, j0 + G <= 32): f(q, F, R, vw) with
 // vw = vf | vr << 16.  Every digit is a constant-shift field of three 64-bit views; codes roll with one
-// multiply each.  ``vlut``: the 16-word table above (shared memory), or nullptr to compute the values.
+// multiply each.  ``vlut``: the 16-word table above (shared memory), or nullptr to compute the values;
+// ``lut5``: the 1024-entry digit-group table (shared memory), or nullptr to run the digit loop.
 template <int G, class Fn>
-PG_HD void pg_interior_visit(const PgWindow &w, int j0, int k, uint64_t pow5km1, const uint32_t *vlut, Fn &&f) {
+PG_HD void pg_interior_visit(const PgWindow &w, int j0, int k, uint64_t pow5km1, const uint32_t *vlut, const uint16_t *lut5, Fn &&f) {
     const uint64_t dout64 = pg_win64(w, j0);
-    uint64_t F = 0, R = 0, p5 = 1;
-    for (int i = 0; i < k; i++) {
-        uint32_t d = (uint32_t)(dout64 >> (2 * i)) & 3u;      // k <= 27 digits: all inside the 64-bit view
-        F += (uint64_t)d * p5; R = R * 5 + (3u - d); p5 *= 5;
+    uint64_t F = 0, R = 0;
+    if (lut5) {
+        pg_codes_init_lut(dout64, k, lut5, F, R);
+    } else {
+        uint64_t p5 = 1;
+        for (int i = 0; i < k; i++) {
+            uint32_t d = (uint32_t)(dout64 >> (2 * i)) & 3u;      // k <= 27 digits: all inside the 64-bit view
+            F += (uint64_t)d * p5; R = R * 5 + (3u - d); p5 *= 5;
+        }
     }
     // the G per-position digit fields: 32-bit views are enough (and half the shift work) for G <= 16
     using view_t = typename PgView<(G <= 16)>::type;

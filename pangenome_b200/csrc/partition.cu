@@ -19,26 +19,37 @@
 
 namespace {
 
-constexpr int KP_G = 16;                               // positions per thread
-// CTA tile = THREADS x 16 positions: 256 threads (4096 positions, 88 KB of smem, 2 CTAs/SM) for the
-// single-GPU path; 512 threads (8192 positions, one CTA per SM) when buckets are peer memory - twice
+constexpr int KP_G = 16;                               // positions (K2a) / records (K2b) per thread
+// CTA tile = THREADS x 16 positions: 256 threads (4096 positions, 75 KB of smem, 3 CTAs/SM) for local
+// buckets; 512 threads (8192 positions, one CTA per SM) when buckets are peer memory - twice
 // the run length per bucket on NVLink (2 GPUs: K2a + exchange 0.85 ms against 0.92 ms with 256 threads)
 constexpr int KP_MAX_PARTS = 1024;
+constexpr uint16_t NOREC = 0xFFFFu;
+
+// Where a tile's sorted records go.  Bucket i holds part_cap records; local bucket sets carry one more
+// bucket of spill_cap records at index n_parts (the SPILL): a record whose bucket is full goes there instead
+// of being dropped, so hash skew (one k-mer making up a visible share of the input: poly-A, satellites) costs
+// nothing but a few scattered stores.  part_counts[i] counts everything PRODUCED for bucket i (it may exceed
+// part_cap: the surplus went to the spill), part_counts[n_parts] what was offered to the spill.
+struct BucketOut {
+    uint4 *records; int64_t part_cap, spill_cap; unsigned long long *part_counts; int n_parts, sub_bits;
+    // fused exchange: when `peers` is set, bucket (owner, sub) is written straight into rank `owner`'s
+    // receive buffer over NVLink (peer-mapped pointer), at the slice reserved for source rank `my_rank`
+    uint4 *const *peers; int my_rank;
+};
 
 struct PartArgs {
     const uint64_t *pk2; const uint32_t *amb; int64_t n_words;
     const int64_t *seq_off; int64_t n_rec, g_begin, g_end; int k; uint64_t pow5km1;
     int64_t t_first, n_tiles;
-    int sub_bits, owner_bits; int n_parts;
-    uint4 *records; int64_t part_cap; unsigned long long *part_counts;
-    // fused exchange: when `peers` is set, bucket (owner, sub) is written straight into rank `owner`'s
-    // receive buffer over NVLink (peer-mapped pointer), at the slice reserved for source rank `my_rank`
-    uint4 *const *peers; int my_rank;
+    int owner_bits;
+    BucketOut out;
     // distinct-key estimator: keys whose mix has bits 8..15 == 0 (a 1/256 sample of the KEY space, so every
     // occurrence of a sampled key is sampled) go into a small CAS set; 256 x its size estimates the table
     uint64_t *sample_keys; uint64_t sample_mask; unsigned long long *sample_count;
     // device-side arguments: when set, n_rec / the stream range come from K1's count block and record
-    // index ON THE DEVICE, so the host can enqueue K1 -> K2a -> K3 without waiting for K1's result
+    // index ON THE DEVICE, so the host can enqueue K1 -> K2a -> K3 without waiting for K1's result;
+    // g_begin / g_end are then offsets RELATIVE to the first record (one round of a multi-round build)
     const int64_t *d_counts; int64_t cap_records;
 };
 
@@ -61,12 +72,137 @@ __device__ __forceinline__ void sample_key(const PartArgs &a, uint64_t key, uint
 template <bool GENERAL>
 __device__ __forceinline__ uint32_t part_of(const PartArgs &a, uint64_t key) {
     uint64_t h = pg_mix64(key);
-    uint32_t sub = a.sub_bits ? (uint32_t)(h >> (64 - a.sub_bits)) : 0u;      // hash prefix = table region (tv_home)
+    uint32_t sub = a.out.sub_bits ? (uint32_t)(h >> (64 - a.out.sub_bits)) : 0u;      // hash prefix = table region (tv_home)
     if (!GENERAL) return sub;
     if (a.sample_keys && ((h >> 8) & 0xFFu) == 0) sample_key(a, key, h);
     uint32_t owner = a.owner_bits ? (uint32_t)(h & ((1u << a.owner_bits) - 1u)) : 0u;   // low bits: disjoint from the slot bits
-    return (owner << a.sub_bits) | sub;
+    return (owner << a.out.sub_bits) | sub;
 }
+
+// ---- the counting sort of one CTA tile, shared by K2a (records computed from the sequence) and K2b
+// (records re-read from coarse buckets).  Staging: MAXR records of 12 bytes (the key, and the masks with the
+// increment (1 or 2) folded into bit 31 - shared memory is what limits the CTAs per SM), their bucket ids,
+// the permutation, and per bucket: histogram, tile offset, ticket, room, global base, destination pointer.
+template <int MAXR>
+struct TileSort {
+    uint64_t *s_key; uint32_t *s_mi; uint16_t *s_pid, *s_perm;
+    uint32_t *s_hist, *s_off, *s_tick, *s_room; unsigned long long *s_base; uint4 **s_dst;
+    __device__ __forceinline__ void carve(unsigned char *smem, int n_parts) {
+        s_key = reinterpret_cast<uint64_t *>(smem);
+        s_mi = reinterpret_cast<uint32_t *>(s_key + MAXR);
+        s_pid = reinterpret_cast<uint16_t *>(s_mi + MAXR);             // MAXR bucket ids (NOREC = slot unused)
+        s_perm = s_pid + MAXR;                                         // sorted index -> natural index
+        s_hist = reinterpret_cast<uint32_t *>(s_perm + MAXR);          // n_parts
+        s_off = s_hist + n_parts;                                      // n_parts: exclusive offsets
+        s_tick = s_off + n_parts;                                      // n_parts: tickets
+        s_room = s_tick + n_parts;                                     // n_parts: records of this tile the bucket can still take
+        s_base = reinterpret_cast<unsigned long long *>(s_room + n_parts);
+        s_dst = reinterpret_cast<uint4 **>(s_base + n_parts);          // n_parts: address of sorted position 0
+    }
+    static int bytes(int n_parts) { return MAXR * 12 + MAXR * 2 * 2 + 4 * n_parts * 4 + 2 * n_parts * 8 + 16; }
+    __device__ __forceinline__ void emit(int slot, uint32_t pid, uint64_t key, uint32_t masks, uint32_t inc) const {
+        s_key[slot] = key;
+        s_mi[slot] = masks | ((inc - 1u) << 31);
+        s_pid[slot] = (uint16_t)pid;
+        atomicAdd(&s_hist[pid], 1u);
+    }
+    __device__ __forceinline__ uint4 record(uint32_t i) const {
+        const uint64_t key = s_key[i];
+        const uint32_t mi = s_mi[i];
+        return make_uint4((uint32_t)key, (uint32_t)(key >> 32), mi & 0x7FFFFFFFu, 1u + (mi >> 31));
+    }
+    __device__ __forceinline__ void reset(int n_parts, int threads) const {
+        for (int i = threadIdx.x; i < n_parts; i += threads) { s_hist[i] = 0; s_tick[i] = 0; }
+    }
+
+    // Phases 2-4 (after a barrier that follows the emits): reserve space with one global atomicAdd per bucket
+    // per tile, scan the histogram, build the permutation, write coalesced runs.  All threads must call.
+    template <int THREADS>
+    __device__ __forceinline__ void sort_write(const BucketOut &o, uint32_t *s_chunk, uint32_t *s_nrec, uint64_t pol) const {
+        const int n_parts = o.n_parts;
+        {
+            const int lane = threadIdx.x & 31;
+            for (int base = 0; base < n_parts; base += THREADS) {
+                const int i = base + threadIdx.x;
+                uint32_t h = i < n_parts ? s_hist[i] : 0;
+                if (i < n_parts) s_base[i] = h ? atomicAdd(o.part_counts + i, (unsigned long long)h) : 0ull;
+                uint32_t inc = h;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+                if (i < n_parts) s_off[i] = inc - h;                         // offset inside its 32-bucket chunk
+                if (lane == 31) s_chunk[i >> 5] = inc;                       // chunk total (chunks past n_parts hold 0)
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {       // exclusive scan of the <= 32 chunk totals
+            const int nchunk = (n_parts + 31) >> 5;
+            uint32_t v = (int)threadIdx.x < nchunk ? s_chunk[threadIdx.x] : 0, inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if ((int)threadIdx.x >= d) inc += y; }
+            s_chunk[threadIdx.x] = inc - v;
+            if (threadIdx.x == 31) *s_nrec = inc;
+        }
+        __syncthreads();
+        // final offsets, and per bucket the address its sorted position 0 would map to: record at sorted
+        // position p goes to s_dst[pid][p] (its run in the bucket starts at s_base, its run in the tile at s_off)
+        for (int i = threadIdx.x; i < n_parts; i += THREADS) {
+            const uint32_t off = s_off[i] + s_chunk[i >> 5];
+            s_off[i] = off;
+            uint4 *bucket;
+            if (o.peers) {     // [source rank][sub][part_cap] in the owner's memory: the layout an all-to-all would produce
+                const uint32_t owner = (uint32_t)i >> o.sub_bits, sub = (uint32_t)i & ((1u << o.sub_bits) - 1u);
+                bucket = o.peers[owner] + (((int64_t)o.my_rank << o.sub_bits) + sub) * o.part_cap;
+            } else {
+                bucket = o.records + (int64_t)i * o.part_cap;
+            }
+            const unsigned long long base = s_base[i];
+            s_dst[i] = bucket + ((int64_t)base - (int64_t)off);
+            // records of this tile that still fit the bucket (the rest go to the spill; without one they are dropped
+            // and the host sees the overflow in part_counts)
+            const int64_t room = o.part_cap - (int64_t)base;
+            s_room[i] = room <= 0 ? 0u : (room > 0xFFFF ? 0xFFFFu : (uint32_t)room);
+        }
+        __syncthreads();
+        const uint32_t nrec = *s_nrec;
+        if (nrec == 0) return;
+        // ---- 3. permutation: sorted position -> natural index ------------------------------------
+        for (uint32_t i = threadIdx.x; i < (uint32_t)MAXR; i += THREADS) {
+            const uint32_t pid = s_pid[i];
+            if (pid == NOREC) continue;
+            const uint32_t rank = atomicAdd(&s_tick[pid], 1u);
+            const bool fits = rank < s_room[pid];
+            s_perm[s_off[pid] + rank] = fits ? (uint16_t)i : NOREC;
+            if (!fits && o.spill_cap > 0) {            // rare: the bucket is full - one scattered store into the spill
+                const unsigned long long at = atomicAdd(o.part_counts + n_parts, 1ull);
+                if ((int64_t)at < o.spill_cap) o.records[(int64_t)n_parts * o.part_cap + (int64_t)at] = record(i);
+            }
+        }
+        __syncthreads();
+        // ---- 4. coalesced write-out: consecutive threads write consecutive records of one bucket; four
+        // independent chains (perm -> bucket id -> address, record) per thread hide the shared-memory latency
+        const bool remote = o.peers != nullptr;
+        for (uint32_t o0 = threadIdx.x; o0 < nrec; o0 += 4 * THREADS) {
+            uint32_t idx[4]; uint4 *dst[4]; uint4 rec[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t p = o0 + j * THREADS;
+                idx[j] = p < nrec ? (uint32_t)s_perm[p] : (uint32_t)NOREC;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (idx[j] != NOREC) {
+                    dst[j] = s_dst[s_pid[idx[j]]] + (o0 + j * THREADS);
+                    rec[j] = record(idx[j]);
+                }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (idx[j] != NOREC) {
+                    if (remote) *dst[j] = rec[j];
+                    else pg_st_stream_l2first(dst[j], rec[j], pol);
+                }
+        }
+    }
+};
 
 template <int MODE, int KP_THREADS, bool GENERAL>
 __global__ void __launch_bounds__(KP_THREADS, KP_THREADS == 256 ? 3 : 1)
@@ -75,45 +211,35 @@ k2a_partition(PartArgs a) {
     if (a.d_counts) {      // all records of the packed stream, bounds read from the device
         const int64_t n_rec = a.d_counts[0];
         if (n_rec > a.cap_records) {          // the record index was truncated: poison bucket 0, the host falls back
-            if (blockIdx.x == 0 && threadIdx.x == 0) a.part_counts[0] = 1ull << 62;
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                a.out.part_counts[0] = 1ull << 62;
+                if (a.out.spill_cap > 0) a.out.part_counts[a.out.n_parts] = 1ull << 62;      // a spill would absorb bucket 0's "overflow"
+            }
             return;
         }
         a.n_rec = n_rec;
-        a.g_begin = n_rec > 0 ? a.seq_off[0] : 0;
-        a.g_end = n_rec > 0 ? a.seq_off[n_rec] : 0;
-        a.n_words = ((a.g_end + 31) >> 5) + 4;
+        const int64_t s0 = n_rec > 0 ? a.seq_off[0] : 0, s1 = n_rec > 0 ? a.seq_off[n_rec] : 0;
+        const int64_t lo = s0 + a.g_begin, hi = s0 + a.g_end;          // this round's slice of [s0, s1)
+        a.g_begin = lo < s1 ? lo : s1;
+        a.g_end = (a.g_end < 0 || hi > s1) ? s1 : hi;                  // g_end < 0: to the end of the stream
+        a.n_words = ((s1 + 31) >> 5) + 4;
         a.t_first = a.g_begin / KP_TILE;
-        a.n_tiles = (a.g_end + KP_TILE - 1) / KP_TILE - a.t_first;
+        a.n_tiles = a.g_end > a.g_begin ? (a.g_end + KP_TILE - 1) / KP_TILE - a.t_first : 0;
     }
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int RPP = (MODE == PG_MODE_LITERAL_RC) ? 2 : 1;               // records per position
     constexpr int MAXR = KP_TILE * RPP;
-    constexpr uint16_t NOREC = 0xFFFFu;
-    // MAXR staged records, 12 bytes each (shared memory is what limits the CTAs per SM): the key, and the masks
-    // with the increment (1 or 2) folded into bit 31
-    uint64_t *s_key = reinterpret_cast<uint64_t *>(smem);
-    uint32_t *s_mi = reinterpret_cast<uint32_t *>(s_key + MAXR);
-    uint16_t *s_pid = reinterpret_cast<uint16_t *>(s_mi + MAXR);             // MAXR bucket ids (NOREC = slot unused)
-    uint16_t *s_perm = s_pid + MAXR;                                         // sorted index -> natural index
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_perm + MAXR);          // n_parts
-    uint32_t *s_off = s_hist + a.n_parts;                                    // n_parts: exclusive offsets
-    uint32_t *s_tick = s_off + a.n_parts;                                    // n_parts: tickets
-    uint32_t *s_room = s_tick + a.n_parts;                                   // n_parts: records of this tile the bucket can still take
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_room + a.n_parts);
-    uint4 **s_dst = reinterpret_cast<uint4 **>(s_base + a.n_parts);          // n_parts: address of sorted position 0
+    TileSort<MAXR> ts;
+    ts.carve(smem, a.out.n_parts);
     __shared__ uint32_t s_nrec;
     __shared__ uint32_t s_chunk[32];
     const uint64_t pol = pg_policy_evict_first();
     __shared__ uint32_t s_vlut[16];
+    __shared__ uint16_t s_lut5[PG_LUT5_SIZE];
     if (threadIdx.x < 16) s_vlut[threadIdx.x] = pg_vlut_entry(threadIdx.x);      // visible after the tile loop's first barrier
+    for (int i = threadIdx.x; i < PG_LUT5_SIZE; i += KP_THREADS) s_lut5[i] = (uint16_t)pg_lut5_entry(i);
 
-    auto emit = [&](int slot, uint64_t key, uint32_t masks, uint32_t inc) {
-        uint32_t pid = part_of<GENERAL>(a, key);
-        s_key[slot] = key;
-        s_mi[slot] = masks | ((inc - 1u) << 31);
-        s_pid[slot] = (uint16_t)pid;
-        atomicAdd(&s_hist[pid], 1u);
-    };
+    auto emit = [&](int slot, uint64_t key, uint32_t masks, uint32_t inc) { ts.emit(slot, part_of<GENERAL>(a, key), key, masks, inc); };
     // staging slot of this thread's q-th position: consecutive lanes take consecutive slots, so the 16-byte
     // record stores of a warp fall into distinct banks (a [thread][q] layout costs 8 wavefronts per store)
     auto emit_pos = [&](int q, uint64_t F, uint64_t R, uint32_t vw) {      // vw = vf | vr << 16
@@ -129,7 +255,7 @@ k2a_partition(PartArgs a) {
 
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         __syncthreads();
-        for (int i = threadIdx.x; i < a.n_parts; i += KP_THREADS) { s_hist[i] = 0; s_tick[i] = 0; }
+        ts.reset(a.out.n_parts, KP_THREADS);
         __syncthreads();
         // ---- 1. compute this thread's records ------------------------------------------------
         const int64_t g0 = (a.t_first + tile) * KP_TILE + (int64_t)threadIdx.x * KP_G;
@@ -145,7 +271,7 @@ k2a_partition(PartArgs a) {
             const int k = a.k;
             if (pg_is_interior(w, g0, KP_G, k, rs, re, r >= 0, a.g_begin, a.g_end)) {
                 // ---- fast path: 16 ACGT positions strictly inside one record (kmer_core.cuh)
-                pg_interior_visit<KP_G>(w, j0, k, a.pow5km1, s_vlut, emit_pos);
+                pg_interior_visit<KP_G>(w, j0, k, a.pow5km1, s_vlut, s_lut5, emit_pos);
                 done = true;
             } else {
                 // ---- generic path: record edges, ambiguity codes, range ends (all the quirks) ----
@@ -165,7 +291,7 @@ k2a_partition(PartArgs a) {
                         pg_occ_vals(w, j, g - rs, re - rs, k, vf, vr);
                         emit_pos(q, F, R, vf | (vr << 16));
                     } else {
-                        for (int e = 0; e < RPP; e++) s_pid[e * KP_TILE + q * KP_THREADS + threadIdx.x] = NOREC;
+                        for (int e = 0; e < RPP; e++) ts.s_pid[e * KP_TILE + q * KP_THREADS + threadIdx.x] = NOREC;
                     }
                     pg_codes_roll(w, j, k, a.pow5km1, F, R);
                 }
@@ -173,90 +299,99 @@ k2a_partition(PartArgs a) {
             }
         }
         if (!done)
-            for (int e = 0; e < KP_G * RPP; e++) s_pid[e * KP_THREADS + threadIdx.x] = NOREC;
+            for (int e = 0; e < KP_G * RPP; e++) ts.s_pid[e * KP_THREADS + threadIdx.x] = NOREC;
         __syncthreads();
-        // ---- 2. reserve space: one global atomicAdd per bucket per tile (all in flight at once, every
-        // thread owns buckets tid, tid+128, ..) and local exclusive offsets by a block scan of the histogram
-        {
-            const int lane = threadIdx.x & 31;
-            uint32_t run = 0;       // exclusive prefix of the 32-bucket chunks this thread has seen (same for the whole warp)
-            for (int base = 0; base < a.n_parts; base += KP_THREADS) {
-                const int i = base + threadIdx.x;
-                uint32_t h = i < a.n_parts ? s_hist[i] : 0;
-                if (i < a.n_parts) s_base[i] = h ? atomicAdd(a.part_counts + i, (unsigned long long)h) : 0ull;
-                uint32_t inc = h;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-                if (i < a.n_parts) s_off[i] = inc - h;                       // offset inside its 32-bucket chunk
-                if (lane == 31) s_chunk[i >> 5] = inc;                       // chunk total (chunks past n_parts hold 0)
-                (void)run;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {       // exclusive scan of the <= 32 chunk totals
-            const int nchunk = (a.n_parts + 31) >> 5;
-            uint32_t v = (int)threadIdx.x < nchunk ? s_chunk[threadIdx.x] : 0, inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += y; }
-            s_chunk[threadIdx.x] = inc - v;
-            if (threadIdx.x == 31) s_nrec = inc;
-        }
-        __syncthreads();
-        // final offsets, and per bucket the address its sorted position 0 would map to: record at sorted
-        // position o goes to s_dst[pid][o] (its run in the bucket starts at s_base, its run in the tile at s_off)
-        for (int i = threadIdx.x; i < a.n_parts; i += KP_THREADS) {
-            const uint32_t off = s_off[i] + s_chunk[i >> 5];
-            s_off[i] = off;
-            uint4 *bucket;
-            if (a.peers) {     // [source rank][sub][part_cap] in the owner's memory: the layout an all-to-all would produce
-                const uint32_t owner = (uint32_t)i >> a.sub_bits, sub = (uint32_t)i & ((1u << a.sub_bits) - 1u);
-                bucket = a.peers[owner] + (((int64_t)a.my_rank << a.sub_bits) + sub) * a.part_cap;
-            } else {
-                bucket = a.records + (int64_t)i * a.part_cap;
-            }
-            const unsigned long long base = s_base[i];
-            s_dst[i] = bucket + ((int64_t)base - (int64_t)off);
-            // records of this tile that still fit the bucket (the host sees the overflow in part_counts)
-            const int64_t room = a.part_cap - (int64_t)base;
-            s_room[i] = room <= 0 ? 0u : (room > 0xFFFF ? 0xFFFFu : (uint32_t)room);
-        }
-        __syncthreads();
-        const uint32_t nrec = s_nrec;
-        if (nrec == 0) continue;
-        // ---- 3. permutation: sorted position -> natural index ------------------------------------
-        for (uint32_t i = threadIdx.x; i < (uint32_t)MAXR; i += KP_THREADS) {
-            uint32_t pid = s_pid[i];
-            if (pid == NOREC) continue;
-            const uint32_t rank = atomicAdd(&s_tick[pid], 1u);
-            s_perm[s_off[pid] + rank] = rank < s_room[pid] ? (uint16_t)i : NOREC;
-        }
-        __syncthreads();
-        // ---- 4. coalesced write-out: consecutive threads write consecutive records of one bucket; four
-        // independent chains (perm -> bucket id -> address, record) per thread hide the shared-memory latency
-        const bool remote = a.peers != nullptr;
-        for (uint32_t o0 = threadIdx.x; o0 < nrec; o0 += 4 * KP_THREADS) {
-            uint32_t idx[4]; uint4 *dst[4]; uint4 rec[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t o = o0 + j * KP_THREADS;
-                idx[j] = o < nrec ? (uint32_t)s_perm[o] : (uint32_t)NOREC;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (idx[j] != NOREC) {
-                    dst[j] = s_dst[s_pid[idx[j]]] + (o0 + j * KP_THREADS);
-                    const uint64_t key = s_key[idx[j]];
-                    const uint32_t mi = s_mi[idx[j]];
-                    rec[j] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), mi & 0x7FFFFFFFu, 1u + (mi >> 31));
-                }
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (idx[j] != NOREC) {
-                    if (remote) *dst[j] = rec[j];
-                    else pg_st_stream_l2first(dst[j], rec[j], pol);
-                }
-        }
+        ts.template sort_write<KP_THREADS>(a.out, s_chunk, &s_nrec, pol);
     }
+}
+
+// K2b: split coarse buckets into table regions.  On the multi-GPU path records cross NVLink bucketed by OWNER
+// only (long runs: a 8192-position tile gives 1024-record = 16 KB runs per peer instead of 512-byte ones), and the
+// receiver sorts what arrived - n_seg segments, one per source rank - into the 2^sub_bits hash-prefix regions K3
+// sweeps.  Same counting sort as K2a, the records are simply re-read instead of computed: 32 B of HBM traffic per
+// record.  Also what keeps a region inside L2 when a table needs more regions than one K2a pass can address.
+struct SplitArgs {
+    const uint4 *in; const int64_t *seg_off, *seg_cnt; int n_seg; int64_t seg_cap;
+    BucketOut out;
+    int64_t *stats;        // optional table statistics: PG_STAT_LOST is raised when an input segment claims more than seg_cap
+};
+constexpr int KB_THREADS = 256;
+constexpr int KB_MAX_SEG = 64;
+__global__ void __launch_bounds__(KB_THREADS, 3)
+k2b_split(SplitArgs a) {
+    constexpr int KB_TILE = KB_THREADS * KP_G;
+    extern __shared__ __align__(16) unsigned char smem[];
+    TileSort<KB_TILE> ts;
+    ts.carve(smem, a.out.n_parts);
+    __shared__ uint32_t s_nrec;
+    __shared__ uint32_t s_chunk[32];
+    __shared__ long long s_tile0[KB_MAX_SEG + 1];       // first tile of every segment (exclusive prefix of ceil(cnt / tile))
+    const uint64_t pol = pg_policy_evict_first();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int s = 0; s < a.n_seg; s++) {
+            long long c = a.seg_cnt[s];
+            if (c > a.seg_cap) {       // the sender dropped records (its wire bucket overflowed): never read past the segment
+                if (blockIdx.x == 0 && a.stats) atomicExch(reinterpret_cast<unsigned long long *>(a.stats + PG_STAT_LOST), 1ull);
+                c = a.seg_cap;
+            }
+            if (c < 0) c = 0;
+            s_tile0[s] = t; t += (c + KB_TILE - 1) / KB_TILE;
+        }
+        s_tile0[a.n_seg] = t;
+    }
+    __syncthreads();
+    const long long n_tiles = s_tile0[a.n_seg];
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        ts.reset(a.out.n_parts, KB_THREADS);
+        int seg = 0;
+        while (seg + 1 < a.n_seg && tile >= s_tile0[seg + 1]) seg++;
+        long long cnt = a.seg_cnt[seg]; if (cnt > a.seg_cap) cnt = a.seg_cap;
+        const long long i0 = (tile - s_tile0[seg]) * KB_TILE;
+        const uint4 *src = a.in + a.seg_off[seg] + i0;
+        const long long left = cnt - i0;                   // records of this tile: min(left, KB_TILE)
+        __syncthreads();
+        // two batches of eight 16-byte loads in flight per thread (sixteen would spill at 3 CTAs per SM)
+#pragma unroll
+        for (int h = 0; h < KP_G; h += 8) {
+            uint4 r[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int slot = (h + q) * KB_THREADS + threadIdx.x;
+                if (slot < left) r[q] = pg_ld_stream_l2first(src + slot, pol);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int slot = (h + q) * KB_THREADS + threadIdx.x;
+                if (slot < left) {
+                    const uint64_t key = (uint64_t)r[q].x | ((uint64_t)r[q].y << 32);
+                    const uint32_t pid = a.out.sub_bits ? (uint32_t)(pg_mix64(key) >> (64 - a.out.sub_bits)) : 0u;
+                    ts.emit(slot, pid, key, r[q].z, r[q].w);
+                } else {
+                    ts.s_pid[slot] = NOREC;
+                }
+            }
+        }
+        __syncthreads();
+        ts.template sort_write<KB_THREADS>(a.out, s_chunk, &s_nrec, pol);
+    }
+}
+
+// What K3 sweeps after K2a / K2b filled a local bucket set: per-bucket counts clamped to the capacities (the
+// spill is region n_parts), and the sticky PG_STAT_LOST flag when records were dropped - a bucket overflowed
+// without a spill, or the spill itself overflowed.  One tiny CTA; keeps the step free of host read-backs.
+__global__ void k_buckets_plan(const unsigned long long *__restrict__ counts, int n_parts, int64_t part_cap, int64_t spill_cap,
+                               int64_t *__restrict__ seg_cnt, int64_t *stats) {
+    bool lost = false;
+    for (int i = threadIdx.x; i <= n_parts; i += blockDim.x) {
+        const unsigned long long c = counts[i];
+        const int64_t cap = i < n_parts ? part_cap : spill_cap;
+        if (i < n_parts) { if (spill_cap <= 0 && c > (unsigned long long)part_cap) lost = true; }
+        else if (c > (unsigned long long)(spill_cap > 0 ? spill_cap : 0)) lost = true;
+        seg_cnt[i] = c > (unsigned long long)cap ? cap : (int64_t)c;
+    }
+    if (lost && stats) atomicExch(reinterpret_cast<unsigned long long *>(stats + PG_STAT_LOST), 1ull);
 }
 
 // K3: insert update records region by region.  The records of table region b arrive as n_src
@@ -303,39 +438,60 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
 
 int part_smem_bytes(int mode, int n_parts, int threads) {
     int maxr = (mode == PG_MODE_LITERAL_RC ? 2 : 1) * threads * KP_G;
-    return maxr * 12 + maxr * 2 * 2 + 4 * n_parts * 4 + 2 * n_parts * 8 + 16;
+    return maxr * 12 + maxr * 2 * 2 + 4 * n_parts * 4 + 2 * n_parts * 8 + 16;       // == TileSort<maxr>::bytes(n_parts)
 }
 
 }  // namespace
 
+// Validate a caller's bucket set and turn it into the kernels' view.
+static int make_bucket_out(const pg_bucket_set *b, const char *who, BucketOut &o) {
+    if (!b || !b->d_part_counts || b->part_cap < 1 || b->spill_cap < 0 || b->owner_bits < 0 || b->owner_bits > 6 || b->sub_bits < 0 ||
+        b->sub_bits > 10 || (1 << (b->owner_bits + b->sub_bits)) > KP_MAX_PARTS)
+        return pg_fail(PG_ERR_INVALID, "%s: bad bucket set (owner_bits 0..6, sub_bits 0..10, at most %d buckets)", who, KP_MAX_PARTS);
+    if (!b->d_records == !b->d_peer_bases) return pg_fail(PG_ERR_INVALID, "%s: exactly one of d_records / d_peer_bases must be set", who);
+    if (b->d_peer_bases && (b->spill_cap != 0 || b->my_rank < 0 || b->my_rank >= (1 << b->owner_bits)))
+        return pg_fail(PG_ERR_INVALID, "%s: peer bucket sets have no spill and need 0 <= my_rank < 2^owner_bits", who);
+    if (b->d_records && (reinterpret_cast<uintptr_t>(b->d_records) & 15)) return pg_fail(PG_ERR_INVALID, "%s: records must be 16-byte aligned", who);
+    o.records = reinterpret_cast<uint4 *>(b->d_records); o.part_cap = b->part_cap; o.spill_cap = b->spill_cap;
+    o.part_counts = reinterpret_cast<unsigned long long *>(b->d_part_counts);
+    o.n_parts = 1 << (b->owner_bits + b->sub_bits); o.sub_bits = b->sub_bits;
+    o.peers = reinterpret_cast<uint4 *const *>(b->d_peer_bases); o.my_rank = b->my_rank;
+    return PG_OK;
+}
+
+static int ctas_per_sm(int smem_dynamic, int smem_static) {
+    int per_sm = 227 * 1024 / (smem_dynamic + smem_static + 1024);      // 227 KB usable per SM, 1 KB reserved per CTA
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 12) per_sm = 12;
+    return per_sm;
+}
+
+// g_begin / g_end: absolute stream offsets, or - with d_counts - offsets relative to the first record (g_end < 0 = to the end)
 static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
-                            int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
-                            uint64_t *d_records, uint64_t *const *d_peers, int my_rank, int64_t part_cap,
-                            int64_t *d_part_counts, uint64_t *d_sample_keys, int64_t sample_cap, int64_t *d_sample_count,
+                            int64_t n_rec, int64_t g_begin, int64_t g_end, const pg_bucket_set *b, bool zero_counts,
+                            uint64_t *d_sample_keys, int64_t sample_cap, int64_t *d_sample_count,
                             const int64_t *d_counts, int64_t cap_records, int64_t max_bases, pg_stream_t stream_) {
     if (!t || t->k < 1 || t->k > 27 || t->mode < 0 || t->mode > 2)
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: bad table descriptor (only mode and k are used)");
-    if (!d_pk2 || !d_amb || !d_seq_off || (!d_records && !d_peers) || !d_part_counts || n_rec < 0 || g_begin < 0 || g_end < g_begin || part_cap < 1)
+    if (!d_pk2 || !d_amb || !d_seq_off || n_rec < 0 || g_begin < 0 || (!d_counts && g_end < g_begin))
         return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: bad arguments");
-    if (owner_bits < 0 || owner_bits > 6 || sub_bits < 0 || sub_bits > 10 || (1 << (owner_bits + sub_bits)) > KP_MAX_PARTS)
-        return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: owner_bits/sub_bits out of range");
-    cudaStream_t st = (cudaStream_t)stream_;
-    int n_parts = 1 << (owner_bits + sub_bits);
-    PG_CUDA(cudaMemsetAsync(d_part_counts, 0, (size_t)n_parts * 8, st));
-    if (d_counts) { n_rec = 1; g_begin = 0; g_end = max_bases > 0 ? max_bases : 1; }     // grid sizing only; the kernel reads the real values
-    if (n_rec == 0 || g_end == g_begin) return PG_OK;
     PartArgs a;
+    int rc = make_bucket_out(b, "pg_kmer_partition", a.out); if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int n_parts = a.out.n_parts;
+    if (zero_counts) PG_CUDA(cudaMemsetAsync(b->d_part_counts, 0, (size_t)(n_parts + 1) * 8, st));
+    int64_t span = g_end - g_begin;                                     // grid sizing only in device-argument mode
+    if (d_counts) { n_rec = 1; span = (g_end < 0 || g_end - g_begin > max_bases) ? max_bases - (g_begin < max_bases ? g_begin : max_bases) : g_end - g_begin; }
+    if (n_rec == 0 || span <= 0) return PG_OK;
     a.pk2 = reinterpret_cast<const uint64_t *>(d_pk2); a.amb = d_amb; a.n_words = ((g_end + 31) >> 5) + 4;
     a.seq_off = d_seq_off; a.n_rec = n_rec; a.g_begin = g_begin; a.g_end = g_end; a.k = t->k; a.pow5km1 = pg_pow5(t->k - 1);
     static int thr_env = -1;
     if (thr_env < 0) { const char *e = getenv("PG_K2A_THREADS"); thr_env = e ? atoi(e) : 0; }
-    const int threads = (thr_env == 128 || thr_env == 256 || thr_env == 512) ? thr_env : (d_peers ? (t->mode == PG_MODE_LITERAL_RC ? 256 : 512) : 256);
+    const bool peer = b->d_peer_bases != nullptr;
+    const int threads = (thr_env == 128 || thr_env == 256 || thr_env == 512) ? thr_env : (peer ? (t->mode == PG_MODE_LITERAL_RC ? 256 : 512) : 256);
     const int tile = threads * KP_G;
-    a.t_first = g_begin / tile; a.n_tiles = (g_end + tile - 1) / tile - a.t_first;
-    a.sub_bits = sub_bits; a.owner_bits = owner_bits; a.n_parts = n_parts;
-    a.records = reinterpret_cast<uint4 *>(d_records); a.part_cap = part_cap;
-    a.peers = reinterpret_cast<uint4 *const *>(d_peers); a.my_rank = my_rank;
-    a.part_counts = reinterpret_cast<unsigned long long *>(d_part_counts);
+    a.t_first = g_begin / tile; a.n_tiles = (g_begin + span + tile - 1) / tile - a.t_first;
+    a.owner_bits = b->owner_bits;
     a.d_counts = d_counts; a.cap_records = cap_records;
     a.sample_keys = nullptr; a.sample_mask = 0; a.sample_count = nullptr;
     if (d_sample_keys) {
@@ -345,10 +501,10 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
         a.sample_count = reinterpret_cast<unsigned long long *>(d_sample_count);
     }
     int smem = part_smem_bytes(t->mode, n_parts, threads);
-    int per_sm = 227 * 1024 / (smem + 1024);      // 227 KB usable per SM, 1 KB reserved per CTA if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
-    int64_t maxg = (int64_t)pg_num_sms() * per_sm;
+    int64_t maxg = (int64_t)pg_num_sms() * ctas_per_sm(smem, 2048 + 256);      // static: the 2 KB digit-group table + small arrays
     int grid = (int)(a.n_tiles < maxg ? a.n_tiles : maxg);
-    const bool general = a.sample_keys != nullptr || owner_bits > 0;
+    if (grid < 1) grid = 1;
+    const bool general = a.sample_keys != nullptr || b->owner_bits > 0;
 #define K2A_LAUNCH(M, T)                                                                                                    \
     do {                                                                                                                    \
         if (general) {                                                                                                      \
@@ -377,12 +533,34 @@ static int partition_launch(const pg_table *t, const uint32_t *d_pk2, const uint
     return PG_OK;
 }
 
+static pg_bucket_set local_set(uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, int owner_bits, int sub_bits) {
+    pg_bucket_set b;
+    b.d_records = d_records; b.d_peer_bases = nullptr; b.d_part_counts = d_part_counts; b.part_cap = part_cap; b.spill_cap = 0;
+    b.owner_bits = owner_bits; b.sub_bits = sub_bits; b.my_rank = 0; b.reserved = 0;
+    return b;
+}
+static pg_bucket_set peer_set(uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts, int owner_bits, int sub_bits) {
+    pg_bucket_set b = local_set(nullptr, part_cap, d_part_counts, owner_bits, sub_bits);
+    b.d_peer_bases = d_peer_bases; b.my_rank = my_rank;
+    return b;
+}
+
+// NB the classic entry points keep their contract: d_part_counts has n_parts counters (no spill counter), so the
+// memset there covers n_parts words only
+static int classic_zero(int64_t *d_part_counts, int owner_bits, int sub_bits, pg_stream_t stream_) {
+    if (!d_part_counts || owner_bits < 0 || sub_bits < 0 || owner_bits + sub_bits > 10) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition: bad arguments");
+    PG_CUDA(cudaMemsetAsync(d_part_counts, 0, (size_t)(1 << (owner_bits + sub_bits)) * 8, (cudaStream_t)stream_));
+    return PG_OK;
+}
+
 extern "C" int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                                  int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
                                  uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, uint64_t *d_sample_keys,
                                  int64_t sample_cap, int64_t *d_sample_count, pg_stream_t stream_) {
-    return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, owner_bits, sub_bits, d_records, nullptr, 0,
-                            part_cap, d_part_counts, d_sample_keys, sample_cap, d_sample_count, nullptr, 0, 0, stream_);
+    int rc = classic_zero(d_part_counts, owner_bits, sub_bits, stream_); if (rc) return rc;
+    pg_bucket_set b = local_set(d_records, part_cap, d_part_counts, owner_bits, sub_bits);
+    return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, &b, false, d_sample_keys, sample_cap, d_sample_count,
+                            nullptr, 0, 0, stream_);
 }
 
 // Same as pg_kmer_partition over ALL records of a packed stream, but n_rec and the stream range are read on
@@ -391,18 +569,19 @@ extern "C" int pg_kmer_partition_dev(const pg_table *t, const uint32_t *d_pk2, c
                                      const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
                                      uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream_) {
     if (!d_counts || cap_records < 0 || max_bases < 0) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_dev: bad arguments");
-    return partition_launch(t, d_pk2, d_amb, d_seq_off, 1, 0, 1, owner_bits, sub_bits, d_records, nullptr, 0,
-                            part_cap, d_part_counts, nullptr, 0, nullptr, d_counts, cap_records, max_bases, stream_);
+    int rc = classic_zero(d_part_counts, owner_bits, sub_bits, stream_); if (rc) return rc;
+    pg_bucket_set b = local_set(d_records, part_cap, d_part_counts, owner_bits, sub_bits);
+    return partition_launch(t, d_pk2, d_amb, d_seq_off, 1, 0, -1, &b, false, nullptr, 0, nullptr, d_counts, cap_records, max_bases, stream_);
 }
 
 extern "C" int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                                      int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
                                      uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
                                      pg_stream_t stream_) {
-    if (!d_peer_bases || my_rank < 0 || my_rank >= (1 << owner_bits))
-        return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p: bad peer table / rank");
-    return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, owner_bits, sub_bits, nullptr, d_peer_bases, my_rank,
-                            part_cap, d_part_counts, nullptr, 0, nullptr, nullptr, 0, 0, stream_);
+    if (!d_peer_bases) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p: bad peer table");
+    int rc = classic_zero(d_part_counts, owner_bits, sub_bits, stream_); if (rc) return rc;
+    pg_bucket_set b = peer_set(d_peer_bases, my_rank, part_cap, d_part_counts, owner_bits, sub_bits);
+    return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, &b, false, nullptr, 0, nullptr, nullptr, 0, 0, stream_);
 }
 
 // pg_kmer_partition_p2p with device-side bounds (see pg_kmer_partition_dev): the multi-GPU step without a host read-back
@@ -410,11 +589,50 @@ extern "C" int pg_kmer_partition_p2p_dev(const pg_table *t, const uint32_t *d_pk
                                          const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
                                          uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
                                          pg_stream_t stream_) {
-    if (!d_counts || cap_records < 0 || max_bases < 0) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p_dev: bad arguments");
-    if (!d_peer_bases || my_rank < 0 || my_rank >= (1 << owner_bits))
-        return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p_dev: bad peer table / rank");
-    return partition_launch(t, d_pk2, d_amb, d_seq_off, 1, 0, 1, owner_bits, sub_bits, nullptr, d_peer_bases, my_rank,
-                            part_cap, d_part_counts, nullptr, 0, nullptr, d_counts, cap_records, max_bases, stream_);
+    if (!d_counts || cap_records < 0 || max_bases < 0 || !d_peer_bases) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p_dev: bad arguments");
+    int rc = classic_zero(d_part_counts, owner_bits, sub_bits, stream_); if (rc) return rc;
+    pg_bucket_set b = peer_set(d_peer_bases, my_rank, part_cap, d_part_counts, owner_bits, sub_bits);
+    return partition_launch(t, d_pk2, d_amb, d_seq_off, 1, 0, -1, &b, false, nullptr, 0, nullptr, d_counts, cap_records, max_bases, stream_);
+}
+
+// ---- bucket-set API: rounds, spill, receiver-side split (the streaming builders) ---------------------------
+extern "C" int pg_kmer_partition_to(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                                    int64_t n_rec, int64_t g_begin, int64_t g_end, const int64_t *d_counts, int64_t cap_records,
+                                    int64_t max_bases, const pg_bucket_set *out, uint64_t *d_sample_keys, int64_t sample_cap,
+                                    int64_t *d_sample_count, pg_stream_t stream_) {
+    if (d_counts && (cap_records < 0 || max_bases < 0)) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_to: bad device-argument sizes");
+    return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, out, true, d_sample_keys, sample_cap, d_sample_count,
+                            d_counts, cap_records, max_bases, stream_);
+}
+
+extern "C" int pg_records_split(const uint64_t *d_records_in, const int64_t *d_seg_off, const int64_t *d_seg_cnt, int n_seg,
+                                int64_t seg_cap, const pg_bucket_set *out, int64_t *d_table_stats, pg_stream_t stream_) {
+    SplitArgs a;
+    int rc = make_bucket_out(out, "pg_records_split", a.out); if (rc) return rc;
+    if (out->d_peer_bases || out->owner_bits != 0) return pg_fail(PG_ERR_INVALID, "pg_records_split: the output must be a local bucket set with owner_bits 0");
+    if (!d_records_in || !d_seg_off || !d_seg_cnt || n_seg < 1 || n_seg > KB_MAX_SEG || seg_cap < 1 || (reinterpret_cast<uintptr_t>(d_records_in) & 15))
+        return pg_fail(PG_ERR_INVALID, "pg_records_split: bad arguments (1..%d segments, 16-byte aligned records)", KB_MAX_SEG);
+    cudaStream_t st = (cudaStream_t)stream_;
+    PG_CUDA(cudaMemsetAsync(out->d_part_counts, 0, (size_t)(a.out.n_parts + 1) * 8, st));
+    a.in = reinterpret_cast<const uint4 *>(d_records_in); a.seg_off = d_seg_off; a.seg_cnt = d_seg_cnt; a.n_seg = n_seg; a.seg_cap = seg_cap;
+    a.stats = d_table_stats;
+    const int smem = TileSort<KB_THREADS * KP_G>::bytes(a.out.n_parts);
+    PG_CUDA(cudaFuncSetAttribute(k2b_split, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t max_tiles = (int64_t)n_seg * ((seg_cap + KB_THREADS * KP_G - 1) / (KB_THREADS * KP_G));
+    int64_t maxg = (int64_t)pg_num_sms() * ctas_per_sm(smem, 1024);
+    int grid = (int)(max_tiles < maxg ? max_tiles : maxg);
+    k2b_split<<<grid < 1 ? 1 : grid, KB_THREADS, smem, st>>>(a);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_buckets_plan(const pg_bucket_set *b, int64_t *d_seg_cnt, int64_t *d_table_stats, pg_stream_t stream_) {
+    BucketOut o;
+    int rc = make_bucket_out(b, "pg_buckets_plan", o); if (rc) return rc;
+    if (b->d_peer_bases || !d_seg_cnt) return pg_fail(PG_ERR_INVALID, "pg_buckets_plan: needs a local bucket set and an output array");
+    k_buckets_plan<<<1, 256, 0, (cudaStream_t)stream_>>>(o.part_counts, o.n_parts, o.part_cap, o.spill_cap, d_seg_cnt, d_table_stats);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
 }
 
 // ---- peer memory for the fused exchange (CUDA IPC; one process per GPU) ------------------------

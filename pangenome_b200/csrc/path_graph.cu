@@ -122,6 +122,8 @@ k5_mark(TableView rd, int mode, SeqArgs a, int strand, uint32_t *__restrict__ hi
     __shared__ __align__(16) uint64_t s_pk[K2_TILE_WORDS + 4];
     __shared__ __align__(16) uint32_t s_am[K2_TILE_WORDS + 8];
     __shared__ uint32_t s_cnt;
+    __shared__ uint16_t s_lut5[PG_LUT5_SIZE];
+    for (int i = threadIdx.x; i < PG_LUT5_SIZE; i += K2_THREADS) s_lut5[i] = (uint16_t)pg_lut5_entry(i);      // visible after the first barrier
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int64_t w0 = a.w_first + tile * K2_TILE_WORDS;
         __syncthreads();
@@ -137,7 +139,7 @@ k5_mark(TableView rd, int mode, SeqArgs a, int strand, uint32_t *__restrict__ hi
             int64_t r = find_record(a.seq_off, a.n_rec, g0);
             int64_t rs = r >= 0 ? __ldg(a.seq_off + r) : 0, re = __ldg(a.seq_off + r + 1);
             if (pg_is_interior(w, g0, 32, a.k, rs, re, r >= 0, a.g_begin, a.g_end)) {
-                pg_interior_visit<32>(w, 0, a.k, a.pow5km1, nullptr, [&](int q, uint64_t F, uint64_t R, uint32_t) {
+                pg_interior_visit<32>(w, 0, a.k, a.pow5km1, nullptr, s_lut5, [&](int q, uint64_t F, uint64_t R, uint32_t) {
                     uint64_t so;
                     if (rdbg_hit(rd, mode, strand ? R : F, strand ? F : R, so)) bits |= 1u << q;
                 });

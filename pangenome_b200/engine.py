@@ -166,7 +166,8 @@ class DbgTable:
         self.mode = int(mode)
         self.slots = torch.empty(2 * self.capacity, dtype=torch.int64, device=device)
         self.stats = torch.zeros(_lib.PG_STAT_WORDS, dtype=torch.int64, device=device)
-        self.c = PgTable(self.slots.data_ptr(), self.capacity, self.stats.data_ptr(), self.mode, self.k, 1, 0)
+        # alloc_capacity: what an epoch wrap must rewrite even while set_capacity() selects a prefix of the buffer
+        self.c = PgTable(self.slots.data_ptr(), self.capacity, self.stats.data_ptr(), self.mode, self.k, 1, 0, self.capacity)
         # a fresh allocation holds arbitrary tags: write every slot once; from then on clear() is an epoch bump
         check(self.L.pg_table_clear(ctypes.byref(self.c), _stream()), "pg_table_clear")
 

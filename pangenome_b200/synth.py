@@ -56,12 +56,10 @@ def pangenome(n_genomes=10, length=5_000_000, snp=0.01, seed=1):
     return fasta_bytes(recs)
 
 
-def plant_like(n_genomes=8, length=500_000_000, n_chrom=5, seed=2, genome_seed0=300,
-               repeat_frac=0.6, n_families=2000, snp=0.01):
-    """Configs 4/5 ("repeat-rich plant-like"): ~60 % of the ancestor is copies of
-    a repeat-family library (family length 200-10 000, copy divergence 5-20 %),
-    plus 0.5 % poly-A / microsatellite tracts; genomes at 1 % SNP; ``n_chrom``
-    records per genome."""
+def plant_ancestor(length=500_000_000, seed=2, repeat_frac=0.6, n_families=2000):
+    """Ancestor of the "repeat-rich plant-like" sets (configs 4/5): iid ACGT of which ~``repeat_frac`` is overwritten by
+    copies of a repeat-family library (family length 200-10 000, copy divergence 5-20 %), plus 0.5 % poly-A /
+    microsatellite tracts of 20-60 bases.  uint8 digits 0..3."""
     rng = np.random.default_rng(seed)
     anc = rng.integers(0, 4, length, dtype=np.uint8)
     fam_len = rng.integers(200, min(10_001, max(201, length // 8)), n_families)
@@ -85,12 +83,55 @@ def plant_like(n_genomes=8, length=500_000_000, n_chrom=5, seed=2, genome_seed0=
         else:
             unit = rng.integers(0, 4, int(rng.integers(2, 5)), dtype=np.uint8)
             anc[pos:pos + tl] = np.resize(unit, tl)
-    recs = []
+    return anc
+
+
+def _snp_copy_blocked(rng, anc, rate, block=1 << 26):
+    """_snp_copy for arrays of hundreds of Mbp: same model, drawn block by block to bound the temporaries."""
+    s = anc.copy()
+    for a in range(0, anc.size, block):
+        v = s[a:a + block]
+        m = rng.random(v.size) < rate
+        v[m] = (v[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) % 4
+    return s
+
+
+def plant_genome_records(anc, g, n_chrom=5, genome_seed0=300, snp=0.01):
+    """The ``n_chrom`` records of genome ``g``: the ancestor at ``snp`` substitutions per site (seed genome_seed0+g),
+    cut into equal chromosomes."""
+    s = _ACGT[_snp_copy_blocked(np.random.default_rng(genome_seed0 + g), anc, snp)]
+    bounds = np.linspace(0, anc.size, n_chrom + 1).astype(np.int64)
+    return [(b"g%d chr%d synthetic" % (g, c + 1), s[bounds[c]:bounds[c + 1]]) for c in range(n_chrom)]
+
+
+def plant_layout(n_genomes, length, n_chrom=5, width=80):
+    """Byte layout of the plant-like FASTA file without generating it: [(genome, chrom, byte offset, byte length)] and
+    the file size.  Lets every rank of a multi-GPU run find ITS byte range of the one file and generate only
+    the genomes that fall into it."""
     bounds = np.linspace(0, length, n_chrom + 1).astype(np.int64)
+    out, off = [], 0
     for g in range(n_genomes):
-        s = _ACGT[_snp_copy(np.random.default_rng(genome_seed0 + g), anc, snp)]
         for c in range(n_chrom):
-            recs.append((b"g%d chr%d synthetic" % (g, c + 1), s[bounds[c]:bounds[c + 1]]))
+            n = int(bounds[c + 1] - bounds[c])
+            size = len(b">g%d chr%d synthetic\n" % (g, c + 1)) + n + (n + width - 1) // width
+            out.append((g, c, off, size))
+            off += size
+    return out, off
+
+
+def plant_like(n_genomes=8, length=500_000_000, n_chrom=5, seed=2, genome_seed0=300,
+               repeat_frac=0.6, n_families=2000, snp=0.01, records=None):
+    """Configs 4/5 ("repeat-rich plant-like"): see plant_ancestor; genomes at 1 % SNP; ``n_chrom`` records per genome.
+    ``records``: optional (first, end) range of record indices (genome-major) - only those are generated and returned,
+    byte-identical to the same records of the whole file."""
+    anc = plant_ancestor(length, seed, repeat_frac, n_families)
+    first, end = (0, n_genomes * n_chrom) if records is None else records
+    recs = []
+    for g in range(first // n_chrom, (end + n_chrom - 1) // n_chrom if end > first else first // n_chrom):
+        rr = plant_genome_records(anc, g, n_chrom, genome_seed0, snp)
+        for c in range(n_chrom):
+            if first <= g * n_chrom + c < end:
+                recs.append(rr[c])
     return fasta_bytes(recs)
 
 

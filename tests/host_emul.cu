@@ -106,9 +106,13 @@ extern "C" int64_t emul_dbg(const uint32_t *pk2_32, const uint32_t *amb, int64_t
         int64_t r = lo - 1;
         int64_t rs = r >= 0 ? seq_off[r] : 0, re = seq_off[r + 1];
         if (pg_is_interior(w, g0, 32, k, rs, re, r >= 0, g_begin, g_end)) {     // the kernels' fast path
-            uint32_t vlut[16];                       // the kernels keep this table in shared memory
+            uint32_t vlut[16];                       // the kernels keep these tables in shared memory
             for (uint32_t i = 0; i < 16; i++) vlut[i] = pg_vlut_entry(i);
-            pg_interior_visit<32>(w, 0, k, p5, (wi & 1) ? vlut : nullptr, [&](int, uint64_t F, uint64_t R, uint32_t vw) {
+            static uint16_t lut5[PG_LUT5_SIZE];
+            static bool lut_ready = false;
+            if (!lut_ready) { for (uint32_t i = 0; i < PG_LUT5_SIZE; i++) lut5[i] = (uint16_t)pg_lut5_entry(i); lut_ready = true; }
+            // alternate between the table-driven and the loop forms of both helpers
+            pg_interior_visit<32>(w, 0, k, p5, (wi & 1) ? vlut : nullptr, (wi & 2) ? nullptr : lut5, [&](int, uint64_t F, uint64_t R, uint32_t vw) {
                 if (mode == PG_MODE_CANONICAL) { PgUpdate u = pg_canonical_update_w(F, R, vw); upsert(u.key, u.masks, u.inc); }
                 else { upsert(F, vw & 0xFFFFu, 1); if (mode == PG_MODE_LITERAL_RC) upsert(R, vw >> 16, 1); }
             });

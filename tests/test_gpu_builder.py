@@ -1,0 +1,157 @@
+"""GPU parity of the streaming builder (pangenome_b200/builder.py): rounds, spill buckets, the receiver-side
+split K2b, against the oracle and the reference's golden vectors.  Bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import load_small_cases
+from pangenome_b200.synth import pangenome, plant_like, survey_4x1m
+
+pytestmark = pytest.mark.gpu
+CASES = load_small_cases()
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pangenome_b200 import builder, engine
+    return engine, builder
+
+
+def _triples(t):
+    ks, vs, cs = t.export()
+    return [[int(a), int(b), int(d)] for a, b, d in zip(ks, vs, cs)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_round_builder_golden(mods, case):
+    eng, bld = mods
+    data = case["input_latin1"].encode("latin-1")
+    k, c, Ns = case["k"], case["c"], case.get("Ns", 2 ** 63)
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    rc0 = bool((c >> 1) & 1)
+    for mode in ((2, 1) if rc0 else (0,)):
+        for rounds in (1, 3):
+            t, n_rec, b = bld.build_table(packed, k, rc=rc0, Ns=Ns, mode=mode, rounds=rounds)
+            assert _triples(t) == case["dbg"], "mode %d rounds %d" % (mode, rounds)
+
+
+def test_rounds_device_bounds_and_rebuild(mods):
+    """All records with bounds read on the device (lazy K1), several rounds, the same builder twice (buffer parity and the
+    epoch bump carry over from build to build)."""
+    import torch
+    eng, bld = mods
+    from pangenome_b200 import _lib
+    data = survey_4x1m()
+    want = oracle.table_checksum(*oracle.run(data, 27, stages=1)["dbg"])
+    d = eng.to_device_bytes(data)
+    for rounds in (1, 2, 5):
+        b = bld.RoundBuilder(27, _lib.PG_MODE_CANONICAL, len(data), rounds=rounds)
+        for _ in range(3):
+            b.begin()
+            t = b.build_async(eng.PackedSeqs(d, lazy=True))
+            torch.cuda.synchronize()
+            b.verify()
+            assert t.checksum() == want, rounds
+        assert b.n_rounds == rounds
+
+
+def test_spill_absorbs_hash_skew(mods):
+    """One k-mer (poly-A) making up a large share of the input overflows its bucket; the spill takes the surplus and the
+    table is still exact.  Without enough spill the build reports LostRecords instead of a wrong table."""
+    import torch
+    eng, bld = mods
+    from pangenome_b200 import _lib
+    rng = np.random.default_rng(11)
+    recs = [b">r%d\n" % i + bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 3000)) + b"A" * 4000 + b"\n" for i in range(12)]
+    data = b"".join(recs)
+    k = 21
+    ref = oracle.run(data, k, stages=1)
+    want = oracle.table_checksum(*ref["dbg"])
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    # tight buckets (slack 1.0 -> about 1/n_sub of the records each): the poly-A bucket must spill
+    b = bld.RoundBuilder(k, _lib.PG_MODE_CANONICAL, len(data), capacity=1 << 18, sub_bytes=1 << 14, slack=1.0, spill_frac=1.0)
+    assert b.sets[0].n_parts >= 64
+    b.sets[0].c.part_cap = b.sets[0].part_cap = 2048          # far below the 4000 x 12 poly-A records that hash to one bucket
+    b.sets[0].seg_off.copy_(torch.arange(b.sets[0].n_parts + 1, device="cuda") * 2048)
+    b.begin()
+    t = b.build_async(packed, packed.n_rec)
+    torch.cuda.synchronize()
+    b.verify()
+    assert int(b.sets[0].counts[-1].item()) > 10000            # the spill really was used
+    assert t.checksum() == want
+    # no room in the spill either: the flag trips, build_table() recovers
+    b2 = bld.RoundBuilder(k, _lib.PG_MODE_CANONICAL, len(data), capacity=1 << 18, sub_bytes=1 << 14)
+    b2.sets[0].c.part_cap = b2.sets[0].part_cap = 2048
+    b2.sets[0].c.spill_cap = b2.sets[0].spill_cap = 16
+    b2.sets[0].seg_off.copy_(torch.arange(b2.sets[0].n_parts + 1, device="cuda") * 2048)
+    b2.begin()
+    b2.build_async(packed, packed.n_rec)
+    torch.cuda.synchronize()
+    with pytest.raises(bld.LostRecords):
+        b2.verify()
+    t3, _, _ = bld.build_table(packed, k)
+    assert t3.checksum() == want
+
+
+def test_k2b_split_path_on_one_gpu(mods):
+    """The multi-GPU data flow on one device: K2a into 2 coarse buckets, K2b (pg_records_split) re-sorts the two segments into
+    hash-prefix regions (+ spill), plan, K3."""
+    import torch
+    eng, bld = mods
+    from pangenome_b200 import _lib
+    L = _lib.load()
+    data = plant_like(n_genomes=3, length=200_000, n_chrom=2, n_families=40)
+    k = 27
+    want = oracle.table_checksum(*oracle.run(data, k, stages=1)["dbg"])
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    n_rec = packed.n_rec
+    g0, g1 = int(packed.seq_off[0]), int(packed.seq_off[n_rec])
+    coarse = bld.LocalBuckets(1, int((g1 - g0) * 0.6) + 4096, 0, "cuda")
+    for sub_bits, part_cap in ((6, None), (9, None), (4, 3000)):
+        n = g1 - g0
+        fine = bld.LocalBuckets(sub_bits, part_cap or int(n / (1 << sub_bits) * 1.3) + 2048, n, "cuda")
+        t = eng.DbgTable(4 * n, k, _lib.PG_MODE_CANONICAL)
+        desc = _lib.PgTable(None, 2, None, _lib.PG_MODE_CANONICAL, k, 1, 0, 0)
+        P, S = eng._ptr, eng._stream
+        eng.check(L.pg_kmer_partition_to(ctypes.byref(desc), P(packed.pk2), P(packed.amb), P(packed.d_seq_off), n_rec, g0, g1, None, 0, 0,
+                                         ctypes.byref(coarse.c), None, 0, None, S()), "pg_kmer_partition_to")
+        eng.check(L.pg_count_short(ctypes.byref(t.c), P(packed.d_seq_off), n_rec, g0, g1, S()), "pg_count_short")
+        eng.check(L.pg_records_split(P(coarse.records), P(coarse.seg_off), P(coarse.counts), 2, coarse.part_cap, ctypes.byref(fine.c),
+                                     P(t.stats), S()), "pg_records_split")
+        eng.check(L.pg_buckets_plan(ctypes.byref(fine.c), P(fine.seg_cnt), P(t.stats), S()), "pg_buckets_plan")
+        eng.check(L.pg_insert_records(ctypes.byref(t.c), P(fine.records), P(fine.seg_off), P(fine.seg_cnt), fine.n_parts + 1, 1, 0, S()),
+                  "pg_insert_records")
+        torch.cuda.synchronize()
+        st = t.stats_host()
+        assert st[_lib.PG_STAT_LOST] == 0 and st[_lib.PG_STAT_OVERFLOW] == 0
+        cnt = fine.counts.cpu().numpy()
+        assert int(cnt[:-1].sum()) == packed.n_positions(k)
+        if part_cap:
+            assert cnt[-1] > 0                               # tight buckets: the spill took the surplus
+        assert t.checksum() == want, (sub_bits, part_cap)
+
+
+def test_plant_like_single_gpu_parity(mods):
+    """BASELINE configs 4/5 in miniature (repeat families, poly-A / microsatellite tracts, 5 chromosomes per genome):
+    dBG, rdBG, .xyz in file order and rows against the oracle."""
+    eng, bld = mods
+    from pangenome_b200 import graph
+    data = plant_like(n_genomes=4, length=400_000, n_chrom=5, n_families=60)
+    k = 27
+    ref = oracle.run(data, k, stages=4)
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    assert packed.n_rec == 20
+    t, n_rec, b = bld.build_table(packed, k, rounds=3)
+    ks, vs, cs = t.export()
+    assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
+    rd = t.select_rdbg()
+    rk, _ = rd.rdbg_export()
+    assert np.array_equal(rk, ref["rdbg"])
+    res = graph.seq2graph_device(packed, rd, k)
+    assert res.xyz_lines() == ref["xyz"]
+    assert res.rows(packed, data) == ref["rows"]
