@@ -160,17 +160,8 @@ int pg_kmer_partition(const pg_table *t, const uint32_t *d_pk2, const uint32_t *
                       int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
                       uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts,
                       uint64_t *d_sample_keys, int64_t sample_cap, int64_t *d_sample_count, pg_stream_t stream);
-/* Fused extraction + exchange over NVLink peer memory: like pg_kmer_partition, but bucket
- * (owner, sub) is stored straight into rank `owner`'s receive buffer (d_peer_bases[owner], a
- * peer-mapped pointer; the own rank's entry is its own buffer) at slice
- * [my_rank][sub][part_cap] - the layout an all-to-all of the padded buckets would produce.
- * d_part_counts[(owner << sub_bits) | sub] still counts locally; the host exchanges that small
- * matrix (which is also the barrier that orders the peer stores before K3).
- * pg_peer_alloc / open / close / free: CUDA IPC plumbing for those buffers (64-byte handle). */
-int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
-                          int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
-                          uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
-                          pg_stream_t stream);
+/* CUDA IPC plumbing for the receive buffers of the fused extraction + exchange (peer bucket sets, below):
+ * pg_peer_alloc / open / close / free (64-byte handle; one process per GPU). */
 int pg_peer_alloc(int64_t bytes, void **d_ptr, uint8_t *handle64);
 int pg_peer_open(const uint8_t *handle64, void **d_ptr);
 int pg_peer_close(void *d_ptr);
@@ -183,10 +174,6 @@ int pg_peer_free(void *d_ptr);
 int pg_kmer_partition_dev(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                           const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
                           uint64_t *d_records, int64_t part_cap, int64_t *d_part_counts, pg_stream_t stream);
-int pg_kmer_partition_p2p_dev(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
-                              const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
-                              uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
-                              pg_stream_t stream);
 int pg_count_short_dev(const pg_table *t, const int64_t *d_seq_off, const int64_t *d_counts, int64_t cap_records,
                        pg_stream_t stream);
 
@@ -359,9 +346,10 @@ int pg_host_build_oakht(const uint64_t *keys, const uint16_t *vals, const uint8_
  * same byte size)") - not part of the hot path.  n_ops operations, each on one pseudo-random 16-byte slot; the regions
  * (region_slots slots each) are swept in order by the whole grid like pg_insert_records does.  mode: 0 load, 1 load +
  * red.add, 2 load + cas.b128, 3 the config-2 mix (1/3 cas, 2/3 red), 4 red only, 5 load + red.or + red.add; +8 also
- * streams one 16-byte record per operation from d_records.  Overwrites the slots. */
+ * streams one 16-byte record per operation from d_records; ilp = 1, 2, 4 or 8 independent operations in flight per
+ * thread.  Overwrites the slots. */
 int pg_microbench_slots(uint64_t *d_slots, int64_t capacity, int64_t region_slots, int64_t n_ops, int mode, int ctas_per_sm,
-                        const uint64_t *d_records, uint64_t *d_sink, pg_stream_t stream);
+                        int ilp, const uint64_t *d_records, uint64_t *d_sink, pg_stream_t stream);
 
 #ifdef __cplusplus
 }

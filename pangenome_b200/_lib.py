@@ -51,19 +51,17 @@ SIGNATURES = {
     "pg_kmer_insert": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "pg_count_short": (c_int, [PT, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "pg_kmer_partition": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
-    "pg_kmer_partition_p2p": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_int, c_i64, c_vp, c_vp]),
     "pg_peer_alloc": (c_int, [c_i64, ctypes.POINTER(c_vp), ctypes.c_char_p]),
     "pg_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "pg_peer_close": (c_int, [c_vp]),
     "pg_peer_free": (c_int, [c_vp]),
-    "pg_kmer_partition_p2p_dev": (c_int, [PT, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_int, c_i64, c_vp, c_vp]),
     "pg_kmer_partition_dev": (c_int, [PT, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
     "pg_count_short_dev": (c_int, [PT, c_vp, c_vp, c_i64, c_vp]),
     "pg_insert_records": (c_int, [PT, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "pg_kmer_partition_to": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, BT, c_vp, c_i64, c_vp, c_vp]),
     "pg_records_split": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, BT, c_vp, c_vp]),
     "pg_buckets_plan": (c_int, [BT, c_vp, c_vp, c_vp]),
-    "pg_microbench_slots": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    "pg_microbench_slots": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "pg_table_count": (c_int, [PT, c_vp]),
     "pg_table_export": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "pg_table_checksum": (c_int, [PT, c_vp, c_vp]),

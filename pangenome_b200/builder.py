@@ -12,9 +12,9 @@ A build is cut into ROUNDS of stream positions.  Per round and rank:
                      plan (clamped counts, PG_STAT_LOST), K3 region sweep into the table
 
 Two record buffers alternate, so K2a of round r+1 runs while K2b/K3 of round r drain the other buffer: the
-issue-bound extraction (and its NVLink write-out) overlaps the latency-bound table sweep.  Nothing is read
-back inside a build; verify() looks at the table's statistics block afterwards (overflow / lost-record flags)
-and the callers fall back to a safer configuration (more rounds, larger table) when it trips.
+issue-bound extraction (and its NVLink write-out) overlaps the table sweep, which is bound by L2 sector requests.
+Nothing is read back inside a build; verify() looks at the table's statistics block afterwards (overflow /
+lost-record flags) and the callers fall back to a safer configuration (more rounds, larger table) when it trips.
 
 Memory: a round holds round_len x 16 B x slack per buffer, the table 16 B per slot; both are sized for the
 HBM that is actually free (180 GB on a B200), so inputs far larger than one round stream through.
@@ -82,13 +82,16 @@ def table_capacity_for(n_keys_upper, free_bytes, load=0.5, max_fraction=0.55):
 
 class RoundBuilder:
     """See the module docstring.  ``n_bases_max``: upper bound of this rank's stream length per build (the file size
-    will do).  ``rounds`` / ``round_len``: how the stream is cut (default: PG_ROUNDS or 1 round on one GPU, 4 across
-    GPUs, and never more than 2^27 positions per round)."""
+    will do).  ``rounds`` / ``round_len``: how the stream is cut.  Default: ONE round whenever its records fit
+    (PG_ROUNDS overrides) in the free HBM next to the table: every K3 launch re-reads and writes back
+    the table sectors of all the keys its round touches, and in a pangenome every round touches nearly all of them -
+    measured on config 2, K3 takes 1.01 / 1.86 / 2.55 ms in 1 / 2 / 4 rounds (profiles/r2c_*), more than the overlap of
+    K2a with K3 wins back.  Rounds are for inputs whose records do not fit, not for speed."""
 
-    MAX_ROUND = 1 << 27
+    MAX_ROUND = 1 << 31          # K3 indexes the records of one region with 32 bits
 
     def __init__(self, k, mode, n_bases_max, world=1, rank=0, device="cuda", capacity=None, rounds=None, round_len=None,
-                 sub_bytes=8 << 20, slack=1.25, spill_frac=1.0 / 16):
+                 sub_bytes=None, slack=1.25, spill_frac=1.0 / 16):
         engine._require_cuda()
         self.L = _lib.load()
         self.k, self.mode = int(min(max(1, k), 27)), int(mode)
@@ -106,18 +109,35 @@ class RoundBuilder:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             n_max, n_sum = int(tm[0].item()), int(t[1].item())
         self.n_bases_max = n_max
-        if rounds is None and round_len is None:
-            rounds = int(os.environ.get("PG_ROUNDS", "0")) or (4 if self.world > 1 else 1)
-            rounds = max(rounds, (n_max + self.MAX_ROUND - 1) // self.MAX_ROUND)
-        self.n_rounds, self.round_len = plan_rounds(n_max, rounds, round_len)
         # ---- the table: every key lives on exactly one rank; sized for the worst case (all positions distinct, evenly
         # spread) while that is affordable, else for what the free HBM allows (the overflow flag reports a table too small)
         free = torch.cuda.mem_get_info(dev)[0]
-        R, W = self.round_len, self.world
-        buf_bytes = (2 if W == 1 else 3) * int(R * per_pos * 16 * slack * 1.1)
+        W = self.world
+        if W > 1:       # every rank must plan the same rounds: agree on the smallest free HBM
+            f = torch.tensor([free], dtype=torch.int64, device=dev)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN)
+            free = int(f.item())
         per_rank_keys = (n_sum * per_pos + W - 1) // W
-        cap = engine.next_pow2(capacity) if capacity else table_capacity_for(per_rank_keys, max(free - buf_bytes, 1 << 30))
+        cap = engine.next_pow2(capacity) if capacity else table_capacity_for(per_rank_keys, free)
+        # ---- rounds: as few as the free HBM allows (see the class docstring).  Bytes of record buffers per stream position:
+        # one local set when a single round suffices, two alternating ones otherwise; across GPUs two receive buffers
+        # (peer-written) plus the local set K2b fills
+        spill = 1.0 + spill_frac
+        if W == 1:
+            bpp1, bppn = 16.0 * per_pos * slack * spill, 2 * 16.0 * per_pos * slack * spill
+        else:
+            bpp1 = bppn = 16.0 * slack * (2 + slack * spill)
+        if rounds is None and round_len is None:
+            rounds = int(os.environ.get("PG_ROUNDS", "0"))
+            if not rounds:
+                room = max(0.85 * free - cap * 16, 0.05 * free)
+                rounds = 1 if n_max * bpp1 <= room else max(2, int(-(-n_max * bppn // room)))
+            rounds = max(rounds, (n_max + self.MAX_ROUND - 1) // self.MAX_ROUND)
+        self.n_rounds, self.round_len = plan_rounds(n_max, rounds, round_len)
+        R = self.round_len
         self.table = engine.DbgTable(cap, self.k, self.mode, device=dev)
+        if sub_bytes is None:
+            sub_bytes = int(os.environ.get("PG_SUB_MB", "8")) << 20
         self.sub_bits = engine.sub_bits_for(cap, sub_bytes)
         n_sub = 1 << self.sub_bits
         # ---- record buffers
@@ -303,6 +323,20 @@ class RoundBuilder:
         return d
 
 
+def global_record_prefix(packed, Ns, strands, world=1):
+    """How many of THIS rank's records a stage processes under ``-n`` when the file is split across ranks: the
+    running base count (kmer_numba.py:1227, 1820, 1847) continues from the ranks before this one."""
+    if world == 1:
+        return packed.record_prefix(Ns, strands)
+    mine = torch.tensor([int(packed.seq_lengths.sum()) * strands], dtype=torch.int64, device=packed.pk2.device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    before = sum(int(p.item()) for p in parts[:dist.get_rank()])
+    if Ns - before < 0:
+        return 0
+    return packed.record_prefix(Ns - before, strands)
+
+
 def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capacity=None, rounds=None, max_attempts=4):
     """The product's stage-1 build: RoundBuilder with automatic recovery - more rounds (smaller buckets relative
     to their capacity) after lost records, a larger table after an overflow.  Returns (DbgTable, n_rec, builder)."""
@@ -310,7 +344,7 @@ def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capa
     if mode is None:
         mode = _lib.PG_MODE_CANONICAL if rc else _lib.PG_MODE_LITERAL
     strands = 1 if mode == _lib.PG_MODE_LITERAL else 2
-    n_rec = packed.record_prefix(Ns, strands)
+    n_rec = global_record_prefix(packed, Ns, strands, world)
     n_bases = int(packed.seq_off[n_rec] - packed.seq_off[0]) if n_rec > 0 else 0
     spill_frac = 1.0 / 16
     err = None

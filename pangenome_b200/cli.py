@@ -5,9 +5,13 @@
 Same flags (``-i -k -n -c -r -d -R -D``; ``-k27`` and ``-k 27`` forms; unknown
 flags such as ``-m`` are skipped exactly like upstream, F1), same ``# `` banner
 lines, same table rows, same side-file names.  ``-d`` / ``-D`` read tables in the
-reference's ``.npz`` layout.  Extra long options (ignored by the reference's parser,
-so scripts stay portable): ``--min-edge-weight W``, ``--no-mcl-file``, ``--dump-db``
-(write ``<input>_db.npz`` like the reference always does).
+reference's ``.npz`` layout; like upstream the dBG is saved to ``<input>_db.npz`` after stage 1
+(``--no-dump-db`` skips the file, the banners stay).  Extra long options (ignored by the reference's
+parser, so scripts stay portable): ``--min-edge-weight W``, ``--no-mcl-file``, ``--no-dump-db``.
+
+Multi-GPU: ``torchrun --nproc-per-node N kmer_b200.py -i input.fasta -k 27`` - every rank packs its
+record-aligned byte range of the one input file, the dBG is hash-partitioned across the GPUs
+(pangenome_b200/builder.py), rank 0 prints the table and writes the side files.
 """
 import sys
 from time import time
@@ -66,6 +70,21 @@ def _eval_n(text):
 CHUNK = 2 ** 33      # bases (both strands counted) between dBG checkpoints, kmer_numba.py entry_point
 
 
+def _init_distributed():
+    """Under torchrun (WORLD_SIZE > 1): one process per GPU, NCCL.  Returns (world, rank)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 1, 0
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_world_size(), dist.get_rank()
+
+
 def entry_point(argv, out=sys.stdout):
     args, extra, flags = parse_args(argv)
     qry, kmer, Ns, rc = args['-i'], int(args['-k']), _eval_n(args['-n']), int(args['-c'])
@@ -75,9 +94,12 @@ def entry_point(argv, out=sys.stdout):
     if args['-R']:
         raise SystemExit("pangenome_b200: -R (resuming the edge-weight stage from a _rdb_brkpt.npz) is not supported by the "
                          "GPU path; -r (dBG checkpoint) is")
+    world, rank = _init_distributed()
     from . import stages
-    p = lambda *a: print(*a, file=out)
+    p = (lambda *a: print(*a, file=out)) if rank == 0 else (lambda *a: None)      # rank 0 owns stdout and the side files
     dbs, rdb = args['-d'], args['-D']
+    if world > 1 and (dbs or rdb or args['-r']):
+        raise SystemExit("pangenome_b200: -d / -D / -r start from a saved table and run on one GPU; launch without torchrun")
     rc1 = ((rc & 1) == 1)
     if dbs or rdb:
         # kmer_numba.py:2072-2100: start from a dBG (-d) or rdBG (-D) table saved in the reference's .npz layout
@@ -96,13 +118,16 @@ def entry_point(argv, out=sys.stdout):
     rc0 = ((rc >> 1) == 1)
     kmer_dict = stages.seq2rdbg(qry, kmer, 5, Ns, brkpt=args['-r'], chunk=CHUNK, rc=rc0)    # :2111
     p('# finished in', time() - st, 'seconds')
-    # the reference always dumps the table to <qry>_db.npz and reloads it here (:2116-2126); the result does
-    # not depend on it, so the GPU table stays resident and the file is only written on request
-    if '--dump-db' in flags:
-        p('# save dBG to disk')
-        st = time()
+    # the reference dumps the table to <qry>_db.npz and reloads it here (:2116-2126).  The file is written like upstream
+    # (kmer_numba.py -d reads it); the reload is skipped - the GPU table stays resident - but its banner is kept so the
+    # stdout of the two programs differs in the timing figures only
+    p('# save dBG to disk')
+    st = time()
+    if '--no-dump-db' not in flags:
         stages.dump(kmer_dict, qry + '_db')
-        p('# finished in', time() - st, 'seconds')
+    p('# finished in', time() - st, 'seconds')
+    p('# load dBG from disk')
+    p('# finished in', 0.0, 'seconds')
     p('# build the reduced dBG')
     st = time()
     rdbg_dict = stages.dbg2rdbg(kmer_dict)

@@ -315,9 +315,12 @@ struct SplitArgs {
     BucketOut out;
     int64_t *stats;        // optional table statistics: PG_STAT_LOST is raised when an input segment claims more than seg_cap
 };
-constexpr int KB_THREADS = 256;
 constexpr int KB_MAX_SEG = 64;
-__global__ void __launch_bounds__(KB_THREADS, 3)
+// 256-thread tiles (4096 records, 3 CTAs/SM) up to 256 regions; 512-thread tiles (8192 records, one CTA per SM) beyond:
+// with 1024 regions a 4096-record tile leaves 4-record (64-byte) runs per bucket - measured 46 G records/s on BASELINE
+// config 4 at 2 GPUs against 116 G records/s with 128 regions (profiles/r2d_*)
+template <int KB_THREADS>
+__global__ void __launch_bounds__(KB_THREADS, KB_THREADS == 256 ? 3 : 1)
 k2b_split(SplitArgs a) {
     constexpr int KB_TILE = KB_THREADS * KP_G;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -436,6 +439,55 @@ k3_insert_records(TableView t, const uint4 *__restrict__ records, const int64_t 
     publish_claims(t, n_claimed);
 }
 
+// K3 with the record stream one step ahead: the sweep above keeps ONE dependent chain per thread (record -> slot ->
+// atomic), so a region pass costs at least that chain's latency (~3.5 us) however few records the region holds - the floor
+// a multi-round build pays once per round and region.  Here the load of a thread's NEXT record (possibly of the next
+// region) is in flight while the current one is inserted, which takes the HBM read of the stream off the chain.
+// (More independent chains per thread do NOT help at full load: the random-slot micro-benchmark saturates at ~110 G
+// sector requests/s whatever the threads x operations in flight - profiles/r2b_microbench.jsonl - and K3 already moves
+// that many; a batched variant with 2..8 records in flight per thread measured 1.03-5.4 ms against 1.01 ms.)
+struct K3Cursor {
+    const uint4 *__restrict__ records; const int64_t *__restrict__ seg_off, *__restrict__ seg_cnt;
+    int n_regions; int64_t seg_cap; uint32_t stride, rot, start, i; int b; uint32_t c; const uint4 *base;
+    __device__ __forceinline__ void open_region() {
+        int64_t c64 = __ldg(seg_cnt + b);
+        if (c64 > seg_cap) c64 = seg_cap;
+        c = c64 > 0x7FFFFFFF ? 0x7FFFFFFFu : (c64 < 0 ? 0u : (uint32_t)c64);
+        base = records + __ldg(seg_off + b);
+        i = start;
+    }
+    // load the next record of this thread's walk (false at the end of the sweep)
+    __device__ __forceinline__ bool next(uint4 &r) {
+        for (;;) {
+            if (i < c) { r = pg_ld_stream(base + i); i += stride; return true; }
+            if (++b >= n_regions) return false;
+            start += rot; if (start >= stride) start -= stride;
+            open_region();
+        }
+    }
+};
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k3_insert_ahead(TableView t, const uint4 *__restrict__ records, const int64_t *__restrict__ seg_off,
+                const int64_t *__restrict__ seg_cnt, int n_regions, int64_t seg_cap) {
+    K3Cursor cur;
+    cur.records = records; cur.seg_off = seg_off; cur.seg_cnt = seg_cnt; cur.n_regions = n_regions; cur.seg_cap = seg_cap;
+    cur.stride = gridDim.x * blockDim.x; cur.rot = ((gridDim.x * 618u) / 1000u) * blockDim.x;
+    cur.start = blockIdx.x * blockDim.x + threadIdx.x; cur.b = 0;
+    uint32_t n_claimed = 0;
+    if (n_regions > 0) {
+        cur.open_region();
+        uint4 r, rn;
+        bool have = cur.next(r);
+        while (have) {
+            const bool have_next = cur.next(rn);            // in flight while r is inserted
+            table_upsert(t, (uint64_t)r.x | ((uint64_t)r.y << 32), r.z, r.w, n_claimed);
+            r = rn; have = have_next;
+        }
+    }
+    publish_claims(t, n_claimed);
+}
+
 int part_smem_bytes(int mode, int n_parts, int threads) {
     int maxr = (mode == PG_MODE_LITERAL_RC ? 2 : 1) * threads * KP_G;
     return maxr * 12 + maxr * 2 * 2 + 4 * n_parts * 4 + 2 * n_parts * 8 + 16;       // == TileSort<maxr>::bytes(n_parts)
@@ -539,12 +591,6 @@ static pg_bucket_set local_set(uint64_t *d_records, int64_t part_cap, int64_t *d
     b.owner_bits = owner_bits; b.sub_bits = sub_bits; b.my_rank = 0; b.reserved = 0;
     return b;
 }
-static pg_bucket_set peer_set(uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts, int owner_bits, int sub_bits) {
-    pg_bucket_set b = local_set(nullptr, part_cap, d_part_counts, owner_bits, sub_bits);
-    b.d_peer_bases = d_peer_bases; b.my_rank = my_rank;
-    return b;
-}
-
 // NB the classic entry points keep their contract: d_part_counts has n_parts counters (no spill counter), so the
 // memset there covers n_parts words only
 static int classic_zero(int64_t *d_part_counts, int owner_bits, int sub_bits, pg_stream_t stream_) {
@@ -574,27 +620,6 @@ extern "C" int pg_kmer_partition_dev(const pg_table *t, const uint32_t *d_pk2, c
     return partition_launch(t, d_pk2, d_amb, d_seq_off, 1, 0, -1, &b, false, nullptr, 0, nullptr, d_counts, cap_records, max_bases, stream_);
 }
 
-extern "C" int pg_kmer_partition_p2p(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
-                                     int64_t n_rec, int64_t g_begin, int64_t g_end, int owner_bits, int sub_bits,
-                                     uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
-                                     pg_stream_t stream_) {
-    if (!d_peer_bases) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p: bad peer table");
-    int rc = classic_zero(d_part_counts, owner_bits, sub_bits, stream_); if (rc) return rc;
-    pg_bucket_set b = peer_set(d_peer_bases, my_rank, part_cap, d_part_counts, owner_bits, sub_bits);
-    return partition_launch(t, d_pk2, d_amb, d_seq_off, n_rec, g_begin, g_end, &b, false, nullptr, 0, nullptr, nullptr, 0, 0, stream_);
-}
-
-// pg_kmer_partition_p2p with device-side bounds (see pg_kmer_partition_dev): the multi-GPU step without a host read-back
-extern "C" int pg_kmer_partition_p2p_dev(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
-                                         const int64_t *d_counts, int64_t cap_records, int64_t max_bases, int owner_bits, int sub_bits,
-                                         uint64_t *const *d_peer_bases, int my_rank, int64_t part_cap, int64_t *d_part_counts,
-                                         pg_stream_t stream_) {
-    if (!d_counts || cap_records < 0 || max_bases < 0 || !d_peer_bases) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_p2p_dev: bad arguments");
-    int rc = classic_zero(d_part_counts, owner_bits, sub_bits, stream_); if (rc) return rc;
-    pg_bucket_set b = peer_set(d_peer_bases, my_rank, part_cap, d_part_counts, owner_bits, sub_bits);
-    return partition_launch(t, d_pk2, d_amb, d_seq_off, 1, 0, -1, &b, false, nullptr, 0, nullptr, d_counts, cap_records, max_bases, stream_);
-}
-
 // ---- bucket-set API: rounds, spill, receiver-side split (the streaming builders) ---------------------------
 extern "C" int pg_kmer_partition_to(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                                     int64_t n_rec, int64_t g_begin, int64_t g_end, const int64_t *d_counts, int64_t cap_records,
@@ -616,12 +641,22 @@ extern "C" int pg_records_split(const uint64_t *d_records_in, const int64_t *d_s
     PG_CUDA(cudaMemsetAsync(out->d_part_counts, 0, (size_t)(a.out.n_parts + 1) * 8, st));
     a.in = reinterpret_cast<const uint4 *>(d_records_in); a.seg_off = d_seg_off; a.seg_cnt = d_seg_cnt; a.n_seg = n_seg; a.seg_cap = seg_cap;
     a.stats = d_table_stats;
-    const int smem = TileSort<KB_THREADS * KP_G>::bytes(a.out.n_parts);
-    PG_CUDA(cudaFuncSetAttribute(k2b_split, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t max_tiles = (int64_t)n_seg * ((seg_cap + KB_THREADS * KP_G - 1) / (KB_THREADS * KP_G));
+    static int thr_env = -1;
+    if (thr_env < 0) { const char *e = getenv("PG_K2B_THREADS"); thr_env = e ? atoi(e) : 0; }
+    const int threads = (thr_env == 256 || thr_env == 512) ? thr_env : (a.out.n_parts > 256 ? 512 : 256);
+    const int tile = threads * KP_G;
+    const int smem = threads == 256 ? TileSort<256 * KP_G>::bytes(a.out.n_parts) : TileSort<512 * KP_G>::bytes(a.out.n_parts);
+    const int64_t max_tiles = (int64_t)n_seg * ((seg_cap + tile - 1) / tile);
     int64_t maxg = (int64_t)pg_num_sms() * ctas_per_sm(smem, 1024);
     int grid = (int)(max_tiles < maxg ? max_tiles : maxg);
-    k2b_split<<<grid < 1 ? 1 : grid, KB_THREADS, smem, st>>>(a);
+    if (grid < 1) grid = 1;
+    if (threads == 256) {
+        PG_CUDA(cudaFuncSetAttribute(k2b_split<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k2b_split<256><<<grid, 256, smem, st>>>(a);
+    } else {
+        PG_CUDA(cudaFuncSetAttribute(k2b_split<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k2b_split<512><<<grid, 512, smem, st>>>(a);
+    }
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
@@ -665,10 +700,11 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
     if (seg_cap <= 0) seg_cap = INT64_MAX;
     if (reinterpret_cast<uintptr_t>(d_records) & 15) return pg_fail(PG_ERR_INVALID, "pg_insert_records: records must be 16-byte aligned");
     TableView tv = make_view(t);
-    static int gmul = -1, rotate = 1;
+    static int gmul = -1, rotate = 1, ahead = 0;
     if (gmul < 0) {
         const char *e = getenv("PG_K3_GRID"); gmul = e ? atoi(e) : 5;
         e = getenv("PG_K3_ROTATE"); rotate = e ? atoi(e) : 1;
+        e = getenv("PG_K3_AHEAD"); ahead = e ? atoi(e) : 0;
     }
     // the grid is exactly the resident CTAs (a region sweep must not leave a second wave behind): 8 per SM caps the
     // kernel at 32 registers, which costs it a few stack slots; 6 per SM runs it spill-free at 38
@@ -676,9 +712,12 @@ extern "C" int pg_insert_records(const pg_table *t, const uint64_t *d_records, c
     const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
     cudaStream_t st = (cudaStream_t)stream_;
 #define K3_LAUNCH(M, R) k3_insert_records<M, R><<<grid, 256, 0, st>>>(tv, recs, d_seg_off, d_seg_cnt, n_regions, n_src, seg_cap)
-    if (gmul >= 7) { if (rotate) K3_LAUNCH(8, true); else K3_LAUNCH(8, false); }
+#define K3A_LAUNCH(M) k3_insert_ahead<M><<<grid, 256, 0, st>>>(tv, recs, d_seg_off, d_seg_cnt, n_regions, seg_cap)
+    if (ahead && n_src == 1) { if (gmul >= 6) K3A_LAUNCH(6); else if (gmul == 5) K3A_LAUNCH(5); else K3A_LAUNCH(4); }
+    else if (gmul >= 7) { if (rotate) K3_LAUNCH(8, true); else K3_LAUNCH(8, false); }
     else { if (rotate) K3_LAUNCH(6, true); else K3_LAUNCH(6, false); }
 #undef K3_LAUNCH
+#undef K3A_LAUNCH
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

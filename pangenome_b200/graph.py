@@ -226,30 +226,50 @@ class GraphResult:
         per record, forward rows then rc rows mirrored to (n-end, n-start, '-')."""
         ids = packed.ids if data is None else record_ids(packed, data)     # a multi-GPU global index brings its ids
         lens = packed.seq_lengths
-        per_rec = {}
+        parts = []
         for rec, start, end, sign, lab in self.rows_raw:
-            for r, s, e, l in zip(rec.tolist(), start.tolist(), end.tolist(), lab.tolist()):
-                if sign > 0:
-                    per_rec.setdefault((r, 0), []).append((ids[r], s, e, "+", l))
-                else:
-                    n = int(lens[r])
-                    per_rec.setdefault((r, 1), []).append((ids[r], n - e, n - s, "-", l))
-        out = []
-        for key in sorted(per_rec):
-            out.extend(per_rec[key])
-        return out
+            rec = np.asarray(rec, dtype=np.int64)
+            if rec.size == 0:
+                continue
+            start, end, lab = np.asarray(start, np.int64), np.asarray(end, np.int64), np.asarray(lab, np.int64)
+            if sign > 0:
+                parts.append((rec, np.zeros(rec.size, np.int64), start, end, lab))
+            else:
+                n = lens[rec].astype(np.int64)
+                parts.append((rec, np.ones(rec.size, np.int64), n - end, n - start, lab))
+        if not parts:
+            return []
+        rec, strand, start, end, lab = [np.concatenate(c) for c in zip(*parts)]
+        order = np.lexsort((np.arange(rec.size), strand, rec))             # stable: walk order inside a record-strand
+        sym = ("+", "-")
+        return [(ids[r], s, e, sym[d], l) for r, d, s, e, l in
+                zip(rec[order].tolist(), strand[order].tolist(), start[order].tolist(), end[order].tolist(), lab[order].tolist())]
 
 
 def record_ids(packed, data):
-    """seqid = header line minus '>' and minus its last byte (kmer_numba.py:156, 1947)."""
-    ids = []
-    n = len(data)
-    for off in packed.hdr_off.tolist():
-        e = data.find(b"\n", off)
-        if e < 0:
-            e = n - 1                      # Q8: the final line loses its last byte even without '\n'
-        ids.append(bytes(data[off + 1:e]).decode("utf-8", errors="replace"))
-    return ids
+    """seqid = header line minus '>' and minus its last byte (kmer_numba.py:156, 1947).  ``data``: bytes or a uint8
+    array (np.memmap of the input file); header ends are found with windowed vector searches, never by scanning the file."""
+    a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.asarray(data)
+    offs = np.asarray(packed.hdr_off, dtype=np.int64)
+    n = int(a.size)
+    ends = np.empty(offs.size, dtype=np.int64)
+    W, B = 128, 1 << 15
+    win = np.arange(W, dtype=np.int64)[None, :]
+    for lo in range(0, offs.size, B):
+        o = offs[lo:lo + B]
+        nl = a[np.minimum(o[:, None] + win, n - 1)] == 10
+        has = nl.any(axis=1)
+        e = np.where(has, o + nl.argmax(axis=1), -1)
+        for j in np.nonzero(~has)[0].tolist():      # a header longer than the window: chunked search
+            p, found = int(o[j]) + W, -1
+            while p < n and found < 0:
+                hit = np.nonzero(a[p:p + (1 << 16)] == 10)[0]
+                found = p + int(hit[0]) if hit.size else -1
+                p += 1 << 16
+            e[j] = found
+        ends[lo:lo + B] = e
+    ends[ends < 0] = n - 1                           # Q8: the final line loses its last byte even without a newline
+    return [bytes(a[o + 1:e]).decode("utf-8", errors="replace") for o, e in zip(offs.tolist(), ends.tolist())]
 
 
 def labels_from_mcl(lines, xyz_edges):

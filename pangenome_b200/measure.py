@@ -52,7 +52,7 @@ def merged_checksum(table, world=1):
     return n, s, x
 
 
-def slot_ceiling(capacity, region_slots, n_ops, mode, ctas_per_sm=5, reps=3, device="cuda"):
+def slot_ceiling(capacity, region_slots, n_ops, mode, ctas_per_sm=5, ilp=1, reps=3, device="cuda"):
     """G operations/s of pg_microbench_slots (best of ``reps``)."""
     L = _lib.load()
     slots = torch.zeros(2 * capacity, dtype=torch.int64, device=device)
@@ -62,7 +62,7 @@ def slot_ceiling(capacity, region_slots, n_ops, mode, ctas_per_sm=5, reps=3, dev
     for _ in range(reps + 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        engine.check(L.pg_microbench_slots(engine._ptr(slots), capacity, region_slots, n_ops, mode, ctas_per_sm,
+        engine.check(L.pg_microbench_slots(engine._ptr(slots), capacity, region_slots, n_ops, mode, ctas_per_sm, ilp,
                                            engine._ptr(recs) if recs is not None else None, engine._ptr(sink), engine._stream()),
                      "pg_microbench_slots")
         e1.record()

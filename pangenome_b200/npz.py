@@ -30,8 +30,14 @@ def oakht_image(keys, vals, cnts, offset=0):
 def dump(table, fn, compressed=True, offset=0):
     """Write ``fn`` (``.npz`` appended like the reference does) from a DbgTable.  ``offset``: the byte
     offset a chunk checkpoint resumes from (parameters[5], :258)."""
-    fn = fn[:-4] if fn.endswith(".npz") else fn
     k, v, c = table.export(sort=False)
+    return dump_entries(k, v, c, fn, compressed, offset)
+
+
+def dump_entries(k, v, c, fn, compressed=True, offset=0):
+    """The same from (key, val, count) entries in the reference's convention (e.g. the merged export of a
+    hash-partitioned table)."""
+    fn = fn[:-4] if fn.endswith(".npz") else fn
     params, okeys, ovals, ocnts = oakht_image(k, v, c, offset)
     (np.savez_compressed if compressed else np.savez)(fn, parameters=params, keys=okeys, values=ovals, counts=ocnts)
     return fn + ".npz"

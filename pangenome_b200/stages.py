@@ -13,14 +13,31 @@ from . import _lib, engine, graph
 
 class DbgHandle:
     """What seq2rdbg returns: the device table plus the packed sequences it was
-    built from (later stages reuse them instead of re-reading the file)."""
+    built from (later stages reuse them instead of re-reading the file).  ``world`` / ``rank``: the
+    hash-partitioned table of a multi-GPU run (this rank's keys, this rank's records)."""
 
-    def __init__(self, table, packed, data, n_rec):
+    def __init__(self, table, packed, data, n_rec, world=1, rank=0, builder=None):
         self.table, self.packed, self.data, self.n_rec = table, packed, data, n_rec
+        self.world, self.rank, self.builder = world, rank, builder
 
 
 def _read(qry):
-    return np.fromfile(qry, dtype=np.uint8)
+    """The whole file as a read-only uint8 view of its page-cache pages (np.memmap: nothing is copied on the host; the
+    H2D copy streams straight out of the mapping)."""
+    if os.path.getsize(qry) == 0:
+        return np.zeros(0, dtype=np.uint8)
+    return np.memmap(qry, dtype=np.uint8, mode="r")
+
+
+def _dist_env():
+    """(world, rank) when launched under torchrun with more than one rank, else (1, 0)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_world_size(), dist.get_rank()
+    except ImportError:
+        pass
+    return 1, 0
 
 
 def seq_chk(qry):
@@ -45,19 +62,32 @@ def seq2rdbg(qry, kmer=13, bits=5, Ns=1e6, chunk=2 ** 32, brkpt="./breakpoint", 
     if bits != 5:
         raise ValueError("only the reference's base-5 code (bits=5) is supported")
     kmer = min(max(1, int(kmer)), 27)
+    world, rank = _dist_env()
     if data is None:
         if seq_chk(qry) != "fasta":
             raise SystemExit("pangenome_b200: %s is not FASTA (the reference's fastq branch is broken upstream)" % qry)
-        data = _read(qry)
-    raw = data.tobytes() if isinstance(data, np.ndarray) else bytes(data)
+        if world > 1:      # this rank's record-aligned byte range of the one file
+            from . import shard
+            data, _, _ = shard.read_rank_range(qry, world, rank)
+            data = np.frombuffer(data, dtype=np.uint8)
+        else:
+            data = _read(qry)
     packed = engine.PackedSeqs(engine.to_device_bytes(data))
     strands = 2 if rc else 1
     resume = bool(brkpt) and os.path.isfile(brkpt)
+    from . import builder
+    if world > 1:
+        if resume:
+            raise SystemExit("pangenome_b200: -r (dBG checkpoint resume) runs on one GPU; launch without torchrun")
+        table, n_rec, b = builder.build_table(packed, kmer, rc=bool(rc), Ns=Ns, world=world, rank=rank)
+        return DbgHandle(table, packed, data, n_rec, world, rank, b)
     if not resume and strands * int(packed.n_bases) <= chunk:
-        table, n_rec = engine.build_dbg(packed, kmer, rc=bool(rc), Ns=Ns)
-        return DbgHandle(table, packed, raw, n_rec)
+        # the streaming two-phase build (K2a partition + K3 region sweep): what bench.py times
+        table, n_rec, b = builder.build_table(packed, kmer, rc=bool(rc), Ns=Ns)
+        return DbgHandle(table, packed, data, n_rec, builder=b)
+    raw = data.tobytes() if isinstance(data, np.ndarray) else bytes(data)
     table = _build_chunked(qry, raw, packed, kmer, Ns, chunk, brkpt if resume else None, bool(rc))
-    return DbgHandle(table, packed, raw, packed.n_rec)
+    return DbgHandle(table, packed, data, packed.n_rec)
 
 
 def plan_chunks(lens, chunk, Ns):
@@ -143,8 +173,15 @@ def _build_chunked(qry, raw, packed, kmer, Ns, chunk, brkpt, rc):
 
 
 def dump(kmer_dict, fn):
-    """kmer_numba.py dump (:243-261): ``<fn>.npz`` in the reference's oakht layout."""
+    """kmer_numba.py dump (:243-261): ``<fn>.npz`` in the reference's oakht layout.  A hash-partitioned table is merged on
+    rank 0 first (every key lives on exactly one rank)."""
     from . import npz
+    if kmer_dict.world > 1:
+        from . import multigpu
+        merged = multigpu.gather_export(kmer_dict.table, kmer_dict.world, kmer_dict.rank)
+        if kmer_dict.rank != 0:
+            return None
+        return npz.dump_entries(*merged, fn)
     return npz.dump(kmer_dict.table, fn)
 
 
@@ -155,11 +192,14 @@ def load_dbg(qry, fn, kmer):
     data = _read(qry)
     packed = engine.PackedSeqs(engine.to_device_bytes(data))
     table = npz.load(fn, kmer, device=packed.pk2.device)
-    return DbgHandle(table, packed, data.tobytes(), packed.n_rec)
+    return DbgHandle(table, packed, data, packed.n_rec)
 
 
 def dbg2rdbg(kmer_dict):
-    """Stage 2: keep nodes with indegree != 1 or outdegree != 1."""
+    """Stage 2: keep nodes with indegree != 1 or outdegree != 1.  On a hash-partitioned table (multi-GPU) the selection
+    is part of seq2graph (every rank selects among its keys, the small rdBG tables are all-gathered there)."""
+    if kmer_dict.world > 1:
+        return kmer_dict
     rd = kmer_dict.table.select_rdbg()
     return DbgHandle(rd, kmer_dict.packed, kmer_dict.data, kmer_dict.n_rec)
 
@@ -171,20 +211,34 @@ def seq2graph(qry, kmer=13, bits=5, Ns=1e6, brkpt="./breakpoint_rdbg.npz", rdbg_
     out = out or sys.stdout
     kmer = min(max(1, int(kmer)), 27)
     packed, data = rdbg_dict.packed, rdbg_dict.data
+    world, rank = rdbg_dict.world, rdbg_dict.rank
     oname = qry + "_rdbg_weight.xyz"
     mcl_lines = None
     if cluster and os.path.isfile(oname + ".mcl"):
-        print("# the mcl has been ran", file=out)
+        if rank == 0:
+            print("# the mcl has been ran", file=out)
         with open(oname + ".mcl") as f:
             mcl_lines = f.read().split("\n")
             if mcl_lines and mcl_lines[-1] == "":
                 mcl_lines.pop()
+    if world > 1:
+        from . import builder, multigpu
+        import torch.distributed as dist
+        n_rec = builder.global_record_prefix(packed, Ns, 1, world)
+        res, rows = multigpu.seq2graph_distributed(packed, rdbg_dict.table, kmer, world, rank, data, rc=bool(rc), min_weight=min_weight,
+                                                   n_rec=n_rec, mcl_lines=mcl_lines)
+        if rank == 0:
+            res.write_xyz(oname)
+            if mcl_lines is None and write_mcl:
+                res.write_mcl(oname + ".mcl")
+            out.write("".join("%s\t%d\t%d\t%s\t%d\n" % r for r in rows))
+        dist.barrier()
+        return LabelDict(res.nodes[1], res.nodes[2], res.nodes[3]) if rank == 0 else None
     res = graph.seq2graph_device(packed, rdbg_dict.table, kmer, Ns=Ns, rc=bool(rc), min_weight=min_weight, mcl_lines=mcl_lines)
     res.write_xyz(oname)
     if mcl_lines is None and write_mcl:
         res.write_mcl(oname + ".mcl")
-    for seqid, st, ed, strand, lab in res.rows(packed, data):
-        out.write("%s\t%d\t%d\t%s\t%d\n" % (seqid, st, ed, strand, lab))
+    out.write("".join("%s\t%d\t%d\t%s\t%d\n" % r for r in res.rows(packed, data)))
     return LabelDict(res.nodes[1], res.nodes[2], res.nodes[3])
 
 

@@ -76,22 +76,37 @@ def test_cfg2_rdbg_graph_rows(ctx):
     assert res.rows(packed, data) == [tuple(r) for r in facts["rows"]]
 
 
-def test_cfg3_full_size_checksum():
-    """BASELINE config 3 (200 x 5 Mbp = 1 Gbp, k = 27): 2.0 G insertions; the table checksum must equal
-    the C oracle's (tests/golden/cfg3_oracle_facts.json, 14 CPU-minutes to produce).  Needs ~70 GB of HBM."""
+@pytest.mark.parametrize("k", [15, 21, 27])
+def test_cfg3_full_size_checksum(k):
+    """BASELINE config 3 (200 x 5 Mbp = 1 Gbp, k sweep 15/21/27): 2.0 G insertions through the streaming builder (2 rounds of <= 2^29 positions);
+    the table checksum must equal the C oracle's (tests/golden/cfg3_oracle_facts.json, 12-15 CPU-minutes per k to produce).
+    Needs ~50 GB of HBM."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     if torch.cuda.get_device_properties(0).total_memory < 100e9:
         pytest.skip("needs a 180 GB B200")
-    from pangenome_b200 import engine
+    from pangenome_b200 import builder, engine
     facts = json.load(open(os.path.join(GOLDEN, "cfg3_oracle_facts.json")))
-    data = pangenome(200, 5_000_000)
-    assert len(data) == facts["file_bytes"] and hashlib.sha256(data).hexdigest() == facts["file_sha256"]
+    data = _cfg3_data()
+    assert len(data) == facts["file_bytes"]
     packed = engine.PackedSeqs(engine.to_device_bytes(data))
-    del data
-    f = facts["k"]["27"]
-    assert packed.n_insertions(27) == f["n_inserts"]
-    t, _, buckets = engine.build_dbg_partitioned(packed, 27)
+    f = facts["k"][str(k)]
+    assert packed.n_insertions(k) == f["n_inserts"]
+    t, _, b = builder.build_table(packed, k)
+    assert b.n_rounds >= 2
     assert list(t.checksum()) == f["dbg_checksum"]
-    assert t.n_keys() * 2 == f["dbg_entries"]
+    assert t.n_keys() * 2 == f["dbg_entries"]          # no palindromes at odd k without N
+    b.close()
+
+
+_CFG3 = {}
+
+
+def _cfg3_data():
+    if "d" not in _CFG3:
+        d = pangenome(200, 5_000_000)
+        facts = json.load(open(os.path.join(GOLDEN, "cfg3_oracle_facts.json")))
+        assert hashlib.sha256(d).hexdigest() == facts["file_sha256"]
+        _CFG3["d"] = d
+    return _CFG3["d"]

@@ -1,6 +1,6 @@
-"""Multi-GPU parity (needs >= 2 visible GPUs; skipped on a single-GPU box): runs tests/mg_check.py
-under torchrun - distributed dBG (NCCL all-to-all and fused NVLink peer stores) and the distributed
-stages 2-5 against the oracle on the concatenated input."""
+"""Multi-GPU parity (needs >= 2 visible GPUs; skipped on a single-GPU box): runs tests/mg_check.py under torchrun -
+the hash-partitioned streaming build of ONE file split by byte range (records over NVLink peer stores, receiver-side
+split, region sweep), the distributed stages 2-5 and the CLI, against the oracle on the whole file."""
 import os
 import subprocess
 import sys
@@ -23,4 +23,4 @@ def test_mg_check_torchrun():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     ok = [l for l in out.stdout.splitlines() if l.startswith("mg_check ok")]
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert len(ok) == 6, out.stdout[-2000:]
+    assert len(ok) == 10, out.stdout[-2000:]           # per file: 2 dBG lines, 2 graph lines, 1 CLI line

@@ -68,3 +68,24 @@ def test_record_prefix_ns():
     assert p.record_prefix(300, 1) == 3      # 100, 250, 400 > 300
     assert p.record_prefix(300, 2) == 2      # 200, 500 > 300
     assert p.record_prefix(0, 1) == 1
+
+
+def test_record_ids_and_rows_vectorised():
+    """seqid extraction from a byte view of the file (headers longer than the search window, no final newline, Q8) and
+    the print order of the rows (per record: forward rows, then mirrored rc rows)."""
+    import numpy as np
+    from pangenome_b200 import graph
+    long_hdr = b"L" * 400
+    data = b">a desc\nACGT\n>" + long_hdr + b"\nAC\n>c\nGGGT\n>last no newline"
+    offs = [i for i in range(len(data)) if data[i:i + 1] == b">" and (i == 0 or data[i - 1:i] == b"\n")]
+
+    class P:
+        hdr_off = np.array(offs)
+        seq_lengths = np.array([4, 2, 4, 0])
+    want = ["a desc", long_hdr.decode(), "c", "last no newlin"]
+    assert graph.record_ids(P, data) == want
+    assert graph.record_ids(P, np.frombuffer(data, dtype=np.uint8)) == want
+    res = graph.GraphResult()
+    res.rows_raw = [(np.array([2, 0, 0]), np.array([0, 0, 2]), np.array([3, 2, 4]), 1, np.array([7, 5, 6])),
+                    (np.array([0]), np.array([1]), np.array([3]), -1, np.array([9]))]
+    assert res.rows(P, data) == [("a desc", 0, 2, "+", 5), ("a desc", 2, 4, "+", 6), ("a desc", 1, 3, "-", 9), ("c", 0, 3, "+", 7)]
