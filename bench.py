@@ -408,10 +408,13 @@ def main():
                 traffic = json.load(f).get(args.workload if world == 1 else "%s_n%d" % (args.workload, world))
         except Exception:
             traffic = None
-    roof = {"kernel": "k3_insert_records", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    region = bool(getattr(bld, "region_bits", 0))
+    roof = {"kernel": "k3s_region_build" if region else "k3_insert_records", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src, "ms_per_launch": k3_launch_ms, "launches_per_step": bld.n_rounds,
             "algorithmic_bytes_per_launch": alg_launch,
-            "convention": "insert: 16 B per insertion (SURVEY 8d), 2 insertions per record, per rank and round",
+            "convention": "insert: 16 B per insertion (SURVEY 8d), 2 insertions per record, per rank and round" +
+                          (" (K3s + spill upserts; what it really moves: 16 B/record read + 16 B/slot written = %.0f MB)"
+                           % ((8.0 * n_ins / world / bld.n_rounds + 16.0 * cap) / 1e6) if region else ""),
             "sector_convention": {"bytes_per_launch": sector_launch, "achieved": sector_launch / (k3_launch_ms * 1e-3) / 1e9,
                                   "frac": sector_launch / (k3_launch_ms * 1e-3) / 1e9 / peak,
                                   "what": "64 B per record: one 32-byte sector read + written back (SURVEY 8d minimum DRAM traffic)"},
@@ -423,6 +426,12 @@ def main():
         "frac": part_bytes / (k2a_ms * 1e-3) / 1e9 / peak,
         "convention": "0.25 B/base read + 16 B/record written (materialised for the exchange)" +
                       (", stored into the owners' receive buffers over NVLink" if world > 1 else "")}
+    if "k2c" in kev:
+        k2c_ms = allmax(sum(a.elapsed_time(b) for a, b in kev["k2c"]) / len(kev["k2c"]))
+        b2 = 32.0 * (n_ins / 2) / world / bld.n_rounds
+        roof["other_kernels"]["k2c_refine"] = {"ms_per_launch": k2c_ms, "algorithmic_bytes_per_launch": b2, "achieved": b2 / (k2c_ms * 1e-3) / 1e9,
+                                               "frac": b2 / (k2c_ms * 1e-3) / 1e9 / peak,
+                                               "convention": "16 B/record read + 16 B/record written (hash-prefix buckets -> one bucket per table region)"}
     if world > 1:
         k2b_ms = allmax(sum(a.elapsed_time(b) for a, b in kev["k2b"]) / len(kev["k2b"]))
         b2 = 32.0 * (n_ins / 2) / world / bld.n_rounds

@@ -69,7 +69,9 @@ typedef struct pg_table {
     int32_t mode;        /* PG_MODE_* */
     int32_t k;           /* k-mer length, 1..27 */
     int32_t epoch;       /* 1..1023: generation of the live slots (host side; pg_table_reset advances it) */
-    int32_t reserved;
+    int32_t region_bits; /* 0: linear probing wraps around the whole table.  r > 0: it wraps inside the aligned block of 2^r
+                            slots the home slot lies in, so that block holds every key that hashes into it - the layout
+                            pg_region_build produces (one block = one shared-memory table) and every later upsert keeps */
     int64_t alloc_capacity; /* slots allocated behind d_slots when `capacity` selects only a prefix of the buffer
                                (0 = same as capacity).  When the 10-bit tag wraps, pg_table_reset rewrites ALL of
                                them: a slot beyond `capacity` must not keep a tag of the previous cycle. */
@@ -214,6 +216,29 @@ int pg_records_split(const uint64_t *d_records_in, const int64_t *d_seg_off, con
 int pg_buckets_plan(const pg_bucket_set *b, int64_t *d_seg_cnt, int64_t *d_table_stats, pg_stream_t stream);
 int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_t *d_seg_off,
                       const int64_t *d_seg_cnt, int n_regions, int n_src, int64_t seg_cap, pg_stream_t stream);
+
+/* ---- K2c + K3s: the table built region by region in shared memory (csrc/region_build.cu) ----------------------
+ * Instead of one L2 atomic per update record (pg_insert_records, bound by the chip's random-atomic rate), the records
+ * are bucketed down to ONE bucket per table region of 2^region_bits slots (t->region_bits = 12: 64 KB, or 8 for tiny
+ * tables) and a CTA builds each region in shared memory - 64-bit CAS claim, atomicOr / atomicAdd merge - streaming its
+ * bucket once and writing the finished region to HBM once.  All HBM traffic is sequential.
+ * pg_records_refine (K2c): every bucket of the local set `coarse` (2^sub_bits buckets by the TOP hash bits, owner_bits 0,
+ *   with its spill) is split 2^fine_bits ways by the NEXT hash bits (fine_bits 1..8; 32 B of HBM traffic per record):
+ *   d_fine_records holds 2^(sub_bits+fine_bits) buckets of fine_part_cap records followed by a spill of fine_spill_cap
+ *   records, d_fine_counts one counter more than buckets (zeroed here; same meaning as pg_bucket_set.d_part_counts).
+ *   The coarse spill's records move to the fine spill.  A spill above its capacity raises PG_STAT_LOST in
+ *   d_table_stats (may be NULL).
+ * pg_region_build (K3s): bucket b of d_records (capacity >> region_bits buckets of part_cap records, then the spill)
+ *   becomes region b of the table.  first_round != 0: regions start empty and EVERY slot of the table is rewritten;
+ *   0: they start from what earlier rounds left in HBM.  The spill's records are upserted afterwards with L2 atomics.
+ *   A region that fills up raises PG_STAT_OVERFLOW (rebuild with a larger table), a count above part_cap without a spill
+ *   or a spill above spill_cap raises PG_STAT_LOST.  Probing wraps inside a region (pg_table.region_bits), in this
+ *   call and in every later upsert into the table.
+ * Replaces oakht.__setitem__ + resize (kmer_numba.py:423-474, 540-561) on the build path. */
+int pg_records_refine(const pg_bucket_set *coarse, int fine_bits, uint64_t *d_fine_records, int64_t *d_fine_counts,
+                      int64_t fine_part_cap, int64_t fine_spill_cap, int64_t *d_table_stats, pg_stream_t stream);
+int pg_region_build(const pg_table *t, const uint64_t *d_records, const int64_t *d_counts, int64_t part_cap, int64_t spill_cap,
+                    int first_round, pg_stream_t stream);
 
 /* ---- table read-out ---------------------------------------------------------
  * pg_table_count   : fills PG_STAT_USED / PG_STAT_ENTRIES in t->d_stats.

@@ -14,7 +14,7 @@ c_i64, c_int, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
 
 class PgTable(ctypes.Structure):
     _fields_ = [("d_slots", c_vp), ("capacity", c_i64), ("d_stats", c_vp), ("mode", ctypes.c_int32),
-                ("k", ctypes.c_int32), ("epoch", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("k", ctypes.c_int32), ("epoch", ctypes.c_int32), ("region_bits", ctypes.c_int32),
                 ("alloc_capacity", c_i64)]
 
 
@@ -60,6 +60,8 @@ SIGNATURES = {
     "pg_insert_records": (c_int, [PT, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "pg_kmer_partition_to": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, BT, c_vp, c_i64, c_vp, c_vp]),
     "pg_records_split": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, BT, c_vp, c_vp]),
+    "pg_records_refine": (c_int, [BT, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "pg_region_build": (c_int, [PT, c_vp, c_vp, c_i64, c_i64, c_int, c_vp]),
     "pg_buckets_plan": (c_int, [BT, c_vp, c_vp, c_vp]),
     "pg_microbench_slots": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "pg_table_count": (c_int, [PT, c_vp]),

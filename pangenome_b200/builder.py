@@ -9,7 +9,10 @@ A build is cut into ROUNDS of stream positions.  Per round and rank:
                                (CUDA IPC peer memory) - 8192-position tiles give 16 KB runs per peer
     stream B   [N>1] all-to-all of the W record counts (NCCL) - also the barrier that orders the peer stores
                [N>1] K2b  what arrived (one segment per source) -> hash-prefix buckets (+ spill)
-                     plan (clamped counts, PG_STAT_LOST), K3 region sweep into the table
+                     plan (clamped counts, PG_STAT_LOST), K3 region sweep into the table (L2 atomics)
+               or, on one GPU while the table has at most 2^18 regions of 4096 slots (``region_bits``):
+                     K2c  every hash-prefix bucket -> one bucket per table region,
+                     K3s  one CTA per region builds it in SHARED MEMORY and writes it to HBM once (csrc/region_build.cu)
 
 Two record buffers alternate, so K2a of round r+1 runs while K2b/K3 of round r drain the other buffer: the
 issue-bound extraction (and its NVLink write-out) overlaps the table sweep, which is bound by L2 sector requests.
@@ -90,8 +93,11 @@ class RoundBuilder:
 
     MAX_ROUND = 1 << 31          # K3 indexes the records of one region with 32 bits
 
+    REGION_BITS = 12             # slots per shared-memory table region (64 KB); PG_REGION_BITS=0 selects the L2-atomic K3
+    MAX_REGION_LOG = 18          # 2^10 coarse buckets (K2a) x 2^8 fine ones each (K2c)
+
     def __init__(self, k, mode, n_bases_max, world=1, rank=0, device="cuda", capacity=None, rounds=None, round_len=None,
-                 sub_bytes=None, slack=1.25, spill_frac=1.0 / 16):
+                 sub_bytes=None, slack=1.25, spill_frac=1.0 / 16, region_bits=None, sample=False):
         engine._require_cuda()
         self.L = _lib.load()
         self.k, self.mode = int(min(max(1, k), 27)), int(mode)
@@ -123,8 +129,15 @@ class RoundBuilder:
         # one local set when a single round suffices, two alternating ones otherwise; across GPUs two receive buffers
         # (peer-written) plus the local set K2b fills
         spill = 1.0 + spill_frac
+        # shared-memory region build (one GPU): the table is a whole number of 2^region_bits-slot regions, K2a buckets by
+        # the top ``sub_bits`` hash bits and K2c refines every bucket down to one per region (one more record buffer)
+        if region_bits is None:
+            region_bits = int(os.environ.get("PG_REGION_BITS", str(self.REGION_BITS)))
+        cap_log = cap.bit_length() - 1
+        self.region_bits = region_bits if (W == 1 and region_bits in (8, 12) and 0 <= cap_log - region_bits <= self.MAX_REGION_LOG) else 0
         if W == 1:
-            bpp1, bppn = 16.0 * per_pos * slack * spill, 2 * 16.0 * per_pos * slack * spill
+            fine = 16.0 * per_pos * slack * spill if self.region_bits else 0.0
+            bpp1, bppn = 16.0 * per_pos * slack * spill + fine, 2 * 16.0 * per_pos * slack * spill + fine
         else:
             bpp1 = bppn = 16.0 * slack * (2 + slack * spill)
         if rounds is None and round_len is None:
@@ -139,6 +152,15 @@ class RoundBuilder:
         if sub_bytes is None:
             sub_bytes = int(os.environ.get("PG_SUB_MB", "8")) << 20
         self.sub_bits = engine.sub_bits_for(cap, sub_bytes)
+        self.adaptive = bool(self.region_bits) and not capacity
+        self.sampler = None
+        if self.region_bits:
+            region_log = cap_log - self.region_bits
+            self.sub_bits = region_log if region_log <= 8 else max(8, region_log - 8)
+            self.table.c.region_bits = self.region_bits
+            self.min_capacity = 1 << (self.sub_bits + self.region_bits)       # K2a's buckets must not be finer than the regions
+            if sample and self.n_rounds == 1 and not capacity:
+                self.sampler = engine.KeySampler(n_max * per_pos, dev)
         n_sub = 1 << self.sub_bits
         # ---- record buffers
         if W == 1:
@@ -146,6 +168,14 @@ class RoundBuilder:
             spill_cap = max(1 << 16, int(R * per_pos * spill_frac))
             self.sets = [LocalBuckets(self.sub_bits, part_cap, spill_cap, dev) for _ in range(2 if self.n_rounds > 1 else 1)]
             self.wire = None
+            if self.region_bits:
+                # the fine set: (capacity >> region_bits) buckets + one spill, laid out per build for the capacity in use
+                self._fine_total = int(R * per_pos * slack)
+                self._fine_pad = 256
+                n_regions_max = cap >> self.region_bits
+                self.fine_spill_cap = spill_cap
+                self.fine_records = torch.empty(2 * (self._fine_total + n_regions_max * self._fine_pad + spill_cap), dtype=torch.int64, device=dev)
+                self.fine_counts = torch.zeros(n_regions_max + 1, dtype=torch.int64, device=dev)
         else:
             self.cap_wire = cw = int(R / W * slack) + 8192
             self.wire_bytes = W * cw * 16
@@ -184,13 +214,19 @@ class RoundBuilder:
         self._ev_free = [None, None]        # world 1: K3 finished reading local set i
         self._ev_a2a = None                 # world N: the previous round's count exchange (= every peer drained buffer i)
         self._begun = False
+        self._next_capacity = None
         self.desc = _lib.PgTable(None, 2, None, self.mode, self.k, 1, 0, 0)      # K2a reads mode and k only
         self.launches_per_round = 3 if W == 1 else 4      # K2a, plan, K3 (+ K2b); the count exchange is NCCL's
+        if self.region_bits:
+            self.launches_per_round = 4                   # K2a, K2c, K3s, spill upserts
         self.launches_per_build = 1 + self.n_rounds * self.launches_per_round       # + count_short
 
     # ------------------------------------------------------------------------------------------------
     def begin(self):
         """Empty the table for the next build: an epoch bump (DbgTable.clear), no HBM traffic."""
+        if self._next_capacity and self._next_capacity != self.table.capacity:
+            self.table.set_capacity(self._next_capacity)
+        self._next_capacity = None
         self.table.clear()
         self._begun = True
 
@@ -247,10 +283,19 @@ class RoundBuilder:
                         A.wait_event(self._ev_a2a)          # every peer has drained buffer i (its K2b of two rounds ago)
                     out = self.wire_sets[i]
                 e0 = stamp(A)
+                smp = self.sampler if (self.sampler is not None and r == 0) else None
+                if smp is not None:
+                    smp.reset()
                 check(L.pg_kmer_partition_to(byref(self.desc), P(packed.pk2), P(packed.amb), P(packed.d_seq_off), n_rec_arg, lo, hi,
-                                             d_counts, cap_records, max_bases, byref(out), None, 0, None, engine._stream()),
+                                             d_counts, cap_records, max_bases, byref(out), P(smp.keys) if smp else None, smp.cap if smp else 0,
+                                             P(smp.count) if smp else None, engine._stream()),
                       "pg_kmer_partition_to")
                 e1 = stamp(A)
+                if smp is not None:
+                    # size the table from K2a's 1/256 key-space sample before anything is inserted: one 8-byte read-back
+                    self.last_estimate = smp.estimate()
+                    want = engine.capacity_for(self.last_estimate, t.slots.numel() // 2, load=0.5, margin=1.02)
+                    t.set_capacity(max(self.min_capacity, want))
                 if ev is not None and W > 1:
                     self.sent_total += self.send_counts[i][:W]       # measurement only: records really sent to every owner
                 done = torch.cuda.Event()
@@ -270,9 +315,25 @@ class RoundBuilder:
                     x2 = stamp(B)
                 else:
                     x2 = stamp(B)
-                check(L.pg_buckets_plan(byref(bs.c), P(bs.seg_cnt), P(t.stats), engine._stream()), "pg_buckets_plan")
-                check(L.pg_insert_records(byref(t.c), P(bs.records), P(bs.seg_off), P(bs.seg_cnt), bs.n_parts + 1, 1, 0, engine._stream()),
-                      "pg_insert_records")
+                if self.region_bits:
+                    n_regions = t.capacity >> self.region_bits
+                    fine_bits = (n_regions.bit_length() - 1) - self.sub_bits
+                    if fine_bits > 0:          # K2c: one bucket per region
+                        fine_cap = self._fine_total // n_regions + self._fine_pad
+                        check(L.pg_records_refine(byref(bs.c), fine_bits, P(self.fine_records), P(self.fine_counts), fine_cap,
+                                                  self.fine_spill_cap, P(t.stats), engine._stream()), "pg_records_refine")
+                        recs, cnts, pcap, scap = self.fine_records, self.fine_counts, fine_cap, self.fine_spill_cap
+                    else:
+                        recs, cnts, pcap, scap = bs.records, bs.counts, bs.c.part_cap, bs.c.spill_cap
+                    x2c = stamp(B)
+                    check(L.pg_region_build(byref(t.c), P(recs), P(cnts), pcap, scap, 1 if r == 0 else 0, engine._stream()), "pg_region_build")
+                    if ev is not None:
+                        ev.setdefault("k2c", []).append((x2, x2c))
+                        x2 = x2c
+                else:
+                    check(L.pg_buckets_plan(byref(bs.c), P(bs.seg_cnt), P(t.stats), engine._stream()), "pg_buckets_plan")
+                    check(L.pg_insert_records(byref(t.c), P(bs.records), P(bs.seg_off), P(bs.seg_cnt), bs.n_parts + 1, 1, 0, engine._stream()),
+                          "pg_insert_records")
                 x3 = stamp(B)
                 if W == 1:
                     self._ev_free[si] = torch.cuda.Event()
@@ -291,6 +352,7 @@ class RoundBuilder:
     def flags(self):
         """(table full, records lost) after a synchronise; agreed on by all ranks."""
         s = self.table.stats_host()
+        self._last_used = int(s[_lib.PG_STAT_USED])
         f = torch.tensor([int(s[_lib.PG_STAT_OVERFLOW] != 0), int(s[_lib.PG_STAT_LOST] != 0)], dtype=torch.int64, device=self.device)
         if self.world > 1:
             # a truncated record index poisons the wire counts: the receiver flags PG_STAT_LOST, so it is covered here
@@ -304,6 +366,17 @@ class RoundBuilder:
             raise LostRecords("update records were dropped (bucket/spill overflow or a truncated record index) on some rank")
         if full:
             raise TableFull("dBG table overflow (capacity %d slots per rank)" % self.table.capacity)
+        if self.adaptive:
+            self.retune()
+
+    def retune(self, load=0.5):
+        """Shared-memory region build: size the table for the NEXT build of this builder from the distinct keys the last one
+        found (load <= ``load``; a serving loop sees inputs of one kind).  A K3s launch writes every slot of the table it
+        is given and the stages after it scan every slot, so a table 4x too large costs 4x their HBM traffic; a table
+        too small shows as TableFull and the caller rebuilds larger.  Never below one region per K2a bucket."""
+        used = self._last_used
+        want = max(self.min_capacity, engine.next_pow2(max(2, int(used / load) + 1)))
+        self._next_capacity = min(want, self.table.slots.numel() // 2)        # applied by begin(): the table just built keeps its size
 
     def close(self):
         torch.cuda.synchronize()
@@ -317,6 +390,8 @@ class RoundBuilder:
 
     def describe(self):
         d = {"rounds": self.n_rounds, "round_len": self.round_len, "table_slots": self.table.capacity, "regions": 1 << self.sub_bits,
+             "insert": ("K2c + K3s: %d shared-memory regions of %d slots" % (self.table.capacity >> self.region_bits, 1 << self.region_bits))
+                       if self.region_bits else "K3: L2 atomics over %d hash-prefix regions" % (1 << self.sub_bits),
              "record_buffers_bytes": sum(s.bytes() for s in self.sets) + (2 * self.wire_bytes if self.world > 1 else 0)}
         if self.world > 1:
             d["wire_bucket_records"] = self.cap_wire
@@ -337,9 +412,12 @@ def global_record_prefix(packed, Ns, strands, world=1):
     return packed.record_prefix(Ns - before, strands)
 
 
-def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capacity=None, rounds=None, max_attempts=4):
+def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capacity=None, rounds=None, max_attempts=4,
+                region_bits=None, sample=True):
     """The product's stage-1 build: RoundBuilder with automatic recovery - more rounds (smaller buckets relative
-    to their capacity) after lost records, a larger table after an overflow.  Returns (DbgTable, n_rec, builder)."""
+    to their capacity) after lost records, a larger table after an overflow.  On one GPU the table is built in
+    shared-memory regions and, for a single-round build, sized from K2a's key-space sample (``sample``) instead of the
+    positions upper bound: the stages after it scan every slot.  Returns (DbgTable, n_rec, builder)."""
     k = int(min(max(1, k), 27))
     if mode is None:
         mode = _lib.PG_MODE_CANONICAL if rc else _lib.PG_MODE_LITERAL
@@ -350,7 +428,8 @@ def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capa
     err = None
     for _ in range(max_attempts):
         b = RoundBuilder(k, mode, max(n_bases, 1), world=world, rank=rank, device=packed.pk2.device, capacity=capacity, rounds=rounds,
-                         spill_frac=spill_frac)
+                         spill_frac=spill_frac, region_bits=region_bits, sample=sample)
+        b.adaptive = False              # one build: nothing to retune for
         b.begin()
         b.build_async(packed, n_rec)
         torch.cuda.synchronize()
@@ -363,6 +442,7 @@ def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capa
         except TableFull as e:
             err = e
             capacity = 2 * b.table.capacity
+            sample = False
         b.close()
         del b
     raise PgError("dBG build failed after %d attempts: %s" % (max_attempts, err))

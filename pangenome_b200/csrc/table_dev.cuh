@@ -10,12 +10,21 @@ constexpr uint32_t PG_MAX_PROBE = 1u << 16;
 // Home slot = TOP bits of the 64-bit mix: the high bits of a slot index are then hash bits too, so
 // "region of the table" == "hash prefix" for every capacity (K2a buckets records by that prefix before
 // the table is even sized); the owner rank of the multi-GPU split comes from the LOW bits instead.
-struct TableView { uint64_t *slots; uint64_t capmask; int64_t *stats; int shift; uint64_t tag; };
+// rmask: probing wraps inside the aligned block of rmask + 1 slots the home slot lies in (pg_table.region_bits; the
+// whole table when 0), so a region of a table built in shared memory (region_build.cu) holds ALL the keys that hash into it.
+// hmask: region tables round the home slot down to a group of PG_REGION_GROUP slots (K3s reads a whole group per probe
+// step), so the linear-probing invariant "no free slot between home and the key" is stated from the group's first slot.
+#define PG_REGION_GROUP 4
+struct TableView { uint64_t *slots; uint64_t capmask; int64_t *stats; int shift; uint64_t tag; uint64_t rmask; uint64_t hmask; };
+__host__ __device__ __forceinline__ uint64_t tv_next(const TableView &t, uint64_t s) { return (s & ~t.rmask) | ((s + 1) & t.rmask); }
 inline uint64_t pg_tag(const pg_table *t) { return (uint64_t)(uint32_t)t->epoch << PG_TAG_SHIFT; }
-__host__ __device__ __forceinline__ uint64_t tv_home(const TableView &t, uint64_t key) { return pg_mix64(key) >> t.shift; }
+__host__ __device__ __forceinline__ uint64_t tv_home(const TableView &t, uint64_t key) { return (pg_mix64(key) >> t.shift) & t.hmask; }
 inline TableView make_view(const pg_table *t) {
     int bits = 0; while ((1ll << bits) < t->capacity) bits++;
-    return TableView{t->d_slots, (uint64_t)t->capacity - 1, t->d_stats, 64 - bits, pg_tag(t)};
+    const uint64_t capmask = (uint64_t)t->capacity - 1;
+    const uint64_t rmask = (t->region_bits > 0 && t->region_bits < bits) ? ((1ull << t->region_bits) - 1ull) : capmask;
+    const uint64_t hmask = rmask != capmask ? ~(uint64_t)(PG_REGION_GROUP - 1) : ~0ull;
+    return TableView{t->d_slots, capmask, t->d_stats, 64 - bits, pg_tag(t), rmask, hmask};
 }
 
 // Merge one update into a slot whose key already matches; cv = the value word last seen.
@@ -28,7 +37,8 @@ __device__ __forceinline__ void slot_merge(uint64_t *p, uint64_t cv, uint32_t ma
 // returns the slot index the key lives in (claimed if absent), or -1 when probing gives up
 __device__ __forceinline__ int64_t table_upsert_from(const TableView &t, uint64_t s, uint64_t lo, uint64_t hi, uint64_t key,
                                                      uint32_t masks, uint32_t inc, uint32_t &n_claimed) {
-    for (uint32_t probe = 0; probe < PG_MAX_PROBE; probe++) {
+    const uint32_t max_probe = t.rmask + 1 < PG_MAX_PROBE ? (uint32_t)(t.rmask + 1) : PG_MAX_PROBE;
+    for (uint32_t probe = 0; probe < max_probe; probe++) {
         uint64_t *p = t.slots + 2 * s;
         if (probe) pg_ld_slot_raw(p, lo, hi);
         if ((hi & ~PG_VAL_MASK) != t.tag) {
@@ -40,7 +50,7 @@ __device__ __forceinline__ int64_t table_upsert_from(const TableView &t, uint64_
             lo = olo; hi = ohi;              // lost the race: the slot is live now, look at its key
         }
         if (lo == key) { slot_merge(p, hi & PG_VAL_MASK, masks, inc); return (int64_t)s; }
-        s = (s + 1) & t.capmask;
+        s = tv_next(t, s);
     }
     atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
     return -1;

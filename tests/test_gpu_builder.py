@@ -36,8 +36,10 @@ def test_round_builder_golden(mods, case):
     rc0 = bool((c >> 1) & 1)
     for mode in ((2, 1) if rc0 else (0,)):
         for rounds in (1, 3):
-            t, n_rec, b = bld.build_table(packed, k, rc=rc0, Ns=Ns, mode=mode, rounds=rounds)
-            assert _triples(t) == case["dbg"], "mode %d rounds %d" % (mode, rounds)
+            for rb in (0, 8):       # L2-atomic K3 / shared-memory regions of 256 slots
+                t, n_rec, b = bld.build_table(packed, k, rc=rc0, Ns=Ns, mode=mode, rounds=rounds, region_bits=rb)
+                assert b.region_bits == rb or b.table.capacity < 256
+                assert _triples(t) == case["dbg"], "mode %d rounds %d region_bits %d" % (mode, rounds, rb)
 
 
 def test_rounds_device_bounds_and_rebuild(mods):
@@ -155,3 +157,79 @@ def test_plant_like_single_gpu_parity(mods):
     res = graph.seq2graph_device(packed, rd, k)
     assert res.xyz_lines() == ref["xyz"]
     assert res.rows(packed, data) == ref["rows"]
+
+
+@pytest.mark.parametrize("region_bits,rounds", [(12, 1), (12, 3), (8, 1), (8, 2)])
+def test_region_build_refine_and_retune(mods, region_bits, rounds):
+    """K2a -> K2c (coarse buckets refined to one bucket per region) -> K3s (regions built in shared memory) -> spill, with the
+    bounds read on the device; the same builder three times: verify() retunes the capacity to the distinct keys found
+    (load <= 0.5), which changes the number of regions and K2c's fan-out between builds."""
+    import torch
+    eng, bld = mods
+    from pangenome_b200 import _lib
+    data = survey_4x1m()
+    want = oracle.table_checksum(*oracle.run(data, 27, stages=1)["dbg"])
+    d = eng.to_device_bytes(data)
+    b = bld.RoundBuilder(27, _lib.PG_MODE_CANONICAL, len(data), rounds=rounds, region_bits=region_bits)
+    assert b.region_bits == region_bits and b.adaptive
+    caps = []
+    for _ in range(3):
+        b.begin()
+        t = b.build_async(eng.PackedSeqs(d, lazy=True))
+        torch.cuda.synchronize()
+        caps.append(t.capacity)
+        assert (t.capacity >> region_bits) > (1 << b.sub_bits), "this test must go through K2c"
+        b.verify()
+        assert t.capacity == caps[-1]                          # retuning applies to the NEXT build
+        assert t.checksum() == want, (region_bits, rounds, caps)
+        n_keys = t.n_keys()
+        used, entries = t.count()
+        assert used == n_keys == b._last_used
+    assert caps[1] < caps[0] and caps[2] == caps[1]            # retuned once, then stable
+    assert 0.25 < b._last_used / caps[-1] <= 0.5
+
+
+def test_region_build_sampled_capacity_and_overflow_recovery(mods):
+    """build_table on one GPU: the table is sized from K2a's key-space sample (load <= 0.5); a table forced too small
+    fills a region, which is reported (TableFull) and rebuilt larger - never a wrong table."""
+    import torch
+    eng, bld = mods
+    from pangenome_b200 import _lib
+    data = survey_4x1m()
+    ref = oracle.run(data, 27, stages=1)
+    want = oracle.table_checksum(*ref["dbg"])
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    t, n_rec, b = bld.build_table(packed, 27)
+    assert b.region_bits == 12 and b.sampler is not None
+    used = t.n_keys()
+    assert abs(b.last_estimate - used) < 0.02 * used
+    assert 0.2 < used / t.capacity <= 0.5
+    assert t.checksum() == want
+    ks, vs, cs = t.export()
+    assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
+    # the stages after the build read the region table like any other
+    rd = t.select_rdbg()
+    assert rd.n_members == len(oracle.run(data, 27, stages=2)["rdbg"])
+    # 2^20 slots for ~1.95 M keys: regions fill up
+    small = bld.RoundBuilder(27, _lib.PG_MODE_CANONICAL, len(data), capacity=1 << 20)
+    small.begin()
+    small.build_async(packed, packed.n_rec)
+    torch.cuda.synchronize()
+    with pytest.raises(bld.TableFull):
+        small.verify()
+    t2, _, b2 = bld.build_table(packed, 27, capacity=1 << 20)
+    assert t2.capacity > 1 << 20 and t2.checksum() == want
+
+
+def test_region_table_takes_later_upserts(mods):
+    """A table built in shared-memory regions probes inside a region; the fused insert kernel (pg_kmer_insert) follows the
+    same rule, so adding the same records again only doubles the counts."""
+    eng, bld = mods
+    data = pangenome(3, 60_000, seed=3)
+    ref = oracle.run(data + data.replace(b">", b">x"), 21, stages=1)
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    t, n_rec, b = bld.build_table(packed, 21, region_bits=8)
+    assert b.region_bits == 8 and t.c.region_bits == 8
+    t.insert(packed, n_rec)
+    ks, vs, cs = t.export()
+    assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
