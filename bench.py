@@ -405,7 +405,8 @@ def main():
     if os.path.isfile(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get(args.workload if world == 1 else "%s_n%d" % (args.workload, world))
+                traffic = json.load(f).get((args.workload + ("_region" if getattr(bld, "region_bits", 0) else "")) if world == 1
+                                           else "%s_n%d" % (args.workload, world))
         except Exception:
             traffic = None
     region = bool(getattr(bld, "region_bits", 0))

@@ -145,8 +145,10 @@ struct RegionArgs {
     TableView t; const uint4 *records; const unsigned long long *counts; int64_t part_cap, spill_cap; int n_regions;
 };
 
-template <int RB, bool FIRST>
-__global__ void __launch_bounds__(256, RB == 12 ? 3 : 4)
+// THREADS x RPT records are in flight per CTA batch.  512 threads x 2 records: the shared-memory table (64 KB) limits an SM
+// to 3 CTAs, so the warps that hide the LDS -> compare -> CAS dependency chains have to come from wider CTAs.
+template <int RB, bool FIRST, int THREADS, int RPT>
+__global__ void __launch_bounds__(THREADS, RB == 12 ? 3 : 4)
 k3s_region_build(RegionArgs a) {
     constexpr int NS = 1 << RB;
     constexpr uint32_t CNT_MAX = (1u << 22) - 1u;
@@ -171,10 +173,10 @@ k3s_region_build(RegionArgs a) {
 
     int64_t r = blockIdx.x;
     if (r < a.n_regions)
-        for (int s = threadIdx.x; s < NS; s += 256) init_slot(r, s);
+        for (int s = threadIdx.x; s < NS; s += THREADS) init_slot(r, s);
     __syncthreads();
     for (; r < a.n_regions; r += gridDim.x) {
-        // ---- the region's records: coalesced 16-byte loads, four in flight per thread
+        // ---- the region's records: coalesced 16-byte loads, RPT in flight per thread
         unsigned long long c64 = a.counts[r];
         if (c64 > (unsigned long long)a.part_cap) {     // the surplus sits in the spill; without one it was dropped
             if (a.spill_cap <= 0 && threadIdx.x == 0) raise_lost(t.stats);
@@ -182,52 +184,59 @@ k3s_region_build(RegionArgs a) {
         }
         const uint32_t c = (uint32_t)c64;
         const uint4 *src = a.records + r * a.part_cap;
-        for (uint32_t base = 0; base < c; base += 4 * 256) {
-            uint4 rec[4];
+        for (uint32_t base = 0; base < c; base += RPT * THREADS) {
+            uint4 rec[RPT];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t i = base + j * 256 + threadIdx.x;
+            for (int j = 0; j < RPT; j++) {
+                const uint32_t i = base + j * THREADS + threadIdx.x;
                 if (i < c) rec[j] = pg_ld_stream(src + i);
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t i = base + j * 256 + threadIdx.x;
-                if (i >= c) continue;
+            for (int j = 0; j < RPT; j++) {
                 // One probe step looks at a GROUP of four consecutive slots (two 16-byte shared-memory loads): the probe
                 // sequences of the 32 lanes of a warp differ in length and the warp pays for the longest, so what matters
-                // is the tail - at load 0.5 the longest of 32 sequences is ~2 groups against ~6-9 single slots
+                // is the tail - at load 0.5 the longest of 32 sequences is ~2 groups against ~6-9 single slots.  Match and
+                // free-slot positions come from bit masks (no branch per slot), every lane that claims goes through ONE
+                // CAS site, and the warp reconverges before the merge so the two atomics issue once per batch.
+                const bool act = base + j * THREADS + threadIdx.x < c;
                 const uint32_t klo = rec[j].x, khi = rec[j].y;
                 const uint64_t key = (uint64_t)klo | ((uint64_t)khi << 32);
                 uint32_t g = (uint32_t)(pg_mix64(key) >> t.shift) & (NS - 1) & ~(uint32_t)(PG_REGION_GROUP - 1);
                 int s = -1;
-                for (int probe = 0; probe < NS / PG_REGION_GROUP;) {
-                    const uint4 a = lds128(s_key + g), b = lds128(s_key + g + 2);
-                    const bool m0 = a.x == klo && a.y == khi, m1 = a.z == klo && a.w == khi, m2 = b.x == klo && b.y == khi, m3 = b.z == klo && b.w == khi;
-                    if (m0 || m1 || m2 || m3) { s = (int)g + (m0 ? 0 : (m1 ? 1 : (m2 ? 2 : 3))); break; }
-                    // free slots hold PG_EMPTY; a key's high word is never 0xFFFFFFFF (base-5 codes stay below 2^63)
-                    const int e = a.y == 0xFFFFFFFFu ? 0 : (a.w == 0xFFFFFFFFu ? 1 : (b.y == 0xFFFFFFFFu ? 2 : (b.w == 0xFFFFFFFFu ? 3 : -1)));
-                    if (e >= 0) {
-                        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(s_key + g + e), (unsigned long long)PG_EMPTY,
-                                                                 (unsigned long long)key);
-                        if (old == PG_EMPTY) { n_claimed++; s = (int)g + e; break; }
-                        if (old == key) { s = (int)g + e; break; }
-                        continue;             // another key took that slot first: look at the group again
+                if (act) {
+                    for (int probe = 0; probe < NS / PG_REGION_GROUP;) {
+                        const uint4 a = lds128(s_key + g), b = lds128(s_key + g + 2);
+                        const uint32_t mm = (uint32_t)(a.x == klo && a.y == khi) | ((uint32_t)(a.z == klo && a.w == khi) << 1) |
+                                            ((uint32_t)(b.x == klo && b.y == khi) << 2) | ((uint32_t)(b.z == klo && b.w == khi) << 3);
+                        if (mm) { s = (int)g + __ffs(mm) - 1; break; }
+                        // free slots hold PG_EMPTY; a key's high word is never 0xFFFFFFFF (base-5 codes stay below 2^63)
+                        const uint32_t em = (uint32_t)(a.y == 0xFFFFFFFFu) | ((uint32_t)(a.w == 0xFFFFFFFFu) << 1) |
+                                            ((uint32_t)(b.y == 0xFFFFFFFFu) << 2) | ((uint32_t)(b.w == 0xFFFFFFFFu) << 3);
+                        if (em) {
+                            const int e = (int)g + __ffs(em) - 1;
+                            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(s_key + e), (unsigned long long)PG_EMPTY,
+                                                                     (unsigned long long)key);
+                            if (old == PG_EMPTY) { n_claimed++; s = e; break; }
+                            if (old == key) { s = e; break; }
+                            continue;             // another key took that slot first: look at the group again
+                        }
+                        g = (g + PG_REGION_GROUP) & (NS - 1); probe++;
                     }
-                    g = (g + PG_REGION_GROUP) & (NS - 1); probe++;
+                    if (s < 0)                // the region is full: the table is too small for this input
+                        atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
                 }
-                if (s < 0) {              // the region is full: the table is too small for this input
-                    atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
-                    continue;
+                __syncwarp();
+                if (s >= 0) {
+                    atomicOr(s_mask + s, rec[j].z);
+                    atomicAdd(s_cnt + s, rec[j].w);
                 }
-                atomicOr(s_mask + s, rec[j].z);
-                atomicAdd(s_cnt + s, rec[j].w);
             }
         }
         __syncthreads();
         // ---- write the region out (one 16-byte store per slot, consecutive threads consecutive slots) and start
         // the next one: a slot is re-initialised by the thread that just read it, no barrier in between
         const int64_t nxt = r + gridDim.x;
-        for (int s = threadIdx.x; s < NS; s += 256) {
+        for (int s = threadIdx.x; s < NS; s += THREADS) {
             const uint64_t key = s_key[s];
             uint4 g = make_uint4(0u, 0u, 0u, 0u);
             if (key != PG_EMPTY) {
@@ -258,20 +267,27 @@ k3s_spill_insert(TableView t, const uint4 *__restrict__ spill, const unsigned lo
     publish_claims(t, n_claimed);
 }
 
-template <int RB>
-int launch_regions(const RegionArgs &ra, bool first, cudaStream_t st) {
+template <int RB, int THREADS, int RPT>
+int launch_regions_t(const RegionArgs &ra, bool first, cudaStream_t st) {
     constexpr int smem = (1 << RB) * 16;
-    const int per_sm = RB == 12 ? 3 : 6;
+    const int per_sm = RB == 12 ? 3 : (THREADS == 256 ? 6 : 4);
     int64_t maxg = (int64_t)pg_num_sms() * per_sm;
     const int grid = (int)(ra.n_regions < maxg ? ra.n_regions : maxg);
     if (first) {
-        PG_CUDA(cudaFuncSetAttribute(k3s_region_build<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k3s_region_build<RB, true><<<grid, 256, smem, st>>>(ra);
+        PG_CUDA(cudaFuncSetAttribute(k3s_region_build<RB, true, THREADS, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k3s_region_build<RB, true, THREADS, RPT><<<grid, THREADS, smem, st>>>(ra);
     } else {
-        PG_CUDA(cudaFuncSetAttribute(k3s_region_build<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k3s_region_build<RB, false><<<grid, 256, smem, st>>>(ra);
+        PG_CUDA(cudaFuncSetAttribute(k3s_region_build<RB, false, THREADS, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k3s_region_build<RB, false, THREADS, RPT><<<grid, THREADS, smem, st>>>(ra);
     }
     return PG_OK;
+}
+template <int RB>
+int launch_regions(const RegionArgs &ra, bool first, cudaStream_t st) {
+    static int thr = -1;
+    if (thr < 0) { const char *e = getenv("PG_K3S_THREADS"); thr = e ? atoi(e) : 512; }
+    if (thr == 256) return launch_regions_t<RB, 256, 4>(ra, first, st);
+    return launch_regions_t<RB, 512, 2>(ra, first, st);
 }
 
 }  // namespace

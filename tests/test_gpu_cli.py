@@ -69,8 +69,8 @@ def test_cli_dump_db_and_reload(tmp_path):
 
 
 def test_cli_stage1_runs_the_benchmarked_kernels(tmp_path):
-    """The drop-in's stage 1 is the build bench.py times: its kernel list holds k2a_partition and k3_insert_records (the
-    streaming two-phase build), not the fused single-launch kernel."""
+    """The drop-in's stage 1 is the build bench.py times: its kernel list holds k2a_partition and k3s_region_build (the
+    streaming build into shared-memory table regions), not the fused single-launch kernel."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -89,6 +89,6 @@ def test_cli_stage1_runs_the_benchmarked_kernels(tmp_path):
     if not names:
         pytest.skip("kernel tracing returned no events")
     assert any("k2a_partition" in n for n in names), sorted(names)
-    assert any("k3_insert_records" in n for n in names), sorted(names)
+    assert any("k3s_region_build" in n for n in names), sorted(names)
     assert any("k1_tile_pack" in n for n in names), sorted(names)
     assert not any("k2_kmer_insert" in n for n in names), sorted(names)
