@@ -237,6 +237,13 @@ int pg_insert_records(const pg_table *t, const uint64_t *d_records, const int64_
  * Replaces oakht.__setitem__ + resize (kmer_numba.py:423-474, 540-561) on the build path. */
 int pg_records_refine(const pg_bucket_set *coarse, int fine_bits, uint64_t *d_fine_records, int64_t *d_fine_counts,
                       int64_t fine_part_cap, int64_t fine_spill_cap, int64_t *d_table_stats, pg_stream_t stream);
+/* pg_records_resplit: pg_records_refine on raw arrays, for chains of splits (wire -> 2^5 -> 2^11 -> 2^18 buckets: three
+ * passes of <= 2^7 ways (in_bits <= 13) move a record at ~4 TB/s each, one pass of 2^10 ways at ~1 TB/s because its runs are 128 bytes):
+ * d_in holds 2^in_bits buckets of in_part_cap records + a spill of in_spill_cap (counters in d_in_counts, one more than
+ * buckets); bucket s is split 2^bits ways by hash bits [in_bits, in_bits + bits) into buckets [s << bits, ...) of d_out. */
+int pg_records_resplit(const uint64_t *d_in, const int64_t *d_in_counts, int in_bits, int64_t in_part_cap, int64_t in_spill_cap,
+                       int bits, uint64_t *d_out, int64_t *d_out_counts, int64_t out_part_cap, int64_t out_spill_cap,
+                       int64_t *d_table_stats, pg_stream_t stream);
 int pg_region_build(const pg_table *t, const uint64_t *d_records, const int64_t *d_counts, int64_t part_cap, int64_t spill_cap,
                     int first_round, pg_stream_t stream);
 

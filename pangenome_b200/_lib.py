@@ -61,6 +61,7 @@ SIGNATURES = {
     "pg_kmer_partition_to": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, BT, c_vp, c_i64, c_vp, c_vp]),
     "pg_records_split": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, BT, c_vp, c_vp]),
     "pg_records_refine": (c_int, [BT, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "pg_records_resplit": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "pg_region_build": (c_int, [PT, c_vp, c_vp, c_i64, c_i64, c_int, c_vp]),
     "pg_buckets_plan": (c_int, [BT, c_vp, c_vp, c_vp]),
     "pg_microbench_slots": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp]),

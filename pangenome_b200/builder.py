@@ -75,6 +75,22 @@ def plan_rounds(n_bases_max, rounds=None, round_len=None, tile=_TILE):
     return (n_bases_max + round_len - 1) // round_len, round_len
 
 
+def plan_levels(region_log, world):
+    """Fan-out bits of the partition levels that take a record down to one bucket per table region (2^region_log of
+    them).  Level 0 is K2a's (one GPU) or K2b's (what arrived over the wire) and goes through the bucket-set API (<= 2^10
+    buckets); every further level is a sliced re-split (pg_records_resplit, <= 2^8 ways, input <= 2^13 buckets).  A pass of
+    <= 2^7 ways moves a record at ~4 TB/s, one of 2^10 ways at ~1 TB/s (128-byte runs), so deep tables take three cheap
+    passes rather than two expensive ones."""
+    if region_log <= 8:
+        return [region_log]
+    first = 8 if world == 1 else (6 if region_log <= 12 else 5)
+    rest = region_log - first
+    if rest <= (5 if world == 1 else 7):
+        return [first, rest]
+    a = rest // 2
+    return [first, a, rest - a]
+
+
 def table_capacity_for(n_keys_upper, free_bytes, load=0.5, max_fraction=0.55):
     """Power-of-two slot count for at most ``n_keys_upper`` keys, never more than ``max_fraction`` of the free HBM."""
     cap = engine.next_pow2(max(1024, int(n_keys_upper / load) + 1))
@@ -129,14 +145,15 @@ class RoundBuilder:
         # one local set when a single round suffices, two alternating ones otherwise; across GPUs two receive buffers
         # (peer-written) plus the local set K2b fills
         spill = 1.0 + spill_frac
-        # shared-memory region build (one GPU): the table is a whole number of 2^region_bits-slot regions, K2a buckets by
-        # the top ``sub_bits`` hash bits and K2c refines every bucket down to one per region (one more record buffer)
+        # shared-memory region build: the table is a whole number of 2^region_bits-slot regions, K2a / K2b bucket by the top
+        # ``sub_bits`` hash bits and K2c refines every bucket down to one per region (one more record buffer)
         if region_bits is None:
             region_bits = int(os.environ.get("PG_REGION_BITS", str(self.REGION_BITS)))
+        self._region_pref = region_bits if region_bits in (8, 12) else 0
         cap_log = cap.bit_length() - 1
-        self.region_bits = region_bits if (W == 1 and region_bits in (8, 12) and 0 <= cap_log - region_bits <= self.MAX_REGION_LOG) else 0
+        region_now = bool(self._region_pref) and 0 <= cap_log - self._region_pref <= self.MAX_REGION_LOG
         if W == 1:
-            fine = 16.0 * per_pos * slack * spill if self.region_bits else 0.0
+            fine = 16.0 * per_pos * slack * spill if region_now else 0.0
             bpp1, bppn = 16.0 * per_pos * slack * spill + fine, 2 * 16.0 * per_pos * slack * spill + fine
         else:
             bpp1 = bppn = 16.0 * slack * (2 + slack * spill)
@@ -148,34 +165,17 @@ class RoundBuilder:
             rounds = max(rounds, (n_max + self.MAX_ROUND - 1) // self.MAX_ROUND)
         self.n_rounds, self.round_len = plan_rounds(n_max, rounds, round_len)
         R = self.round_len
-        self.table = engine.DbgTable(cap, self.k, self.mode, device=dev)
         if sub_bytes is None:
             sub_bytes = int(os.environ.get("PG_SUB_MB", "8")) << 20
-        self.sub_bits = engine.sub_bits_for(cap, sub_bytes)
-        self.adaptive = bool(self.region_bits) and not capacity
+        self._sub_bytes, self._per_pos, self._slack, self._spill_frac = sub_bytes, per_pos, slack, spill_frac
+        self.table, self.sets, self.sub_bits, self.region_bits = None, None, None, 0
+        self.fine_records = self.fine_counts = None
+        self.adaptive = bool(self._region_pref) and not capacity
         self.sampler = None
-        if self.region_bits:
-            region_log = cap_log - self.region_bits
-            self.sub_bits = region_log if region_log <= 8 else max(8, region_log - 8)
-            self.table.c.region_bits = self.region_bits
-            self.min_capacity = 1 << (self.sub_bits + self.region_bits)       # K2a's buckets must not be finer than the regions
-            if sample and self.n_rounds == 1 and not capacity:
-                self.sampler = engine.KeySampler(n_max * per_pos, dev)
-        n_sub = 1 << self.sub_bits
         # ---- record buffers
         if W == 1:
-            part_cap = int(R * per_pos / n_sub * slack) + 2048
-            spill_cap = max(1 << 16, int(R * per_pos * spill_frac))
-            self.sets = [LocalBuckets(self.sub_bits, part_cap, spill_cap, dev) for _ in range(2 if self.n_rounds > 1 else 1)]
+            self._arriving = R * per_pos
             self.wire = None
-            if self.region_bits:
-                # the fine set: (capacity >> region_bits) buckets + one spill, laid out per build for the capacity in use
-                self._fine_total = int(R * per_pos * slack)
-                self._fine_pad = 256
-                n_regions_max = cap >> self.region_bits
-                self.fine_spill_cap = spill_cap
-                self.fine_records = torch.empty(2 * (self._fine_total + n_regions_max * self._fine_pad + spill_cap), dtype=torch.int64, device=dev)
-                self.fine_counts = torch.zeros(n_regions_max + 1, dtype=torch.int64, device=dev)
         else:
             self.cap_wire = cw = int(R / W * slack) + 8192
             self.wire_bytes = W * cw * 16
@@ -204,10 +204,11 @@ class RoundBuilder:
                                                   self.owner_bits, 0, rank, 0))
             self.wire_seg_off = torch.arange(W, dtype=torch.int64, device=dev) * cw
             self.sent_total = torch.zeros(W, dtype=torch.int64, device=dev)
-            arriving = W * cw
-            part_cap = int(arriving / n_sub * slack) + 2048
-            spill_cap = max(1 << 16, int(arriving * spill_frac))
-            self.sets = [LocalBuckets(self.sub_bits, part_cap, spill_cap, dev)]
+            self._arriving = W * cw
+        self._configure(cap)
+        if self.region_bits and W == 1 and sample and self.n_rounds == 1 and not capacity:
+            self.sampler = engine.KeySampler(n_max * per_pos, dev)
+        if W > 1:
             dist.barrier()
         self.sA, self.sB = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         self._round = 0                     # global round counter: buffer parity carries over from build to build
@@ -216,16 +217,70 @@ class RoundBuilder:
         self._begun = False
         self._next_capacity = None
         self.desc = _lib.PgTable(None, 2, None, self.mode, self.k, 1, 0, 0)      # K2a reads mode and k only
-        self.launches_per_round = 3 if W == 1 else 4      # K2a, plan, K3 (+ K2b); the count exchange is NCCL's
-        if self.region_bits:
-            self.launches_per_round = 4                   # K2a, K2c, K3s, spill upserts
-        self.launches_per_build = 1 + self.n_rounds * self.launches_per_round       # + count_short
+
+    @property
+    def launches_per_round(self):
+        """Kernels of this library per round: K2a, (K2b,) then plan + K3, or K2c + K3s + spill upserts."""
+        n = 1 + (1 if self.world > 1 else 0)
+        return n + ((len(self.levels) - 1 + 2) if self.region_bits else 2)
+
+    @property
+    def launches_per_build(self):
+        return 1 + self.n_rounds * self.launches_per_round       # + count_short
+
+    def _configure(self, cap):
+        """(Re)build everything that depends on the table capacity: the table itself (a table at least 4x larger than
+        needed is released), whether it is built in shared-memory regions, how many hash-prefix buckets K2a / K2b
+        produce, and the fine bucket set of K2c.  Called at construction and, between builds, by begin() after verify()
+        retuned the capacity."""
+        dev, rb = self.device, self._region_pref
+        cap = engine.next_pow2(cap)
+        cap_log = cap.bit_length() - 1
+        region = bool(rb) and 0 <= cap_log - rb <= self.MAX_REGION_LOG
+        if region:
+            self.levels = plan_levels(cap_log - rb, self.world)
+            sub_bits = self.levels[0]
+        else:
+            self.levels = None
+            sub_bits = engine.sub_bits_for(cap, self._sub_bytes)
+        have = self.table.slots.numel() // 2 if self.table is not None else 0
+        if have < cap or have >= 4 * cap:
+            self.table = None                                    # release before allocating
+            self.table = engine.DbgTable(cap, self.k, self.mode, device=dev)
+        else:
+            self.table.set_capacity(cap)
+        self.region_bits = rb if region else 0
+        self.table.c.region_bits = self.region_bits
+        n_sub = 1 << sub_bits
+        part_cap = int(self._arriving / n_sub * self._slack) + 2048
+        spill_cap = max(1 << 16, int(self._arriving * self._spill_frac))
+        if self.sets is None or sub_bits != self.sub_bits:
+            n_sets = 2 if (self.world == 1 and self.n_rounds > 1) else 1
+            self.sets = None
+            self.sets = [LocalBuckets(sub_bits, part_cap, spill_cap, dev) for _ in range(n_sets)]
+            self._ev_free = [None, None]
+        self.sub_bits = sub_bits
+        if region and len(self.levels) > 1:
+            # the re-split levels ping-pong between a second record buffer and the memory of the level-0 set; every level has
+            # its own counters.  Buckets of a level share its buffer evenly (laid out per build for the capacity in use).
+            n_regions = cap >> rb
+            self.fine_spill_cap = spill_cap
+            need = 2 * (int(self._arriving * self._slack) + n_regions * 256 + spill_cap)
+            if self.fine_records is None or self.fine_records.numel() < need:
+                self.fine_records = None
+                self.fine_records = torch.empty(need, dtype=torch.int64, device=dev)
+            n_max = n_regions
+            if self.fine_counts is None or any(c.numel() < n_max + 1 for c in self.fine_counts) or len(self.fine_counts) < len(self.levels) - 1:
+                self.fine_counts = [torch.zeros(n_max + 1, dtype=torch.int64, device=dev) for _ in self.levels[1:]]
+        # a sampled build fills K2a's buckets before the capacity is known: it must keep at least one region per bucket
+        self.min_capacity = (1 << (sub_bits + rb)) if region else 1024
 
     # ------------------------------------------------------------------------------------------------
     def begin(self):
         """Empty the table for the next build: an epoch bump (DbgTable.clear), no HBM traffic."""
         if self._next_capacity and self._next_capacity != self.table.capacity:
-            self.table.set_capacity(self._next_capacity)
+            torch.cuda.synchronize(self.device)          # buffers may be replaced: nothing of the last build may be in flight
+            self._configure(self._next_capacity)
         self._next_capacity = None
         self.table.clear()
         self._begun = True
@@ -316,15 +371,22 @@ class RoundBuilder:
                 else:
                     x2 = stamp(B)
                 if self.region_bits:
-                    n_regions = t.capacity >> self.region_bits
-                    fine_bits = (n_regions.bit_length() - 1) - self.sub_bits
-                    if fine_bits > 0:          # K2c: one bucket per region
-                        fine_cap = self._fine_total // n_regions + self._fine_pad
-                        check(L.pg_records_refine(byref(bs.c), fine_bits, P(self.fine_records), P(self.fine_counts), fine_cap,
-                                                  self.fine_spill_cap, P(t.stats), engine._stream()), "pg_records_refine")
-                        recs, cnts, pcap, scap = self.fine_records, self.fine_counts, fine_cap, self.fine_spill_cap
-                    else:
-                        recs, cnts, pcap, scap = bs.records, bs.counts, bs.c.part_cap, bs.c.spill_cap
+                    # K2c: re-split level by level down to one bucket per region (the capacity may have been set from the
+                    # key sample after K2a ran: the levels after the first follow the capacity in use)
+                    region_log = (t.capacity >> self.region_bits).bit_length() - 1
+                    levels = [self.sub_bits] + plan_levels(region_log, W)[1:] if region_log > self.sub_bits else [self.sub_bits]
+                    if sum(levels) != region_log:              # sampled capacity: one or two even levels below K2a's buckets
+                        rest = region_log - self.sub_bits
+                        levels = [self.sub_bits] + ([rest] if rest <= 8 else [rest // 2, rest - rest // 2])
+                    recs, cnts, bits, pcap, scap = bs.records, bs.counts, self.sub_bits, bs.c.part_cap, bs.c.spill_cap
+                    bufs = [self.fine_records, bs.records]
+                    for li, lb in enumerate(levels[1:]):
+                        out, ocnt = bufs[li % 2], self.fine_counts[li]
+                        n_out = 1 << (bits + lb)
+                        ocap = (out.numel() // 2 - self.fine_spill_cap) // n_out
+                        check(L.pg_records_resplit(P(recs), P(cnts), bits, pcap, scap, lb, P(out), P(ocnt), ocap, self.fine_spill_cap,
+                                                   P(t.stats), engine._stream()), "pg_records_resplit")
+                        recs, cnts, bits, pcap, scap = out, ocnt, bits + lb, ocap, self.fine_spill_cap
                     x2c = stamp(B)
                     check(L.pg_region_build(byref(t.c), P(recs), P(cnts), pcap, scap, 1 if r == 0 else 0, engine._stream()), "pg_region_build")
                     if ev is not None:
@@ -352,12 +414,13 @@ class RoundBuilder:
     def flags(self):
         """(table full, records lost) after a synchronise; agreed on by all ranks."""
         s = self.table.stats_host()
-        self._last_used = int(s[_lib.PG_STAT_USED])
-        f = torch.tensor([int(s[_lib.PG_STAT_OVERFLOW] != 0), int(s[_lib.PG_STAT_LOST] != 0)], dtype=torch.int64, device=self.device)
+        f = torch.tensor([int(s[_lib.PG_STAT_OVERFLOW] != 0), int(s[_lib.PG_STAT_LOST] != 0), int(s[_lib.PG_STAT_USED])], dtype=torch.int64,
+                         device=self.device)
         if self.world > 1:
             # a truncated record index poisons the wire counts: the receiver flags PG_STAT_LOST, so it is covered here
             dist.all_reduce(f, op=dist.ReduceOp.MAX)
         f = f.cpu()
+        self._last_used = int(f[2])             # the fullest rank's distinct keys: every rank retunes to the same capacity
         return bool(f[0]), bool(f[1])
 
     def verify(self):
@@ -375,8 +438,11 @@ class RoundBuilder:
         is given and the stages after it scan every slot, so a table 4x too large costs 4x their HBM traffic; a table
         too small shows as TableFull and the caller rebuilds larger.  Never below one region per K2a bucket."""
         used = self._last_used
-        want = max(self.min_capacity, engine.next_pow2(max(2, int(used / load) + 1)))
-        self._next_capacity = min(want, self.table.slots.numel() // 2)        # applied by begin(): the table just built keeps its size
+        want = engine.next_pow2(max(1024, int(used / load) + 1))
+        limit = 1 << (self._region_pref + self.MAX_REGION_LOG)
+        if want > limit and used <= 0.7 * limit:              # a denser table (load <= 0.7) that can still be built in regions
+            want = limit
+        self._next_capacity = want                            # applied by begin(): the table just built keeps its size
 
     def close(self):
         torch.cuda.synchronize()
@@ -390,7 +456,8 @@ class RoundBuilder:
 
     def describe(self):
         d = {"rounds": self.n_rounds, "round_len": self.round_len, "table_slots": self.table.capacity, "regions": 1 << self.sub_bits,
-             "insert": ("K2c + K3s: %d shared-memory regions of %d slots" % (self.table.capacity >> self.region_bits, 1 << self.region_bits))
+             "insert": ("K2c + K3s: %d shared-memory regions of %d slots, partition levels (bits) %r"
+                        % (self.table.capacity >> self.region_bits, 1 << self.region_bits, self.levels))
                        if self.region_bits else "K3: L2 atomics over %d hash-prefix regions" % (1 << self.sub_bits),
              "record_buffers_bytes": sum(s.bytes() for s in self.sets) + (2 * self.wire_bytes if self.world > 1 else 0)}
         if self.world > 1:

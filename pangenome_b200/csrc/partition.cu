@@ -474,6 +474,16 @@ extern "C" int pg_records_split(const uint64_t *d_records_in, const int64_t *d_s
     PG_CUDA(cudaMemsetAsync(out->d_part_counts, 0, (size_t)(a.out.n_parts + 1) * 8, st));
     a.in = reinterpret_cast<const uint4 *>(d_records_in); a.seg_off = d_seg_off; a.seg_cnt = d_seg_cnt; a.n_seg = n_seg; a.seg_cap = seg_cap;
     a.stats = d_table_stats;
+    static int v1 = -1;
+    if (v1 < 0) { const char *e = getenv("PG_SPLIT_V1"); v1 = e ? atoi(e) : 0; }
+    if (!v1) {
+        PgMultiSplit m;
+        m.in = a.in; m.seg_off = d_seg_off; m.seg_cnt = reinterpret_cast<const unsigned long long *>(d_seg_cnt); m.n_seg = n_seg; m.seg_cap = seg_cap;
+        m.pass_seg = -1; m.pass_cap = 0; m.lost_on_clamp = 1;
+        m.out = a.out.records; m.out_counts = a.out.part_counts; m.out_part_cap = a.out.part_cap; m.out_spill_cap = a.out.spill_cap;
+        m.n_out = a.out.n_parts; m.skip_bits = 0; m.bits = out->sub_bits; m.sliced = 0; m.stats = d_table_stats;
+        return pg_multisplit_launch(m, st);
+    }
     static int thr_env = -1;
     if (thr_env < 0) { const char *e = getenv("PG_K2B_THREADS"); thr_env = e ? atoi(e) : 0; }
     const int threads = (thr_env == 256 || thr_env == 512) ? thr_env : (a.out.n_parts > 256 ? 512 : 256);

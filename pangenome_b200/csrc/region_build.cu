@@ -303,6 +303,17 @@ extern "C" int pg_records_refine(const pg_bucket_set *coarse, int fine_bits, uin
     cudaStream_t st = (cudaStream_t)stream_;
     const int64_t n_fine = (int64_t)co.n_parts << fine_bits;
     PG_CUDA(cudaMemsetAsync(d_fine_counts, 0, (size_t)(n_fine + 1) * 8, st));
+    static int v1 = -1;
+    if (v1 < 0) { const char *e = getenv("PG_SPLIT_V1"); v1 = e ? atoi(e) : 0; }
+    if (!v1) {
+        PgMultiSplit m;
+        m.in = co.records; m.seg_off = nullptr; m.seg_cnt = co.part_counts; m.n_seg = co.n_parts + 1; m.seg_cap = co.part_cap;
+        m.pass_seg = co.n_parts; m.pass_cap = co.spill_cap; m.lost_on_clamp = 0;
+        m.out = reinterpret_cast<uint4 *>(d_fine_records); m.out_counts = reinterpret_cast<unsigned long long *>(d_fine_counts);
+        m.out_part_cap = fine_part_cap; m.out_spill_cap = fine_spill_cap; m.n_out = n_fine;
+        m.skip_bits = coarse->sub_bits; m.bits = fine_bits; m.sliced = 1; m.stats = d_table_stats;
+        return pg_multisplit_launch(m, st);
+    }
     RefineArgs a;
     a.in = co.records; a.in_counts = co.part_counts; a.n_seg = co.n_parts; a.seg_cap = co.part_cap; a.in_spill_cap = co.spill_cap;
     a.out = reinterpret_cast<uint4 *>(d_fine_records); a.out_counts = reinterpret_cast<unsigned long long *>(d_fine_counts);

@@ -180,3 +180,20 @@ static int ctas_per_sm(int smem_dynamic, int smem_static) {
 }
 
 }  // namespace
+
+// ---- the register-held multisplit (multisplit.cu): K2b and K2c without the permutation pass ----------------------
+// Segments of records in, hash-prefix buckets out.  K2b: n_seg wire segments (seg_off given) -> one local set, bucket =
+// top `bits` hash bits.  K2c: segment s = coarse bucket s (offset s * seg_cap, the set's spill as one more segment that is
+// passed through to the output spill) -> buckets [s << bits, (s + 1) << bits) of the fine set, bucket = the next `bits`
+// hash bits after the `skip_bits` the coarse pass used.
+struct PgMultiSplit {
+    const uint4 *in; const int64_t *seg_off; const unsigned long long *seg_cnt; int n_seg; int64_t seg_cap;
+    int pass_seg; int64_t pass_cap;          // index of the pass-through (spill) segment or -1, and its capacity
+    int lost_on_clamp;                       // a count above seg_cap means records were dropped upstream (K2b): raise PG_STAT_LOST
+    uint4 *out; unsigned long long *out_counts; int64_t out_part_cap, out_spill_cap; int64_t n_out;   // n_out buckets, then the spill
+    int skip_bits, bits, sliced;             // sliced: segment s writes buckets [s << bits, ...)
+    int64_t *stats;
+    int policy;                              // cache-hint experiment switch (PG_SPLIT_POLICY)
+};
+int pg_multisplit_launch(const PgMultiSplit &a, cudaStream_t st);
+
