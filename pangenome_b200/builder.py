@@ -78,14 +78,15 @@ def plan_rounds(n_bases_max, rounds=None, round_len=None, tile=_TILE):
 def plan_levels(region_log, world):
     """Fan-out bits of the partition levels that take a record down to one bucket per table region (2^region_log of
     them).  Level 0 is K2a's (one GPU) or K2b's (what arrived over the wire) and goes through the bucket-set API (<= 2^10
-    buckets); every further level is a sliced re-split (pg_records_resplit, <= 2^8 ways, input <= 2^13 buckets).  A pass of
-    <= 2^7 ways moves a record at ~4 TB/s, one of 2^10 ways at ~1 TB/s (128-byte runs), so deep tables take three cheap
-    passes rather than two expensive ones."""
+    buckets); every further level is a sliced re-split (pg_records_resplit, <= 2^8 ways, input <= 2^13 buckets).  As few
+    levels as the fan-out limits allow: on BASELINE config 4 at 2 GPUs (2^18 regions per rank) [10, 8], [5, 6, 7] and the
+    older tile sort measured 104 / 107 / 101 ms per step - a pass costs its 32 B per record whatever its fan-out, so the
+    third pass eats what the longer runs of the first two win."""
     if region_log <= 8:
         return [region_log]
-    first = 8 if world == 1 else (6 if region_log <= 12 else 5)
+    first = 8 if world == 1 else min(10, max(6, region_log - 8))
     rest = region_log - first
-    if rest <= (5 if world == 1 else 7):
+    if rest <= 8:
         return [first, rest]
     a = rest // 2
     return [first, a, rest - a]
@@ -243,12 +244,14 @@ class RoundBuilder:
         else:
             self.levels = None
             sub_bits = engine.sub_bits_for(cap, self._sub_bytes)
-        have = self.table.slots.numel() // 2 if self.table is not None else 0
-        if have < cap or have >= 4 * cap:
-            self.table = None                                    # release before allocating
+        if self.table is None:
             self.table = engine.DbgTable(cap, self.k, self.mode, device=dev)
         else:
-            self.table.set_capacity(cap)
+            have = self.table.slots.numel() // 2
+            if have < cap or have >= 4 * cap:
+                self.table.reallocate(cap)                       # in place: callers keep their reference to the table
+            else:
+                self.table.set_capacity(cap)
         self.region_bits = rb if region else 0
         self.table.c.region_bits = self.region_bits
         n_sub = 1 << sub_bits
@@ -268,6 +271,11 @@ class RoundBuilder:
             need = 2 * (int(self._arriving * self._slack) + n_regions * 256 + spill_cap)
             if self.fine_records is None or self.fine_records.numel() < need:
                 self.fine_records = None
+                torch.cuda.empty_cache()                         # what the old table held goes back to the driver first
+                if need * 8 > 0.97 * torch.cuda.mem_get_info(dev)[0]:
+                    # no room for the second record buffer: keep the L2-atomic K3 for this builder
+                    self._region_pref = 0
+                    return self._configure(cap)
                 self.fine_records = torch.empty(need, dtype=torch.int64, device=dev)
             n_max = n_regions
             if self.fine_counts is None or any(c.numel() < n_max + 1 for c in self.fine_counts) or len(self.fine_counts) < len(self.levels) - 1:

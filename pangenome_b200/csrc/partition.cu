@@ -476,7 +476,7 @@ extern "C" int pg_records_split(const uint64_t *d_records_in, const int64_t *d_s
     a.stats = d_table_stats;
     static int v1 = -1;
     if (v1 < 0) { const char *e = getenv("PG_SPLIT_V1"); v1 = e ? atoi(e) : 0; }
-    if (!v1) {
+    if (!v1 && a.out.n_parts <= 256) {       // beyond 256 ways the 8192-record tile sort below is the faster one (profiles/r2k_*)
         PgMultiSplit m;
         m.in = a.in; m.seg_off = d_seg_off; m.seg_cnt = reinterpret_cast<const unsigned long long *>(d_seg_cnt); m.n_seg = n_seg; m.seg_cap = seg_cap;
         m.pass_seg = -1; m.pass_cap = 0; m.lost_on_clamp = 1;

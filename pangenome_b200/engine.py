@@ -176,6 +176,17 @@ class DbgTable:
         (pg_table_reset rewrites the slots only when the 10-bit generation tag wraps)."""
         check(self.L.pg_table_reset(ctypes.byref(self.c), _stream()), "pg_table_reset")
 
+    def reallocate(self, capacity):
+        """Replace the slot buffer by one of ``capacity`` slots IN PLACE (every holder of this object sees the new table;
+        the old buffer is released before the new one is requested).  The contents are gone: epoch 1, all slots cleared."""
+        dev = self.slots.device
+        self.capacity = next_pow2(capacity)
+        self.slots = None
+        self.c.d_slots = None
+        self.slots = torch.empty(2 * self.capacity, dtype=torch.int64, device=dev)
+        self.c.d_slots, self.c.capacity, self.c.alloc_capacity, self.c.epoch = self.slots.data_ptr(), self.capacity, self.capacity, 1
+        check(self.L.pg_table_clear(ctypes.byref(self.c), _stream()), "pg_table_clear")
+
     def set_capacity(self, capacity):
         """Use only the first ``capacity`` (power of two) slots of the allocated buffer."""
         capacity = next_pow2(capacity)
