@@ -272,7 +272,8 @@ class RoundBuilder:
             if self.fine_records is None or self.fine_records.numel() < need:
                 self.fine_records = None
                 torch.cuda.empty_cache()                         # what the old table held goes back to the driver first
-                if need * 8 > 0.97 * torch.cuda.mem_get_info(dev)[0]:
+                room = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+                if need * 8 > 0.97 * room:
                     # no room for the second record buffer: keep the L2-atomic K3 for this builder
                     self._region_pref = 0
                     return self._configure(cap)

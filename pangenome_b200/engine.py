@@ -183,6 +183,7 @@ class DbgTable:
         self.capacity = next_pow2(capacity)
         self.slots = None
         self.c.d_slots = None
+        torch.cuda.empty_cache()          # hand the old segment back whole: a smaller table must not pin it by living inside it
         self.slots = torch.empty(2 * self.capacity, dtype=torch.int64, device=dev)
         self.c.d_slots, self.c.capacity, self.c.alloc_capacity, self.c.epoch = self.slots.data_ptr(), self.capacity, self.capacity, 1
         check(self.L.pg_table_clear(ctypes.byref(self.c), _stream()), "pg_table_clear")
