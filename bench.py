@@ -414,34 +414,37 @@ def main():
     if os.path.isfile(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get((args.workload + ("_region" if getattr(bld, "region_bits", 0) else "")) if world == 1
+                traffic = json.load(f).get((args.workload + ("_compact" if getattr(bld, "compact", False) else
+                                                             ("_region" if getattr(bld, "region_bits", 0) else ""))) if world == 1
                                            else "%s_n%d" % (args.workload, world))
         except Exception:
             traffic = None
     region = bool(getattr(bld, "region_bits", 0))
-    roof = {"kernel": "k3s_region_build" if region else "k3_insert_records", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    rec_b = 8.0 if getattr(bld, "compact", False) else 16.0          # bytes per update record on the streaming stages
+    roof = {"kernel": ("k3s_region_build_c" if rec_b == 8.0 else "k3s_region_build") if region else "k3_insert_records", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src, "ms_per_launch": k3_launch_ms, "launches_per_step": bld.n_rounds,
             "algorithmic_bytes_per_launch": alg_launch,
             "convention": "insert: 16 B per insertion (SURVEY 8d), 2 insertions per record, per rank and round" +
-                          (" (K3s + spill upserts; what it really moves: 16 B/record read + 16 B/slot written = %.0f MB)"
-                           % ((8.0 * n_ins / world / bld.n_rounds + 16.0 * cap) / 1e6) if region else ""),
+                          (" (K3s + spill upserts; what it really moves: %d B/record read + 16 B/slot written = %.0f MB)"
+                           % (rec_b, (rec_b / 2 * n_ins / world / bld.n_rounds + 16.0 * cap) / 1e6) if region else ""),
             "sector_convention": {"bytes_per_launch": sector_launch, "achieved": sector_launch / (k3_launch_ms * 1e-3) / 1e9,
                                   "frac": sector_launch / (k3_launch_ms * 1e-3) / 1e9 / peak,
                                   "what": "64 B per record: one 32-byte sector read + written back (SURVEY 8d minimum DRAM traffic)"},
             "other_kernels": {}}
-    part_bytes = (0.25 * n_bases + 16.0 * (n_ins / 2)) / world / bld.n_rounds
+    part_bytes = (0.25 * n_bases + rec_b * (n_ins / 2)) / world / bld.n_rounds
     k2a_ms = allmax(sum(a.elapsed_time(b) for a, b in kev["k2a"]) / len(kev["k2a"]))
     roof["other_kernels"]["k2a_partition"] = {
         "ms_per_launch": k2a_ms, "algorithmic_bytes_per_launch": part_bytes, "achieved": part_bytes / (k2a_ms * 1e-3) / 1e9,
         "frac": part_bytes / (k2a_ms * 1e-3) / 1e9 / peak,
-        "convention": "0.25 B/base read + 16 B/record written (materialised for the exchange)" +
+        "convention": "0.25 B/base read + %d B/record written%s" % (rec_b, " (materialised for the exchange)" if world > 1 else "") +
                       (", stored into the owners' receive buffers over NVLink" if world > 1 else "")}
     if "k2c" in kev:
         k2c_ms = allmax(sum(a.elapsed_time(b) for a, b in kev["k2c"]) / len(kev["k2c"]))
-        b2 = 32.0 * (n_ins / 2) / world / bld.n_rounds
+        b2 = 2 * rec_b * (n_ins / 2) / world / bld.n_rounds * max(1, len(bld.levels) - 1)
         roof["other_kernels"]["k2c_refine"] = {"ms_per_launch": k2c_ms, "algorithmic_bytes_per_launch": b2, "achieved": b2 / (k2c_ms * 1e-3) / 1e9,
                                                "frac": b2 / (k2c_ms * 1e-3) / 1e9 / peak,
-                                               "convention": "16 B/record read + 16 B/record written (hash-prefix buckets -> one bucket per table region)"}
+                                               "convention": "%d B/record read + %d B/record written per partition level, %d level(s) (hash-prefix buckets -> one bucket per table region)"
+                                                             % (rec_b, rec_b, max(1, len(bld.levels) - 1))}
     if world > 1:
         k2b_ms = allmax(sum(a.elapsed_time(b) for a, b in kev["k2b"]) / len(kev["k2b"]))
         b2 = 32.0 * (n_ins / 2) / world / bld.n_rounds
@@ -473,7 +476,7 @@ def main():
                    "table_slots_per_gpu": cap, "table_bytes_per_gpu": cap * 16, "distinct_canonical_keys": used,
                    "load_factor": used / (cap * world), "builder": bld.describe(),
                    "l2": "every step writes and re-reads %.2f GB of update records per GPU and randomly updates its %.1f GB table (both >> 126 MB L2), which evicts the input"
-                         % (n_ins / 2 * 16 / world / 1e9, cap * 16 / 1e9)},
+                         % (n_ins / 2 * rec_b / world / 1e9, cap * 16 / 1e9)},
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": allsum(int(host.numel())),
                 "d2h_bytes_per_step": int(8 * _lib.PG_STAT_WORDS) * world,
                 "pipelining": "input i+1 uploads and result i-1 is read while step i runs"},

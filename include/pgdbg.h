@@ -75,6 +75,10 @@ typedef struct pg_table {
     int64_t alloc_capacity; /* slots allocated behind d_slots when `capacity` selects only a prefix of the buffer
                                (0 = same as capacity).  When the 10-bit tag wraps, pg_table_reset rewrites ALL of
                                them: a slot beyond `capacity` must not keep a tag of the previous cycle. */
+    int32_t hash_kind;   /* which code the slot-placement hash is taken of: 0 = the base-5 key (default), 1 = the 2-bit code of
+                            an ACGT-only key (keys with an ambiguity digit: the complemented base-5 key) - the layout
+                            pg_region_build_c produces from compact 8-byte records; every later upsert / look-up keeps it */
+    int32_t reserved;
 } pg_table;
 
 const char *pg_last_error(void);
@@ -246,6 +250,37 @@ int pg_records_resplit(const uint64_t *d_in, const int64_t *d_in_counts, int in_
                        int64_t *d_table_stats, pg_stream_t stream);
 int pg_region_build(const pg_table *t, const uint64_t *d_records, const int64_t *d_counts, int64_t part_cap, int64_t spill_cap,
                     int first_round, pg_stream_t stream);
+
+/* ---- the same build on COMPACT 8-byte update records (csrc/compact_build.cu) -----------------------------------
+ * An interior position (the k-mer, the base before and the base after it are ACGT inside one record) travels as
+ *     [ 2-bit code of the canonical k-mer : 54 | previous base * 4 + next base : 4 | rc strand is the key : 1 | palindrome : 1 | 0 : 4 ]
+ * and every other position (record edges: '#', '$', Q1; ambiguity codes) as a 16-byte WIDE record {base-5 key, masks,
+ * increment} in the set's wide spill, where a compact record whose bucket is full goes as well.  Half the record
+ * traffic of the 16-byte path and no base-5 arithmetic in the extraction (both strands' codes roll with shifts); the
+ * base-5 key the reference's table holds (kmer_numba.py:975-988) is produced when a finished region is written out.
+ * Buckets and slots are placed by mix64 of the 2-BIT code: the table must carry hash_kind = 1 (and region_bits = 12).
+ * PG_MODE_CANONICAL only.  One pg_cbuckets per partition level; all levels of a round share the wide spill.
+ * pg_kmer_partition_c (K2a-c): arguments as pg_kmer_partition_to; zeroes out->d_counts and *out->d_wide_count.
+ * pg_records_resplit_c (K2c-c): bucket s of `in` is split 2^bits ways (1..8) by hash bits [in->bits, in->bits + bits)
+ *   into buckets [s << bits, ...) of `out` (out->bits == in->bits + bits; zeroes out->d_counts).
+ * pg_region_build_c (K3s-c): bucket b of `b` (b->bits == log2(capacity) - 12) becomes region b of the table, then the
+ *   wide spill is upserted with L2 atomics.  first_round as pg_region_build.  PG_STAT_OVERFLOW: a region filled up;
+ *   PG_STAT_LOST: the wide spill exceeded wide_cap (or K1's record index was truncated) - rebuild on the 16-byte path. */
+typedef struct pg_cbuckets {
+    uint64_t *d_records;     /* 2^bits buckets of part_cap (even) 8-byte records, 16-byte aligned */
+    int64_t *d_counts;       /* 2^bits counters: records PRODUCED for the bucket (the surplus over part_cap went to the wide spill) */
+    int64_t part_cap;
+    int32_t bits, reserved;
+    uint64_t *d_wide;        /* wide_cap 16-byte records */
+    int64_t *d_wide_count;   /* one counter: records offered to the wide spill */
+    int64_t wide_cap;
+} pg_cbuckets;
+int pg_kmer_partition_c(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
+                        int64_t n_rec, int64_t g_begin, int64_t g_end, const int64_t *d_counts, int64_t cap_records,
+                        int64_t max_bases, const pg_cbuckets *out, uint64_t *d_sample_keys, int64_t sample_cap,
+                        int64_t *d_sample_count, pg_stream_t stream);
+int pg_records_resplit_c(const pg_cbuckets *in, int bits, const pg_cbuckets *out, int k, int64_t *d_table_stats, pg_stream_t stream);
+int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int first_round, pg_stream_t stream);
 
 /* ---- table read-out ---------------------------------------------------------
  * pg_table_count   : fills PG_STAT_USED / PG_STAT_ENTRIES in t->d_stats.

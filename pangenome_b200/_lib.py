@@ -15,7 +15,7 @@ c_i64, c_int, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
 class PgTable(ctypes.Structure):
     _fields_ = [("d_slots", c_vp), ("capacity", c_i64), ("d_stats", c_vp), ("mode", ctypes.c_int32),
                 ("k", ctypes.c_int32), ("epoch", ctypes.c_int32), ("region_bits", ctypes.c_int32),
-                ("alloc_capacity", c_i64)]
+                ("alloc_capacity", c_i64), ("hash_kind", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 PT = ctypes.POINTER(PgTable)
@@ -36,6 +36,15 @@ class PgBucketSet(ctypes.Structure):
 
 
 BT = ctypes.POINTER(PgBucketSet)
+
+
+class PgCBuckets(ctypes.Structure):
+    """Compact (8-byte) update records: include/pgdbg.h pg_cbuckets."""
+    _fields_ = [("d_records", c_vp), ("d_counts", c_vp), ("part_cap", c_i64), ("bits", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("d_wide", c_vp), ("d_wide_count", c_vp), ("wide_cap", c_i64)]
+
+
+CT = ctypes.POINTER(PgCBuckets)
 
 # name -> (restype, argtypes); every symbol include/pgdbg.h declares
 SIGNATURES = {
@@ -64,6 +73,9 @@ SIGNATURES = {
     "pg_records_resplit": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "pg_region_build": (c_int, [PT, c_vp, c_vp, c_i64, c_i64, c_int, c_vp]),
     "pg_buckets_plan": (c_int, [BT, c_vp, c_vp, c_vp]),
+    "pg_kmer_partition_c": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, CT, c_vp, c_i64, c_vp, c_vp]),
+    "pg_records_resplit_c": (c_int, [CT, c_int, CT, c_int, c_vp, c_vp]),
+    "pg_region_build_c": (c_int, [PT, CT, c_int, c_vp]),
     "pg_microbench_slots": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "pg_table_count": (c_int, [PT, c_vp]),
     "pg_table_export": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),

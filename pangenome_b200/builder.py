@@ -29,7 +29,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, engine
-from ._lib import PgBucketSet, PgError, check
+from ._lib import PgBucketSet, PgCBuckets, PgError, check
 
 _TILE = 8192
 
@@ -63,6 +63,27 @@ class LocalBuckets:
 
     def bytes(self):
         return self.records.numel() * 8
+
+
+class CompactBuckets:
+    """The buffers of a compact (8-byte record) build, include/pgdbg.h pg_cbuckets: the level-0 buckets K2a-c fills and the
+    wide spill every level of the round shares (16-byte records the compact form cannot hold + bucket surplus)."""
+
+    def __init__(self, bits, part_cap, wide_cap, device):
+        self.bits, self.n_parts, self.part_cap, self.wide_cap = bits, 1 << bits, int(part_cap) + (int(part_cap) & 1), int(wide_cap)
+        self.records = torch.empty(self.n_parts * self.part_cap, dtype=torch.int64, device=device)
+        self.counts = torch.zeros(self.n_parts, dtype=torch.int64, device=device)
+        self.wide = torch.empty(2 * self.wide_cap, dtype=torch.int64, device=device)
+        self.wide_count = torch.zeros(1, dtype=torch.int64, device=device)
+        self.c = self.view(self.records, self.counts, bits, self.part_cap)
+
+    def view(self, records, counts, bits, part_cap):
+        """A pg_cbuckets over ``records`` / ``counts`` (another partition level) sharing this set's wide spill."""
+        return PgCBuckets(records.data_ptr(), counts.data_ptr(), int(part_cap), int(bits), 0, self.wide.data_ptr(), self.wide_count.data_ptr(),
+                          self.wide_cap)
+
+    def bytes(self):
+        return self.records.numel() * 8 + self.wide.numel() * 8
 
 
 def plan_rounds(n_bases_max, rounds=None, round_len=None, tile=_TILE):
@@ -114,7 +135,7 @@ class RoundBuilder:
     MAX_REGION_LOG = 18          # 2^10 coarse buckets (K2a) x 2^8 fine ones each (K2c)
 
     def __init__(self, k, mode, n_bases_max, world=1, rank=0, device="cuda", capacity=None, rounds=None, round_len=None,
-                 sub_bytes=None, slack=1.25, spill_frac=1.0 / 16, region_bits=None, sample=False):
+                 sub_bytes=None, slack=1.25, spill_frac=1.0 / 16, region_bits=None, sample=False, compact=None):
         engine._require_cuda()
         self.L = _lib.load()
         self.k, self.mode = int(min(max(1, k), 27)), int(mode)
@@ -151,11 +172,19 @@ class RoundBuilder:
         if region_bits is None:
             region_bits = int(os.environ.get("PG_REGION_BITS", str(self.REGION_BITS)))
         self._region_pref = region_bits if region_bits in (8, 12) else 0
+        # compact 8-byte update records (csrc/compact_build.cu): one GPU, canonical mode, 4096-slot regions; PG_COMPACT=0 keeps
+        # the 16-byte records.  verify() switches it off for good when an input overflows the wide spill (many short records
+        # or long ambiguity runs: positions the compact form cannot hold).
+        if compact is None:
+            compact = os.environ.get("PG_COMPACT", "1") != "0"
+        self._compact_pref = bool(compact) and self.world == 1 and self.mode == _lib.PG_MODE_CANONICAL and self._region_pref == 12
+        self.compact = False
         cap_log = cap.bit_length() - 1
         region_now = bool(self._region_pref) and 0 <= cap_log - self._region_pref <= self.MAX_REGION_LOG
         if W == 1:
-            fine = 16.0 * per_pos * slack * spill if region_now else 0.0
-            bpp1, bppn = 16.0 * per_pos * slack * spill + fine, 2 * 16.0 * per_pos * slack * spill + fine
+            rec_b = 8.0 if (self._compact_pref and region_now) else 16.0
+            fine = rec_b * per_pos * slack * spill if region_now else 0.0
+            bpp1, bppn = rec_b * per_pos * slack * spill + fine, 2 * rec_b * per_pos * slack * spill + fine
         else:
             bpp1 = bppn = 16.0 * slack * (2 + slack * spill)
         if rounds is None and round_len is None:
@@ -217,6 +246,7 @@ class RoundBuilder:
         self._ev_a2a = None                 # world N: the previous round's count exchange (= every peer drained buffer i)
         self._begun = False
         self._next_capacity = None
+        self._reconfigure = False
         self.desc = _lib.PgTable(None, 2, None, self.mode, self.k, 1, 0, 0)      # K2a reads mode and k only
 
     @property
@@ -254,9 +284,31 @@ class RoundBuilder:
                 self.table.set_capacity(cap)
         self.region_bits = rb if region else 0
         self.table.c.region_bits = self.region_bits
+        self.compact = bool(region and self._compact_pref)
+        self.table.c.hash_kind = 1 if self.compact else 0
         n_sub = 1 << sub_bits
         part_cap = int(self._arriving / n_sub * self._slack) + 2048
         spill_cap = max(1 << 16, int(self._arriving * self._spill_frac))
+        if self.compact:
+            if self.sets is None or sub_bits != self.sub_bits or not isinstance(self.sets[0], CompactBuckets):
+                n_sets = 2 if self.n_rounds > 1 else 1
+                self.sets = None
+                self.sets = [CompactBuckets(sub_bits, part_cap, spill_cap, dev) for _ in range(n_sets)]
+                self._ev_free = [None, None]
+            self.sub_bits = sub_bits
+            if len(self.levels) > 1:
+                n_regions = cap >> rb
+                need = int(self._arriving * self._slack) + n_regions * 256
+                if self.fine_records is None or self.fine_records.numel() < need:
+                    self.fine_records = None
+                    torch.cuda.empty_cache()
+                    self.fine_records = torch.empty(need, dtype=torch.int64, device=dev)
+                if self.fine_counts is None or any(c.numel() < n_regions + 1 for c in self.fine_counts) or len(self.fine_counts) < len(self.levels) - 1:
+                    self.fine_counts = [torch.zeros(n_regions + 1, dtype=torch.int64, device=dev) for _ in self.levels[1:]]
+            self.min_capacity = 1 << (sub_bits + rb)
+            return
+        if self.sets is not None and isinstance(self.sets[0], CompactBuckets):
+            self.sets, self.fine_records, self.fine_counts = None, None, None       # left the compact path: 16-byte buffers from scratch
         if self.sets is None or sub_bits != self.sub_bits:
             n_sets = 2 if (self.world == 1 and self.n_rounds > 1) else 1
             self.sets = None
@@ -287,10 +339,10 @@ class RoundBuilder:
     # ------------------------------------------------------------------------------------------------
     def begin(self):
         """Empty the table for the next build: an epoch bump (DbgTable.clear), no HBM traffic."""
-        if self._next_capacity and self._next_capacity != self.table.capacity:
+        if (self._next_capacity and self._next_capacity != self.table.capacity) or self._reconfigure:
             torch.cuda.synchronize(self.device)          # buffers may be replaced: nothing of the last build may be in flight
-            self._configure(self._next_capacity)
-        self._next_capacity = None
+            self._configure(self._next_capacity or self.table.capacity)
+        self._next_capacity, self._reconfigure = None, False
         self.table.clear()
         self._begun = True
 
@@ -350,10 +402,11 @@ class RoundBuilder:
                 smp = self.sampler if (self.sampler is not None and r == 0) else None
                 if smp is not None:
                     smp.reset()
-                check(L.pg_kmer_partition_to(byref(self.desc), P(packed.pk2), P(packed.amb), P(packed.d_seq_off), n_rec_arg, lo, hi,
-                                             d_counts, cap_records, max_bases, byref(out), P(smp.keys) if smp else None, smp.cap if smp else 0,
-                                             P(smp.count) if smp else None, engine._stream()),
-                      "pg_kmer_partition_to")
+                part = L.pg_kmer_partition_c if self.compact else L.pg_kmer_partition_to
+                check(part(byref(self.desc), P(packed.pk2), P(packed.amb), P(packed.d_seq_off), n_rec_arg, lo, hi,
+                           d_counts, cap_records, max_bases, byref(out), P(smp.keys) if smp else None, smp.cap if smp else 0,
+                           P(smp.count) if smp else None, engine._stream()),
+                      "pg_kmer_partition_c" if self.compact else "pg_kmer_partition_to")
                 e1 = stamp(A)
                 if smp is not None:
                     # size the table from K2a's 1/256 key-space sample before anything is inserted: one 8-byte read-back
@@ -379,7 +432,28 @@ class RoundBuilder:
                     x2 = stamp(B)
                 else:
                     x2 = stamp(B)
-                if self.region_bits:
+                if self.compact:
+                    # K2c-c: 8-byte records level by level down to one bucket per region, then K3s-c (+ the wide spill)
+                    region_log = (t.capacity >> self.region_bits).bit_length() - 1
+                    levels = [self.sub_bits] + plan_levels(region_log, W)[1:] if region_log > self.sub_bits else [self.sub_bits]
+                    if sum(levels) != region_log:              # sampled capacity: one or two even levels below K2a's buckets
+                        rest = region_log - self.sub_bits
+                        levels = [self.sub_bits] + ([rest] if rest <= 8 else [rest // 2, rest - rest // 2])
+                    cur_c, bits = bs.c, self.sub_bits
+                    bufs = [self.fine_records, bs.records]
+                    for li, lb in enumerate(levels[1:]):
+                        out_rec, ocnt = bufs[li % 2], self.fine_counts[li]
+                        n_out = 1 << (bits + lb)
+                        ocap = (out_rec.numel() // n_out) & ~1
+                        nxt_c = bs.view(out_rec, ocnt, bits + lb, ocap)
+                        check(L.pg_records_resplit_c(byref(cur_c), lb, byref(nxt_c), self.k, P(t.stats), engine._stream()), "pg_records_resplit_c")
+                        cur_c, bits = nxt_c, bits + lb
+                    x2c = stamp(B)
+                    check(L.pg_region_build_c(byref(t.c), byref(cur_c), 1 if r == 0 else 0, engine._stream()), "pg_region_build_c")
+                    if ev is not None:
+                        ev.setdefault("k2c", []).append((x2, x2c))
+                        x2 = x2c
+                elif self.region_bits:
                     # K2c: re-split level by level down to one bucket per region (the capacity may have been set from the
                     # key sample after K2a ran: the levels after the first follow the capacity in use)
                     region_log = (t.capacity >> self.region_bits).bit_length() - 1
@@ -434,6 +508,11 @@ class RoundBuilder:
 
     def verify(self):
         full, lost = self.flags()
+        if lost and self.compact:
+            # the wide spill overflowed (many short records, long ambiguity runs): this input is not one for compact records
+            self._compact_pref = False
+            self._reconfigure = True               # begin() re-configures: 16-byte buffers, hash_kind 0
+            raise LostRecords("the compact build's wide spill overflowed; the builder is back on 16-byte records")
         if lost:
             raise LostRecords("update records were dropped (bucket/spill overflow or a truncated record index) on some rank")
         if full:
@@ -468,6 +547,7 @@ class RoundBuilder:
              "insert": ("K2c + K3s: %d shared-memory regions of %d slots, partition levels (bits) %r"
                         % (self.table.capacity >> self.region_bits, 1 << self.region_bits, self.levels))
                        if self.region_bits else "K3: L2 atomics over %d hash-prefix regions" % (1 << self.sub_bits),
+             "records": "compact: 8 bytes per interior position, 16-byte wide records for the rest" if self.compact else "16 bytes",
              "record_buffers_bytes": sum(s.bytes() for s in self.sets) + (2 * self.wire_bytes if self.world > 1 else 0)}
         if self.world > 1:
             d["wire_bucket_records"] = self.cap_wire
@@ -489,7 +569,7 @@ def global_record_prefix(packed, Ns, strands, world=1):
 
 
 def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capacity=None, rounds=None, max_attempts=4,
-                region_bits=None, sample=True):
+                region_bits=None, sample=True, compact=None):
     """The product's stage-1 build: RoundBuilder with automatic recovery - more rounds (smaller buckets relative
     to their capacity) after lost records, a larger table after an overflow.  On one GPU the table is built in
     shared-memory regions and, for a single-round build, sized from K2a's key-space sample (``sample``) instead of the
@@ -502,9 +582,9 @@ def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capa
     n_bases = int(packed.seq_off[n_rec] - packed.seq_off[0]) if n_rec > 0 else 0
     spill_frac = 1.0 / 16
     err = None
-    for _ in range(max_attempts):
+    for _ in range(max_attempts + 1):
         b = RoundBuilder(k, mode, max(n_bases, 1), world=world, rank=rank, device=packed.pk2.device, capacity=capacity, rounds=rounds,
-                         spill_frac=spill_frac, region_bits=region_bits, sample=sample)
+                         spill_frac=spill_frac, region_bits=region_bits, sample=sample, compact=compact)
         b.adaptive = False              # one build: nothing to retune for
         b.begin()
         b.build_async(packed, n_rec)
@@ -514,7 +594,10 @@ def build_table(packed, k, rc=True, Ns=2 ** 63, mode=None, world=1, rank=0, capa
             return b.table, n_rec, b
         except LostRecords as e:
             err = e
-            rounds, spill_frac = 4 * b.n_rounds, min(1.0, spill_frac * 4)
+            if b.compact:           # positions the compact records cannot hold overflowed the wide spill: 16-byte records
+                compact = False
+            else:
+                rounds, spill_frac = 4 * b.n_rounds, min(1.0, spill_frac * 4)
         except TableFull as e:
             err = e
             capacity = 2 * b.table.capacity

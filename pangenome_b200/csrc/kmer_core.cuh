@@ -159,6 +159,87 @@ PG_HD void pg_interior_visit(const PgWindow &w, int j0, int k, uint64_t pow5km1,
     }
 }
 
+// ---- compact (8-byte) update records: the 2-bit form of an ACGT-only k-mer -----------------------------------------
+// An interior position (pg_is_interior: the k-mer, its previous and its next base are ACGT inside one record) needs
+// 2k <= 54 bits of key and 4 bits of context, so the streaming build (compact_build.cu) moves 8-byte records
+//     [ key2 : 54 | ctx : 6 | 0 : 4 ]     key2 = min(F2, R2), the 2-bit codes of the window and of its reverse complement
+//     ctx bits 0..3 = dprev * 4 + dnext (index of the 16-word value table pg_vlut_entry), bit 4 = the rc strand's code is
+//     the key (swap the two 12-bit values), bit 5 = palindrome (F2 == R2, even k only: fold both values, count twice)
+// instead of the 16-byte {base-5 key, masks, inc}.  2-bit and base-5 codes are positional over the same digits
+// (A0 G1 C2 T3, first base least significant), so F2 < R2 <=> F < R and the canonical choice is the same as
+// pg_canonical_update_w's.  Every other position (record edges with '#' / '$' / Q1, ambiguity codes) travels as a 16-byte
+// "wide" record.  Tables built from compact records are placed by the hash of the 2-bit code (pg_table.hash_kind 1).
+#define PG_C_KEYBITS 54
+#define PG_C_KEYMASK ((1ull << PG_C_KEYBITS) - 1ull)
+#define PG_C_SWAP 16u
+#define PG_C_PAL 32u
+#define PG_WIDE_FLAG 0x8000000000000000ull      // shared-memory region tables: bit 63 marks a base-5 key that has no 2-bit form
+
+PG_HD uint64_t pg_crec_pack(uint64_t F2, uint64_t R2, uint32_t ctx4) {
+    const bool lt = F2 < R2, eq = F2 == R2;
+    const uint32_t c = ctx4 | ((lt || eq) ? 0u : PG_C_SWAP) | (eq ? PG_C_PAL : 0u);
+    return (lt ? F2 : R2) | ((uint64_t)c << PG_C_KEYBITS);
+}
+// masks / increment of a compact record; vw = value-table word of its ctx & 15
+PG_HD void pg_crec_vals(uint32_t ctx, uint32_t vw, uint32_t &masks, uint32_t &inc) {
+    const uint32_t sw = (vw >> 16) | (vw << 16);
+    masks = (ctx & PG_C_PAL) ? ((vw | sw) & 0xFFFFu) : ((ctx & PG_C_SWAP) ? sw : vw);
+    inc = (ctx & PG_C_PAL) ? 2u : 1u;
+}
+// base-5 code of the k two-bit digits of x, digit loop (rare paths; the kernels' common path uses pg_code5_of2 + lut5)
+PG_HD uint64_t pg_code5_of2_loop(uint64_t x, int k) {
+    uint64_t c = 0;
+    for (int i = k - 1; i >= 0; i--) c = c * 5 + ((x >> (2 * i)) & 3u);
+    return c;
+}
+// 2-bit code of a base-5 code; false when a digit is the ambiguity digit 4 (no 2-bit form).  9-digit limbs as pg_rc_code.
+PG_HD bool pg_code2_of5(uint64_t code, int k, uint64_t &x2) {
+    const uint32_t P9 = 1953125u;
+    uint32_t limb[3];
+    limb[0] = (uint32_t)(code % P9); code /= P9;
+    limb[1] = (uint32_t)(code % P9); code /= P9;
+    limb[2] = (uint32_t)code;
+    uint64_t x = 0; bool ok = true;
+    int left = k;
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+        uint32_t v = limb[l];
+        const int n = left < 9 ? left : 9;
+        for (int i = 0; i < n; i++) {
+            const uint32_t d = v % 5u; v /= 5u;
+            ok = ok && d != 4u;
+            x |= (uint64_t)(d & 3u) << (2 * (9 * l + i));
+        }
+        left -= n;
+    }
+    x2 = x;
+    return ok;
+}
+// slot placement hash of a base-5 key in a hash_kind-1 table: the hash of its 2-bit form when it has one
+PG_HD uint64_t pg_hash_kind1(uint64_t code5, int k) {
+    uint64_t x2;
+    return pg_code2_of5(code5, k, x2) ? pg_mix64(x2) : pg_mix64(~code5);
+}
+// Visit G consecutive interior positions like pg_interior_visit, in the 2-bit domain: f(q, F2, R2, ctx4).  No multiplies:
+// both codes roll with shifts.
+template <int G, class Fn>
+PG_HD void pg_interior_visit_c(const PgWindow &w, int j0, int k, Fn &&f) {
+    const uint64_t x0 = pg_win64(w, j0);
+    const uint64_t M = (1ull << (2 * k)) - 1ull;              // k <= 27
+    uint64_t F2 = x0 & M;
+    uint64_t R2 = pg_rev2(~x0) >> (64 - 2 * k);               // digit i of the rc strand = 3 - d[k-1-i]
+    using view_t = typename PgView<(G <= 16)>::type;
+    const view_t dprev_w = (view_t)pg_win64(w, j0 - 1), din_w = (view_t)pg_win64(w, j0 + k);
+    const int top = 2 * (k - 1);
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+        const uint32_t dp = (uint32_t)(dprev_w >> (2 * q)) & 3u, din = (uint32_t)(din_w >> (2 * q)) & 3u;
+        f(q, F2, R2, dp * 4u + din);
+        F2 = (F2 >> 2) | ((uint64_t)din << top);
+        R2 = ((R2 << 2) & M) | (uint64_t)(3u - din);
+    }
+}
+
 // What one position contributes to a table in each mode.
 struct PgUpdate { uint64_t key; uint32_t masks; uint32_t inc; };
 // canonical pairing: slot key = min(F, R); masks = m(orientation 0) | m(orientation 1) << 16,

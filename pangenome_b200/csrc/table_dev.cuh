@@ -15,16 +15,21 @@ constexpr uint32_t PG_MAX_PROBE = 1u << 16;
 // hmask: region tables round the home slot down to a group of PG_REGION_GROUP slots (K3s reads a whole group per probe
 // step), so the linear-probing invariant "no free slot between home and the key" is stated from the group's first slot.
 #define PG_REGION_GROUP 4
-struct TableView { uint64_t *slots; uint64_t capmask; int64_t *stats; int shift; uint64_t tag; uint64_t rmask; uint64_t hmask; };
+// hkind: which code the placement hash is taken of (pg_table.hash_kind): 0 = the base-5 key itself, 1 = its 2-bit form
+// (tables built from compact records, compact_build.cu; generic upserts and look-ups then pay a base-5 -> 2-bit conversion)
+struct TableView { uint64_t *slots; uint64_t capmask; int64_t *stats; int shift; uint64_t tag; uint64_t rmask; uint64_t hmask; int hkind; int k; };
 __host__ __device__ __forceinline__ uint64_t tv_next(const TableView &t, uint64_t s) { return (s & ~t.rmask) | ((s + 1) & t.rmask); }
 inline uint64_t pg_tag(const pg_table *t) { return (uint64_t)(uint32_t)t->epoch << PG_TAG_SHIFT; }
-__host__ __device__ __forceinline__ uint64_t tv_home(const TableView &t, uint64_t key) { return (pg_mix64(key) >> t.shift) & t.hmask; }
+__host__ __device__ __forceinline__ uint64_t tv_home(const TableView &t, uint64_t key) {
+    const uint64_t h = t.hkind ? pg_hash_kind1(key, t.k) : pg_mix64(key);
+    return (h >> t.shift) & t.hmask;
+}
 inline TableView make_view(const pg_table *t) {
     int bits = 0; while ((1ll << bits) < t->capacity) bits++;
     const uint64_t capmask = (uint64_t)t->capacity - 1;
     const uint64_t rmask = (t->region_bits > 0 && t->region_bits < bits) ? ((1ull << t->region_bits) - 1ull) : capmask;
     const uint64_t hmask = rmask != capmask ? ~(uint64_t)(PG_REGION_GROUP - 1) : ~0ull;
-    return TableView{t->d_slots, capmask, t->d_stats, 64 - bits, pg_tag(t), rmask, hmask};
+    return TableView{t->d_slots, capmask, t->d_stats, 64 - bits, pg_tag(t), rmask, hmask, t->hash_kind ? 1 : 0, t->k};
 }
 
 // Merge one update into a slot whose key already matches; cv = the value word last seen.

@@ -81,6 +81,13 @@ extern "C" int64_t emul_pack(const uint8_t *fasta, int64_t nbytes, uint32_t *pk2
 
 struct Slot { uint32_t masks; uint64_t cnt; };
 
+// 1: interior positions go through the compact 8-byte record (pg_interior_visit_c -> pg_crec_pack -> what K3s-c does with
+// it: value word from the context bits, base-5 key from the 2-bit code) instead of the base-5 fast path
+static int g_compact = 0;
+static int64_t g_compact_bad = 0;
+extern "C" void emul_set_compact(int on) { g_compact = on; g_compact_bad = 0; }
+extern "C" int64_t emul_compact_bad() { return g_compact_bad; }
+
 // mirrors k2_kmer_insert (one "thread" per 32-base word) + pg_table_export / pg_rdbg_export
 extern "C" int64_t emul_dbg(const uint32_t *pk2_32, const uint32_t *amb, int64_t n_words32, const int64_t *seq_off, int64_t n_rec,
                             int k, int mode, uint64_t *keys, uint16_t *vals, uint8_t *cnts, int64_t cap,
@@ -111,6 +118,22 @@ extern "C" int64_t emul_dbg(const uint32_t *pk2_32, const uint32_t *amb, int64_t
             static uint16_t lut5[PG_LUT5_SIZE];
             static bool lut_ready = false;
             if (!lut_ready) { for (uint32_t i = 0; i < PG_LUT5_SIZE; i++) lut5[i] = (uint16_t)pg_lut5_entry(i); lut_ready = true; }
+            if (g_compact && mode == PG_MODE_CANONICAL) {
+                pg_interior_visit_c<32>(w, 0, k, [&](int, uint64_t F2, uint64_t R2, uint32_t ctx4) {
+                    const uint64_t rec = pg_crec_pack(F2, R2, ctx4);
+                    const uint64_t key2 = rec & PG_C_KEYMASK;
+                    const uint32_t ctx = (uint32_t)(rec >> PG_C_KEYBITS);
+                    uint32_t masks, inc;
+                    pg_crec_vals(ctx, vlut[ctx & 15u], masks, inc);
+                    const uint64_t key5 = pg_code5_of2(key2, lut5);
+                    uint64_t back;
+                    if (key5 != pg_code5_of2_loop(key2, k) || !pg_code2_of5(key5, k, back) || back != key2 ||
+                        pg_hash_kind1(key5, k) != pg_mix64(key2) || (rec >> 60) != 0)
+                        g_compact_bad++;
+                    upsert(key5, masks, inc);
+                });
+                continue;
+            }
             // alternate between the table-driven and the loop forms of both helpers
             pg_interior_visit<32>(w, 0, k, p5, (wi & 1) ? vlut : nullptr, (wi & 2) ? nullptr : lut5, [&](int, uint64_t F, uint64_t R, uint32_t vw) {
                 if (mode == PG_MODE_CANONICAL) { PgUpdate u = pg_canonical_update_w(F, R, vw); upsert(u.key, u.masks, u.inc); }

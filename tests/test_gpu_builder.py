@@ -40,6 +40,10 @@ def test_round_builder_golden(mods, case):
                 t, n_rec, b = bld.build_table(packed, k, rc=rc0, Ns=Ns, mode=mode, rounds=rounds, region_bits=rb)
                 assert b.region_bits == rb or b.table.capacity < 256
                 assert _triples(t) == case["dbg"], "mode %d rounds %d region_bits %d" % (mode, rounds, rb)
+            if mode == 2:           # compact 8-byte records: 4 regions of 4096 slots, later rounds reload the regions
+                t, n_rec, b = bld.build_table(packed, k, rc=rc0, Ns=Ns, mode=mode, rounds=rounds, region_bits=12, capacity=1 << 14, sample=False)
+                assert b.compact and t.c.hash_kind == 1 and b.region_bits == 12
+                assert _triples(t) == case["dbg"], "compact, rounds %d" % rounds
 
 
 def test_rounds_device_bounds_and_rebuild(mods):
@@ -76,7 +80,7 @@ def test_spill_absorbs_hash_skew(mods):
     want = oracle.table_checksum(*ref["dbg"])
     packed = eng.PackedSeqs(eng.to_device_bytes(data))
     # tight buckets (slack 1.0 -> about 1/n_sub of the records each): the poly-A bucket must spill
-    b = bld.RoundBuilder(k, _lib.PG_MODE_CANONICAL, len(data), capacity=1 << 18, sub_bytes=1 << 14, slack=1.0, spill_frac=1.0)
+    b = bld.RoundBuilder(k, _lib.PG_MODE_CANONICAL, len(data), capacity=1 << 18, sub_bytes=1 << 14, slack=1.0, spill_frac=1.0, compact=False)
     assert b.sets[0].n_parts >= 64
     b.sets[0].c.part_cap = b.sets[0].part_cap = 2048          # far below the 4000 x 12 poly-A records that hash to one bucket
     b.sets[0].seg_off.copy_(torch.arange(b.sets[0].n_parts + 1, device="cuda") * 2048)
@@ -87,7 +91,7 @@ def test_spill_absorbs_hash_skew(mods):
     assert int(b.sets[0].counts[-1].item()) > 10000            # the spill really was used
     assert t.checksum() == want
     # no room in the spill either: the flag trips, build_table() recovers
-    b2 = bld.RoundBuilder(k, _lib.PG_MODE_CANONICAL, len(data), capacity=1 << 18, sub_bytes=1 << 14)
+    b2 = bld.RoundBuilder(k, _lib.PG_MODE_CANONICAL, len(data), capacity=1 << 18, sub_bytes=1 << 14, compact=False)
     b2.sets[0].c.part_cap = b2.sets[0].part_cap = 2048
     b2.sets[0].c.spill_cap = b2.sets[0].spill_cap = 16
     b2.sets[0].seg_off.copy_(torch.arange(b2.sets[0].n_parts + 1, device="cuda") * 2048)
@@ -159,8 +163,8 @@ def test_plant_like_single_gpu_parity(mods):
     assert res.rows(packed, data) == ref["rows"]
 
 
-@pytest.mark.parametrize("region_bits,rounds", [(12, 1), (12, 3), (8, 1), (8, 2)])
-def test_region_build_refine_and_retune(mods, region_bits, rounds):
+@pytest.mark.parametrize("region_bits,rounds,compact", [(12, 1, True), (12, 3, True), (12, 1, False), (12, 3, False), (8, 1, False), (8, 2, False)])
+def test_region_build_refine_and_retune(mods, region_bits, rounds, compact):
     """K2a -> K2c (coarse buckets refined to one bucket per region) -> K3s (regions built in shared memory) -> spill, with the
     bounds read on the device; the same builder three times: verify() retunes the capacity to the distinct keys found
     (load <= 0.5), which changes the number of regions and K2c's fan-out between builds."""
@@ -170,8 +174,8 @@ def test_region_build_refine_and_retune(mods, region_bits, rounds):
     data = survey_4x1m()
     want = oracle.table_checksum(*oracle.run(data, 27, stages=1)["dbg"])
     d = eng.to_device_bytes(data)
-    b = bld.RoundBuilder(27, _lib.PG_MODE_CANONICAL, len(data), rounds=rounds, region_bits=region_bits)
-    assert b.region_bits == region_bits and b.adaptive
+    b = bld.RoundBuilder(27, _lib.PG_MODE_CANONICAL, len(data), rounds=rounds, region_bits=region_bits, compact=compact)
+    assert b.region_bits == region_bits and b.adaptive and b.compact == compact
     caps = []
     for _ in range(3):
         b.begin()
@@ -233,3 +237,83 @@ def test_region_table_takes_later_upserts(mods):
     t.insert(packed, n_rec)
     ks, vs, cs = t.export()
     assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
+
+
+def test_compact_wide_spill_takes_hash_skew_and_edges(mods):
+    """Compact records: a poly-A k-mer overflows its 8-byte bucket, the surplus travels as wide records; record edges and N
+    runs are wide from the start.  Exact table; k even, so palindromes take the fold bit."""
+    import torch
+    eng, bld = mods
+    from pangenome_b200 import _lib
+    rng = np.random.default_rng(12)
+    recs = []
+    for i in range(12):
+        body = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 3000)) + b"A" * 4000 + b"NNNNNNNNNN" + b"ACGT" * 40 + b"TTTTAAAA" * 20
+        recs.append(b">r%d\n" % i + body + b"\n")
+    data = b"".join(recs)
+    for k in (20, 27):
+        ref = oracle.run(data, k, stages=1)
+        want = oracle.table_checksum(*ref["dbg"])
+        packed = eng.PackedSeqs(eng.to_device_bytes(data))
+        b = bld.RoundBuilder(k, _lib.PG_MODE_CANONICAL, len(data), capacity=1 << 18, slack=1.0, spill_frac=1.0)
+        assert b.compact and b.sets[0].n_parts == 64
+        b.sets[0].c.part_cap = b.sets[0].part_cap = 2048          # far below the 4000 x 12 poly-A records of one bucket
+        b.begin()
+        t = b.build_async(packed, packed.n_rec)
+        torch.cuda.synchronize()
+        b.verify()
+        assert int(b.sets[0].counts.max().item()) > 10000 and int(b.sets[0].wide_count.item()) > 10000
+        assert t.checksum() == want, k
+        ks, vs, cs = t.export()
+        assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
+
+
+def test_compact_falls_back_on_short_records(mods):
+    """An input the compact form does not suit (thousands of 60-base records: every position is a record edge) overflows
+    the wide spill: verify() reports it and puts the builder back on 16-byte records; build_table() recovers by itself."""
+    import torch
+    eng, bld = mods
+    from pangenome_b200 import _lib
+    rng = np.random.default_rng(13)
+    data = b"".join(b">s%d\n" % i + bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 60)) + b"\n" for i in range(40000))
+    k = 27
+    want = oracle.table_checksum(*oracle.run(data, k, stages=1)["dbg"])
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    b = bld.RoundBuilder(k, _lib.PG_MODE_CANONICAL, len(data), capacity=1 << 22, spill_frac=1.0 / 64)
+    assert b.compact
+    b.begin()
+    b.build_async(packed, packed.n_rec)
+    torch.cuda.synchronize()
+    with pytest.raises(bld.LostRecords):
+        b.verify()
+    b.begin()
+    assert not b.compact and b.table.c.hash_kind == 0
+    t = b.build_async(packed, packed.n_rec)
+    torch.cuda.synchronize()
+    b.verify()
+    assert t.checksum() == want
+    t2, _, b2 = bld.build_table(packed, k)
+    assert t2.checksum() == want
+
+
+def test_compact_table_takes_later_upserts_and_stages(mods):
+    """A table placed by the hash of the 2-bit code (hash_kind 1) takes later generic upserts (the fused insert kernel
+    converts the base-5 key for the placement hash) and feeds the stages after it like any other."""
+    eng, bld = mods
+    from pangenome_b200 import graph
+    data = pangenome(3, 60_000, seed=3) + b">n\n" + b"ACGTNNACGTTGCA" * 30 + b"\n"
+    ref2 = oracle.run(data + data.replace(b">", b">x"), 21, stages=1)
+    packed = eng.PackedSeqs(eng.to_device_bytes(data))
+    t, n_rec, b = bld.build_table(packed, 21, capacity=1 << 19)
+    assert b.compact and t.c.hash_kind == 1
+    ref = oracle.run(data, 21, stages=4)
+    ks, vs, cs = t.export()
+    assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
+    rd = t.select_rdbg()
+    assert np.array_equal(rd.rdbg_export()[0], ref["rdbg"])
+    res = graph.seq2graph_device(packed, rd, 21)
+    assert res.xyz_lines() == ref["xyz"]
+    assert res.rows(packed, data) == ref["rows"]
+    t.insert(packed, n_rec)
+    ks, vs, cs = t.export()
+    assert np.array_equal(ks, ref2["dbg"][0]) and np.array_equal(vs, ref2["dbg"][1]) and np.array_equal(cs, ref2["dbg"][2])

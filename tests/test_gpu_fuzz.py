@@ -62,6 +62,11 @@ def test_fuzz_whole_pipeline(seed):
         assert ks.tolist() == ref["dbg"][0].tolist() and vs.tolist() == ref["dbg"][1].tolist() and cs.tolist() == ref["dbg"][2].tolist(), data
         t2, _, _ = engine.build_dbg_partitioned(packed, k, rc=rc0)
         assert t2.checksum() == t.checksum(), data
+        if rc0:      # compact 8-byte records (here nearly every position is an edge or ambiguous: the wide path)
+            from pangenome_b200 import builder
+            t3, _, b3 = builder.build_table(packed, k, rc=True, capacity=1 << 13, region_bits=12, sample=False, rounds=1 + it % 2)
+            assert b3.compact and t3.checksum() == t.checksum(), data
+            b3.close()
         rd = t.select_rdbg()
         assert rd.rdbg_export()[0].tolist() == ref["rdbg"].tolist(), data
         res = graph.seq2graph_device(packed, rd, k, rc=rc1)

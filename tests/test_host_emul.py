@@ -153,3 +153,39 @@ def test_emul_single_pass_pack_hostile_layouts(emul):
         assert a[3].tolist() == b[3].tolist() and a[2].tolist() == b[2].tolist() and a[4][:3].tolist() == b[4][:3].tolist()
         nb = int(a[4][1])
         assert np.array_equal(unpack_syms(a[0], a[1], nb), unpack_syms(b[0], b[1], nb))
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if (c["c"] >> 1) & 1 and "Ns" not in c], ids=lambda c: c["name"])
+def test_emul_compact_records_match_golden(emul, case):
+    """compact 8-byte records (compact_build.cu): interior positions through pg_interior_visit_c -> pg_crec_pack -> the
+    expansion K3s-c applies; the table must equal the reference's, and the 2-bit <-> base-5 conversions and the
+    hash_kind-1 placement hash must agree for every record"""
+    data = case["input_latin1"].encode("latin-1")
+    pk2, amb, hdr, so, counts = run_pack(emul, data)
+    emul.emul_compact_bad.restype = ctypes.c_int64
+    emul.emul_set_compact(1)
+    try:
+        (ks, vs, cs), rk = run_dbg(emul, pk2, amb, so, case["k"], 2)
+        assert emul.emul_compact_bad() == 0
+    finally:
+        emul.emul_set_compact(0)
+    assert [[int(a), int(b), int(c)] for a, b, c in zip(ks, vs, cs)] == case["dbg"]
+    assert rk.tolist() == case["rdbg"]
+
+
+@pytest.mark.parametrize("k", [4, 12, 21, 26, 27])
+def test_emul_compact_records_big(emul, k):
+    """1 Mbp x 4 with every k parity (even k: palindromes take the fold-and-count-twice bit)"""
+    data = survey_4x1m()[:600_000]
+    data = data[:data.rfind(b"\n") + 1]
+    pk2, amb, hdr, so, counts = run_pack(emul, data)
+    emul.emul_compact_bad.restype = ctypes.c_int64
+    emul.emul_set_compact(1)
+    try:
+        (ks, vs, cs), rk = run_dbg(emul, pk2, amb, so, k, 2)
+        assert emul.emul_compact_bad() == 0
+    finally:
+        emul.emul_set_compact(0)
+    ref = oracle.run(data, k, stages=2)
+    assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
+    assert np.array_equal(rk, ref["rdbg"])
