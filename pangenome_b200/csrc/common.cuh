@@ -38,6 +38,14 @@ PG_HD uint64_t pg_mix64(uint64_t x) {   // murmur3 fmix64: a bijection on u64
     return x;
 }
 
+// the same without the last xor-shift, which only changes the low 31 bits: for callers that use nothing below bit 31
+// (bucket / region / slot indices of tables up to 2^33 slots are the TOP bits)
+PG_HD uint64_t pg_mix64_top(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    return x;
+}
+
 // ---- base-5 k-mer codes (kmer_numba.py:975-985: code = sum alpha[s[i]] * 5^i) ----
 #define PG_INV5 0xCCCCCCCCCCCCCCCDull   // 5^-1 mod 2^64: exact division of multiples of 5
 PG_HD uint64_t pg_pow5(int e) {

@@ -142,8 +142,13 @@ __device__ __noinline__ void sample_key_c(uint64_t *sample_keys, uint64_t sample
     atomicAdd(sample_count, 1ull << 40);     // set full: poison the estimate so the host falls back to the upper bound
 }
 
-template <int T, bool SAMPLE>
-__global__ void __launch_bounds__(T, 3)
+// KT: compile-time k (pg_interior_visit_ck: no rolling state, constant funnel shifts) or 0 = the k of the arguments.
+// The records are derived twice - bucket + rank before the scan, the record itself after it - instead of held in 32
+// registers across the barriers: with a compile-time k a window costs two funnel shifts, and the kernel is bound by the
+// latency of its dependent chains at 24 warps per SM, not by its instruction count (holding the records measured 0.349 ms
+// against 0.332 ms; ranks from ballots / MATCH.ANY + per-warp counters instead of the histogram atomic: 0.72 / 0.76 ms).
+template <int T, bool SAMPLE, int KT, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 k2a_partition_c(CPartArgs a) {
     constexpr int TILE = T * KP_G;
     if (a.d_counts) {      // all records of the packed stream, bounds read from the device (as k2a_partition)
@@ -172,7 +177,7 @@ k2a_partition_c(CPartArgs a) {
     __shared__ uint32_t s_chunk[32];
     __shared__ uint32_t s_nrec;
     const uint64_t pol = pg_policy_evict_first();
-    const int k = a.k;
+    const int k = KT ? KT : a.k;
     const int shift = 64 - a.out.bits;
 
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -197,13 +202,20 @@ k2a_partition_c(CPartArgs a) {
             int64_t rs = r >= 0 ? __ldg(a.seq_off + r) : 0, re = __ldg(a.seq_off + r + 1);
             interior = pg_is_interior(w, g0, KP_G, k, rs, re, r >= 0, a.g_begin, a.g_end);
             if (interior) {
-                pg_interior_visit_c<KP_G>(w, j0, k, [&](int q, uint64_t F2, uint64_t R2, uint32_t) {
+                auto rank = [&](int q, uint64_t F2, uint64_t R2, uint32_t) {
                     const uint64_t key = F2 < R2 ? F2 : R2;
-                    const uint64_t h = pg_mix64(key);
-                    if (SAMPLE) { if (((h >> 8) & 0xFFu) == 0) sample_key_c(a.sample_keys, a.sample_mask, a.sample_count, key, h); }
+                    uint64_t h;
+                    if (SAMPLE) {
+                        h = pg_mix64(key);
+                        if (((h >> 8) & 0xFFu) == 0) sample_key_c(a.sample_keys, a.sample_mask, a.sample_count, key, h);
+                    } else {
+                        h = pg_mix64_top(key);
+                    }
                     const uint32_t pid = a.out.bits ? (uint32_t)(h >> shift) : 0u;
                     pr[q] = pid | (atomicAdd(&s_hist[pid], 1u) << 10);
-                });
+                };
+                if (KT) pg_interior_visit_ck<(KT ? KT : 27)>(w, j0, rank);
+                else pg_interior_visit_c<KP_G>(w, j0, k, rank);
             } else {
                 // generic path: record edges, ambiguity codes, range ends (all the quirks) -> wide records
                 uint64_t F, R;
@@ -232,14 +244,22 @@ k2a_partition_c(CPartArgs a) {
         tile_offsets<T>(fan, s_hist, s_off, s_end, s_base, s_dst, s_chunk, &s_nrec, a.out.counts, a.out.records, a.out.part_cap);
         // ---- 3. every record to its sorted position
         if (interior) {
-            pg_interior_visit_c<KP_G>(w, j0, k, [&](int q, uint64_t F2, uint64_t R2, uint32_t ctx4) {
-                const uint64_t rc = pg_crec_pack(F2, R2, ctx4);
+            uint32_t ovf = 0;       // records past their bucket's room (rare: hash skew) are handled after the loop, off the common path
+            auto place = [&](int q, uint64_t F2, uint64_t R2, uint32_t ctx4) {
                 const uint32_t pid = pr[q] & 1023u;
                 const uint32_t p = s_off[pid] + (pr[q] >> 10);
-                s_sorted[p] = rc;
+                s_sorted[p] = pg_crec_pack(F2, R2, ctx4);
                 s_spid[p] = (uint16_t)pid;
-                if (p >= s_end[pid]) wide_emit_compact(a.out.wide, a.out.wide_count, a.out.wide_cap, rc, k);
-            });
+                if (p >= s_end[pid]) ovf |= 1u << q;
+            };
+            if (KT) pg_interior_visit_ck<(KT ? KT : 27)>(w, j0, place);
+            else pg_interior_visit_c<KP_G>(w, j0, k, place);
+            if (ovf) {
+                auto spill = [&](int q, uint64_t F2, uint64_t R2, uint32_t ctx4) {
+                    if (ovf & (1u << q)) wide_emit_compact(a.out.wide, a.out.wide_count, a.out.wide_cap, pg_crec_pack(F2, R2, ctx4), k);
+                };
+                pg_interior_visit_c<KP_G>(w, j0, k, spill);
+            }
         }
         __syncthreads();
         // ---- 4. linear copy-out
@@ -318,7 +338,7 @@ k2c_multisplit_c(CSplitArgs a) {
                 pr[2 * q + h] = C_NONE;
                 if (2 * slot + h < left) {
                     const uint64_t rc = h ? ((uint64_t)v[q].z | ((uint64_t)v[q].w << 32)) : ((uint64_t)v[q].x | ((uint64_t)v[q].y << 32));
-                    const uint32_t pid = (uint32_t)(pg_mix64(rc & PG_C_KEYMASK) >> shift) & (uint32_t)(fan - 1);
+                    const uint32_t pid = (uint32_t)(pg_mix64_top(rc & PG_C_KEYMASK) >> shift) & (uint32_t)(fan - 1);
                     pr[2 * q + h] = pid | (atomicAdd(&s_hist[pid], 1u) << 10);
                 }
             }
@@ -327,19 +347,29 @@ k2c_multisplit_c(CSplitArgs a) {
         // ---- 2. offsets in the tile, room in this segment's slice of the output buckets
         tile_offsets<T>(fan, s_hist, s_off, s_end, s_base, s_dst, s_chunk, &s_nrec, a.out.counts + ((int64_t)seg << a.bits),
                         a.out.records + ((int64_t)seg << a.bits) * a.out.part_cap, a.out.part_cap);
-        // ---- 3. every record to its sorted position
+        // ---- 3. every record to its sorted position (one past its bucket's room: remembered, handled off the common path)
+        uint32_t ovf = 0;
 #pragma unroll
         for (int q = 0; q < MSC_LOADS; q++) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t x = pr[2 * q + h];
                 if (x == C_NONE) continue;
-                const uint64_t rc = h ? ((uint64_t)v[q].z | ((uint64_t)v[q].w << 32)) : ((uint64_t)v[q].x | ((uint64_t)v[q].y << 32));
                 const uint32_t pid = x & 1023u;
                 const uint32_t p = s_off[pid] + (x >> 10);
-                s_sorted[p] = rc;
+                reinterpret_cast<uint2 *>(s_sorted)[p] = h ? make_uint2(v[q].z, v[q].w) : make_uint2(v[q].x, v[q].y);
                 s_spid[p] = (uint16_t)pid;
-                if (p >= s_end[pid]) wide_emit_compact(a.out.wide, a.out.wide_count, a.out.wide_cap, rc, a.k);
+                if (p >= s_end[pid]) ovf |= 1u << (2 * q + h);
+            }
+        }
+        if (ovf) {
+#pragma unroll
+            for (int q = 0; q < MSC_LOADS; q++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    if (ovf & (1u << (2 * q + h)))
+                        wide_emit_compact(a.out.wide, a.out.wide_count, a.out.wide_cap,
+                                          h ? ((uint64_t)v[q].z | ((uint64_t)v[q].w << 32)) : ((uint64_t)v[q].x | ((uint64_t)v[q].y << 32)), a.k);
             }
         }
         __syncthreads();
@@ -435,7 +465,7 @@ k3s_region_build_c(CRegionArgs a) {
                 const uint32_t klo = rec[j].x, khi = rec[j].y & (uint32_t)(PG_C_KEYMASK >> 32);
                 const uint32_t ctx = rec[j].y >> (PG_C_KEYBITS - 32);
                 const uint64_t key = (uint64_t)klo | ((uint64_t)khi << 32);
-                uint32_t g = (uint32_t)(pg_mix64(key) >> t.shift) & (NS - 1) & ~(uint32_t)(PG_REGION_GROUP - 1);
+                uint32_t g = (uint32_t)(pg_mix64_top(key) >> t.shift) & (NS - 1) & ~(uint32_t)(PG_REGION_GROUP - 1);
                 int s = -1;
                 if (act) {
                     for (int probe = 0; probe < NS / PG_REGION_GROUP;) {
@@ -551,19 +581,30 @@ extern "C" int pg_kmer_partition_c(const pg_table *t, const uint32_t *d_pk2, con
     const int smem = k2a_c_smem(fan, T);
     static int per_sm_env = -1;
     if (per_sm_env < 0) { const char *e = getenv("PG_K2AC_CTAS"); per_sm_env = e ? atoi(e) : 0; }
+    // 3 CTAs (80 registers) per SM measured 0.278 ms on config 2, 4 CTAs (64 registers, PG_K2AC_CTAS=4) 0.291 ms
     int per_sm = ctas_per_sm(smem, 512);
+    const int want = per_sm_env > 0 ? per_sm_env : 3;
+    if (per_sm > want) per_sm = want;
     if (per_sm > 4) per_sm = 4;
-    if (per_sm_env > 0 && per_sm_env < per_sm) per_sm = per_sm_env;
     const int64_t maxg = (int64_t)pg_num_sms() * per_sm;
     int grid = (int)(a.n_tiles < maxg ? a.n_tiles : maxg);
     if (grid < 1) grid = 1;
+#define K2AC_LAUNCH(S, KT, MB)                                                                                              \
+    do {                                                                                                                    \
+        PG_CUDA(cudaFuncSetAttribute(k2a_partition_c<T, S, KT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
+        k2a_partition_c<T, S, KT, MB><<<grid, T, smem, st>>>(a);                                                            \
+    } while (0)
+    static int kt_env = -1;
+    if (kt_env < 0) { const char *e = getenv("PG_K2AC_GENERIC"); kt_env = e ? atoi(e) : 0; }      // 1: always the runtime-k kernel
+    const int kt = kt_env ? 0 : t->k;
     if (a.sample_keys) {
-        PG_CUDA(cudaFuncSetAttribute(k2a_partition_c<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k2a_partition_c<T, true><<<grid, T, smem, st>>>(a);
+        if (kt == 27) K2AC_LAUNCH(true, 27, 3); else if (kt == 21) K2AC_LAUNCH(true, 21, 3); else K2AC_LAUNCH(true, 0, 3);
+    } else if (per_sm >= 4) {
+        if (kt == 27) K2AC_LAUNCH(false, 27, 4); else if (kt == 21) K2AC_LAUNCH(false, 21, 4); else K2AC_LAUNCH(false, 0, 3);
     } else {
-        PG_CUDA(cudaFuncSetAttribute(k2a_partition_c<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k2a_partition_c<T, false><<<grid, T, smem, st>>>(a);
+        if (kt == 27) K2AC_LAUNCH(false, 27, 3); else if (kt == 21) K2AC_LAUNCH(false, 21, 3); else K2AC_LAUNCH(false, 0, 3);
     }
+#undef K2AC_LAUNCH
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

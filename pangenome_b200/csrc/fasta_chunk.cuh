@@ -264,3 +264,61 @@ PG_HD Sum3 tile_sum3(const TileLocal &t) {
     }
     return s;
 }
+
+// ---- K1 in 32-byte chunks with LOCAL header detection (k1x_* kernels) ------------------------------------------------
+// A header starts where a '>' sits at a line start, and a line starts after a line-ending byte (or at byte 0 of the
+// file): that is a property of two neighbouring bytes, no state machine needed.  What does carry over from chunk to
+// chunk is one bit - "inside a header line" - and it behaves like the carry of an adder: a header start GENERATES it, a
+// line end KILLS it, every other byte PROPAGATES it.  So the in-header mask of a chunk is one 64-bit addition
+// (hdr_fill32), the state a chunk hands on is decided by its last event alone (or, without events, by its entry
+// state), and a warp resolves its 32 chunks with two ballots instead of a scan over 3-variant summaries.
+struct Cls32 { uint32_t nl, gt, amb; uint32_t dig_lo, dig_hi; uint32_t real_nl; };
+// classify 32 bytes = two classify16 halves; left = bytes of the file from the chunk's first byte on (may be <= 0)
+template <bool LINES_ONLY>
+PG_HD Cls32 classify32(const uint32_t w[8], int64_t left) {
+    const int n_lo = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+    const int64_t left_hi = left - 16;
+    const int n_hi = left_hi >= 16 ? 16 : (left_hi > 0 ? (int)left_hi : 0);
+    const ChunkCls a = LINES_ONLY ? classify16_lines(w, n_lo, left <= 16) : classify16(w, n_lo, left <= 16);
+    const ChunkCls b = LINES_ONLY ? classify16_lines(w + 4, n_hi, left_hi <= 16) : classify16(w + 4, n_hi, left_hi <= 16);
+    Cls32 c;
+    c.nl = (a.nl & 0xFFFFu) | (b.nl << 16); c.gt = (a.gt & 0xFFFFu) | (b.gt << 16); c.amb = (a.amb & 0xFFFFu) | (b.amb << 16);
+    c.dig_lo = a.dig; c.dig_hi = b.dig; c.real_nl = a.real_nl + b.real_nl;
+    return c;
+}
+// header starts of a chunk; prev_nl = 1 when the byte before the chunk ends a line or the chunk starts the file
+PG_HD uint32_t hdr_starts32(uint32_t nl, uint32_t gt, uint32_t prev_nl) { return gt & ~nl & ((nl << 1) | (prev_nl & 1u)); }
+// in-header mask: h_i = hs_i | (~nl_i & ~hs_i & h_{i-1}), h_{-1} = cin  - the carries of (g | p) + g + cin
+PG_HD uint32_t hdr_fill32(uint32_t nl, uint32_t hs, uint32_t cin) {
+    const uint64_t x = (uint64_t)(uint32_t)(~nl | hs), y = hs;       // g | p = hs | (~nl & ~hs) = hs | ~nl
+    const uint64_t c = (x + y + (cin & 1u)) ^ x ^ y;                 // carry INTO every bit
+    return (uint32_t)(c >> 1);                                       // carry OUT of bit i = in-header at byte i
+}
+// what a span hands on: 0 = not in a header, 1 = in a header, 2 = whatever it was handed (no event inside)
+enum { HK_RESET = 0, HK_SET = 1, HK_PASS = 2 };
+PG_HD uint32_t hdr_kind32(uint32_t nl, uint32_t hs) {
+    const uint32_t ev = nl | hs;
+    if (!ev) return HK_PASS;
+    return (hs >> pg_msb(ev)) & 1u;
+}
+// entry state of element `idx` (lane of a warp / warp of a tile) from two masks over the elements: fixed = has an event,
+// set = its last event is a header start; `before` = the state handed to element 0
+PG_HD uint32_t hdr_entry_from_masks(uint32_t fixed, uint32_t set, int idx, uint32_t before) {
+    const uint32_t m = idx >= 32 ? fixed : (fixed & ((1u << idx) - 1u));
+    return m ? (set >> pg_msb(m)) & 1u : before;
+}
+// A tile as a function of the state it is handed: bases for entry 0 / entry 1, exit state for both, headers, real '\n's.
+struct TileFn { unsigned long long seq0, seq1, hdr, nl; uint32_t exit0, exit1; };
+PG_HD TileFn tilefn_identity() { TileFn f; f.seq0 = f.seq1 = f.hdr = f.nl = 0; f.exit0 = 0; f.exit1 = 1; return f; }
+PG_HD TileFn tilefn_make(uint32_t seq0, uint32_t pre_seq, uint32_t hdr, uint32_t kind, uint32_t real_nl) {
+    TileFn f; f.seq0 = seq0; f.seq1 = seq0 - pre_seq; f.hdr = hdr; f.nl = real_nl;
+    f.exit0 = kind == HK_PASS ? 0u : kind; f.exit1 = kind == HK_PASS ? 1u : kind;
+    return f;
+}
+PG_HD TileFn tilefn_compose(const TileFn &a, const TileFn &b) {      // a then b
+    TileFn c;
+    c.seq0 = a.seq0 + (a.exit0 ? b.seq1 : b.seq0); c.exit0 = a.exit0 ? b.exit1 : b.exit0;
+    c.seq1 = a.seq1 + (a.exit1 ? b.seq1 : b.seq0); c.exit1 = a.exit1 ? b.exit1 : b.exit0;
+    c.hdr = a.hdr + b.hdr; c.nl = a.nl + b.nl;
+    return c;
+}

@@ -240,6 +240,58 @@ PG_HD void pg_interior_visit_c(const PgWindow &w, int j0, int k, Fn &&f) {
     }
 }
 
+// The same visit for a COMPILE-TIME k and 16 positions starting at a multiple of 16 (K2a-c's thread): no rolling state at
+// all.  The 16 + K + 1 digits a thread looks at lie in three 32-bit words W0..W2 of the digit stream; the window of
+// position q is a funnel shift of two of them by the constant 2q, the reverse-complement window the same on the
+// digit-reversed complement Y0..Y2 (Y digit m = 3 - d[47 - m], so the rc code of position q starts at Y digit 48 - K - q).
+PG_HD uint32_t pg_rev2c32(uint32_t x) {          // complement and reverse the 16 two-bit digits of a word
+    x = ~x;
+#ifdef __CUDA_ARCH__
+    x = __brev(x);
+#else
+    x = (x >> 16) | (x << 16);
+    x = ((x & 0xFF00FF00u) >> 8) | ((x & 0x00FF00FFu) << 8);
+    x = ((x & 0xF0F0F0F0u) >> 4) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x & 0xCCCCCCCCu) >> 2) | ((x & 0x33333333u) << 2);
+    x = ((x & 0xAAAAAAAAu) >> 1) | ((x & 0x55555555u) << 1);
+#endif
+    return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+PG_HD uint32_t pg_funnel_r(uint32_t lo, uint32_t hi, int sh) {      // bits [sh, sh + 32) of hi:lo, 0 <= sh < 32
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+// K digits of the 48-digit stream (w0, w1, w2) starting at digit s (0 <= s, s + K <= 48, 16 < K <= 32)
+template <int K>
+PG_HD uint64_t pg_take_digits(uint32_t w0, uint32_t w1, uint32_t w2, int s) {
+    const uint32_t hmask = K >= 32 ? 0xFFFFFFFFu : ((1u << (2 * (K - 16))) - 1u);
+    uint32_t lo, hi;
+    if (s < 16) { lo = pg_funnel_r(w0, w1, 2 * s); hi = pg_funnel_r(w1, w2, 2 * s); }
+    else { lo = pg_funnel_r(w1, w2, 2 * (s - 16)); hi = w2 >> (2 * (s - 16)); }
+    return (uint64_t)lo | ((uint64_t)(hi & hmask) << 32);
+}
+template <int K, class Fn>
+PG_HD void pg_interior_visit_ck(const PgWindow &w, int j0, Fn &&f) {
+    static_assert(K > 16 && K <= 27, "compile-time k of the compact extraction: 17..27");
+    const bool up = j0 != 0;                                   // j0 is 0 or 16
+    const uint32_t W0 = up ? (uint32_t)(w.cur >> 32) : (uint32_t)w.cur, W1 = up ? (uint32_t)w.nxt : (uint32_t)(w.cur >> 32),
+                   W2 = up ? (uint32_t)(w.nxt >> 32) : (uint32_t)w.nxt;
+    const uint32_t Y0 = pg_rev2c32(W2), Y1 = pg_rev2c32(W1), Y2 = pg_rev2c32(W0);
+    const uint32_t dm1 = up ? ((uint32_t)w.cur >> 30) & 3u : (uint32_t)(w.prv >> 62) & 3u;      // digit j0 - 1
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const uint64_t F2 = pg_take_digits<K>(W0, W1, W2, q);
+        const uint64_t R2 = pg_take_digits<K>(Y0, Y1, Y2, 48 - K - q);
+        const uint32_t dp = q ? (W0 >> (2 * (q - 1))) & 3u : dm1;
+        const int n = q + K;                                   // digit after the window: 17 <= n <= 42
+        const uint32_t din = n < 32 ? (W1 >> (2 * (n - 16))) & 3u : (W2 >> (2 * (n - 32))) & 3u;
+        f(q, F2, R2, dp * 4u + din);
+    }
+}
+
 // What one position contributes to a table in each mode.
 struct PgUpdate { uint64_t key; uint32_t masks; uint32_t inc; };
 // canonical pairing: slot key = min(F, R); masks = m(orientation 0) | m(orientation 1) << 16,

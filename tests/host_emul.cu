@@ -119,7 +119,7 @@ extern "C" int64_t emul_dbg(const uint32_t *pk2_32, const uint32_t *amb, int64_t
             static bool lut_ready = false;
             if (!lut_ready) { for (uint32_t i = 0; i < PG_LUT5_SIZE; i++) lut5[i] = (uint16_t)pg_lut5_entry(i); lut_ready = true; }
             if (g_compact && mode == PG_MODE_CANONICAL) {
-                pg_interior_visit_c<32>(w, 0, k, [&](int, uint64_t F2, uint64_t R2, uint32_t ctx4) {
+                auto take = [&](int, uint64_t F2, uint64_t R2, uint32_t ctx4) {
                     const uint64_t rec = pg_crec_pack(F2, R2, ctx4);
                     const uint64_t key2 = rec & PG_C_KEYMASK;
                     const uint32_t ctx = (uint32_t)(rec >> PG_C_KEYBITS);
@@ -131,7 +131,13 @@ extern "C" int64_t emul_dbg(const uint32_t *pk2_32, const uint32_t *amb, int64_t
                         pg_hash_kind1(key5, k) != pg_mix64(key2) || (rec >> 60) != 0)
                         g_compact_bad++;
                     upsert(key5, masks, inc);
-                });
+                };
+                // the compile-time-k form K2a-c runs for the common k (two 16-position halves), else the rolling form
+                if (g_compact == 2 && k == 27) { pg_interior_visit_ck<27>(w, 0, take); pg_interior_visit_ck<27>(w, 16, take); }
+                else if (g_compact == 2 && k == 21) { pg_interior_visit_ck<21>(w, 0, take); pg_interior_visit_ck<21>(w, 16, take); }
+                else if (g_compact == 2 && k == 17) { pg_interior_visit_ck<17>(w, 0, take); pg_interior_visit_ck<17>(w, 16, take); }
+                else if (g_compact == 2 && k == 26) { pg_interior_visit_ck<26>(w, 0, take); pg_interior_visit_ck<26>(w, 16, take); }
+                else pg_interior_visit_c<32>(w, 0, k, take);
                 continue;
             }
             // alternate between the table-driven and the loop forms of both helpers
@@ -239,5 +245,119 @@ extern "C" int64_t emul_pack2(const uint8_t *fasta, int64_t nbytes, uint32_t *pk
     counts[0] = dead ? 0 : (int64_t)hdr; counts[1] = dead ? 0 : (int64_t)seq; counts[2] = (int64_t)real_nl;
     if (!dead && (int64_t)hdr <= cap_rec) seq_off[hdr] = (int64_t)seq;
     if (dead) seq_off[0] = 0;
+    return counts[1];
+}
+
+
+// mirrors k1x_tile_aggs + k1x_scan + k1x_pack: 32-byte chunks, local header detection, the in-header carry resolved per
+// warp from two masks (hdr_entry_from_masks) and per tile from the warps' kinds, tiles composed as functions of the
+// state they are handed (TileFn)
+namespace {
+struct X1Chunk { Cls32 c; uint32_t hs, kind; };
+template <bool LINES_ONLY>
+static void x1_load(const uint8_t *f, int64_t n, int64_t off, uint32_t prev_nl, X1Chunk &o) {
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t left = n - off;
+    for (int i = 0; i < 32 && i < left; i++) w[i >> 2] |= (uint32_t)f[off + i] << (8 * (i & 3));
+    o.c = classify32<LINES_ONLY>(w, left);
+    o.hs = hdr_starts32(o.c.nl, o.c.gt, prev_nl);
+    o.kind = hdr_kind32(o.c.nl, o.hs);
+}
+// entry state of every chunk of a tile (NCH chunks, warps of 32) given the tile's entry state
+static void x1_entries(const std::vector<X1Chunk> &ch, uint32_t tile_entry, std::vector<uint32_t> &entry, uint32_t &tile_kind) {
+    const int nch = (int)ch.size(), nw = nch / 32;
+    std::vector<uint32_t> wfixed(nw), wset(nw), wkind(nw);
+    for (int wv = 0; wv < nw; wv++) {
+        uint32_t fixed = 0, set = 0;
+        for (int l = 0; l < 32; l++) { uint32_t k = ch[wv * 32 + l].kind; if (k != HK_PASS) fixed |= 1u << l; if (k == HK_SET) set |= 1u << l; }
+        wfixed[wv] = fixed; wset[wv] = set;
+        wkind[wv] = fixed ? (set >> pg_msb(fixed)) & 1u : (uint32_t)HK_PASS;
+    }
+    uint32_t tf = 0, tsx = 0;
+    for (int wv = 0; wv < nw; wv++) { if (wkind[wv] != HK_PASS) tf |= 1u << wv; if (wkind[wv] == HK_SET) tsx |= 1u << wv; }
+    tile_kind = tf ? (tsx >> pg_msb(tf)) & 1u : (uint32_t)HK_PASS;
+    entry.resize(nch);
+    for (int wv = 0; wv < nw; wv++) {
+        const uint32_t wentry = hdr_entry_from_masks(tf, tsx, wv, tile_entry);
+        for (int l = 0; l < 32; l++) entry[wv * 32 + l] = hdr_entry_from_masks(wfixed[wv], wset[wv], l, wentry);
+    }
+}
+}  // namespace
+
+extern "C" int64_t emul_pack3(const uint8_t *fasta, int64_t nbytes, uint32_t *pk2, uint32_t *amb, int64_t n_words,
+                              int64_t *hdr_off, int64_t *seq_off, int64_t cap_rec, int64_t *counts) {
+    memset(pk2, 0, (size_t)n_words * 4); memset(amb, 0, (size_t)n_words * 4);
+    const int NCH = TILE / 32;
+    const int64_t ntiles = (nbytes + TILE - 1) / TILE;
+    std::vector<TileFn> fn((size_t)ntiles);
+    auto prev_nl_of = [&](int64_t off) -> uint32_t { return off == 0 ? 1u : (uint32_t)(fasta[off - 1] == '\n'); };
+    // ---- pass A
+    for (int64_t t = 0; t < ntiles; t++) {
+        std::vector<X1Chunk> ch(NCH);
+        for (int c = 0; c < NCH; c++) {
+            const int64_t off = t * TILE + c * 32;
+            x1_load<true>(fasta, nbytes, off, c == 0 ? (off < nbytes ? prev_nl_of(off) : 1u) : (ch[c - 1].c.nl >> 31), ch[c]);
+        }
+        std::vector<uint32_t> entry; uint32_t kind;
+        x1_entries(ch, 0, entry, kind);
+        uint32_t seq0 = 0, nh = 0, rnl = 0; int first_nl = TILE;
+        for (int c = 0; c < NCH; c++) {
+            const uint32_t h = hdr_fill32(ch[c].c.nl, ch[c].hs, entry[c]);
+            seq0 += pg_popc(~ch[c].c.nl & ~h); nh += pg_popc(ch[c].hs); rnl += ch[c].c.real_nl;
+            if (ch[c].c.nl && first_nl == TILE) first_nl = c * 32 + pg_ctz(ch[c].c.nl);
+        }
+        const uint32_t pre = (ch[0].hs & 1u) ? 0u : (uint32_t)first_nl;
+        fn[(size_t)t] = tilefn_make(seq0, pre, nh, kind, rnl);
+    }
+    // ---- pass B
+    TileFn run = tilefn_identity();
+    std::vector<TileFn> before((size_t)ntiles);
+    for (int64_t t = 0; t < ntiles; t++) { before[(size_t)t] = run; run = tilefn_compose(run, fn[(size_t)t]); }
+    const bool dead = run.nl == 0;
+    counts[0] = dead ? 0 : (int64_t)run.hdr; counts[1] = dead ? 0 : (int64_t)run.seq0; counts[2] = (int64_t)run.nl;
+    if (!dead && (int64_t)run.hdr <= cap_rec) seq_off[run.hdr] = (int64_t)run.seq0;
+    if (dead) { seq_off[0] = 0; return 0; }
+    // ---- pass C
+    for (int64_t t = 0; t < ntiles; t++) {
+        const uint64_t tseq = before[(size_t)t].seq0, thdr = before[(size_t)t].hdr; const uint32_t tentry = before[(size_t)t].exit0;
+        std::vector<X1Chunk> ch(NCH);
+        for (int c = 0; c < NCH; c++) {
+            const int64_t off = t * TILE + c * 32;
+            x1_load<false>(fasta, nbytes, off, c == 0 ? (off < nbytes ? prev_nl_of(off) : 1u) : (ch[c - 1].c.nl >> 31), ch[c]);
+        }
+        std::vector<uint32_t> entry; uint32_t kind;
+        x1_entries(ch, tentry, entry, kind);
+        uint32_t rank = 0, hrank = 0;
+        for (int c = 0; c < NCH; c++) {
+            const int64_t off = t * TILE + c * 32;
+            const uint32_t h = hdr_fill32(ch[c].c.nl, ch[c].hs, entry[c]);
+            const uint32_t seqmask = ~ch[c].c.nl & ~h;
+            uint32_t r2 = rank;
+            for (int half = 0; half < 2; half++) {
+                const uint32_t sm = (seqmask >> (16 * half)) & 0xFFFFu, cnt = pg_popc(sm);
+                if (cnt) {
+                    uint32_t d = pext16_2bit(half ? ch[c].c.dig_hi : ch[c].c.dig_lo, sm), m = pext16_1bit((ch[c].c.amb >> (16 * half)) & 0xFFFFu, sm);
+                    if (cnt < 16) d &= (1u << (2 * cnt)) - 1u;
+                    const uint64_t g = tseq + r2;
+                    const uint32_t sh = 2 * (g & 15);
+                    pk2[g >> 4] |= d << sh;
+                    if (sh && (d >> (32 - sh))) pk2[(g >> 4) + 1] |= d >> (32 - sh);
+                    const uint32_t sh1 = g & 31;
+                    amb[g >> 5] |= m << sh1;
+                    if (sh1 > 16 && (m >> (32 - sh1))) amb[(g >> 5) + 1] |= m >> (32 - sh1);
+                }
+                r2 += cnt;
+            }
+            uint32_t hs = ch[c].hs; uint64_t idx = thdr + hrank;
+            while (hs) {
+                const int j = pg_ctz(hs); hs &= hs - 1;
+                if ((int64_t)idx < cap_rec) { hdr_off[idx] = off + j; seq_off[idx] = (int64_t)(tseq + rank + pg_popc(seqmask & ((1u << j) - 1u))); }
+                idx++;
+            }
+            rank = r2; hrank += pg_popc(ch[c].hs);
+        }
+        const TileFn &f = fn[(size_t)t];
+        if ((tentry ? f.seq1 : f.seq0) != rank || f.hdr != hrank) return -1000 - t;      // pass A's summary must agree with pass C
+    }
     return counts[1];
 }

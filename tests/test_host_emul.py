@@ -26,6 +26,7 @@ def emul():
     L = ctypes.CDLL(_SO)
     L.emul_pack.restype = ctypes.c_int64
     L.emul_pack2.restype = ctypes.c_int64
+    L.emul_pack3.restype = ctypes.c_int64
     L.emul_dbg.restype = ctypes.c_int64
     return L
 
@@ -133,10 +134,11 @@ def test_emul_single_pass_pack_matches_golden(emul, case):
     """the single-pass K1 formulation (states from the last newline, tile_sum3) == the oracle's parse"""
     data = case["input_latin1"].encode("latin-1")
     ref = oracle.run(data, case["k"], c=case["c"], stages=1)
-    pk2, amb, hdr, so, counts = run_pack(emul, data, "emul_pack2")
-    assert so.tolist() == ref["seq_off"].tolist()
-    assert hdr.tolist() == ref["hdr_off"].tolist()
-    assert unpack_syms(pk2, amb, int(counts[1])).tolist() == syms_of_bytes(ref["seq"]).tolist()
+    for fn in ("emul_pack2", "emul_pack3"):
+        pk2, amb, hdr, so, counts = run_pack(emul, data, fn)
+        assert so.tolist() == ref["seq_off"].tolist(), fn
+        assert hdr.tolist() == ref["hdr_off"].tolist(), fn
+        assert unpack_syms(pk2, amb, int(counts[1])).tolist() == syms_of_bytes(ref["seq"]).tolist(), fn
 
 
 def test_emul_single_pass_pack_hostile_layouts(emul):
@@ -148,11 +150,12 @@ def test_emul_single_pass_pack_hostile_layouts(emul):
         data = (b">h\n" if it % 3 else b"") + body
         ref = oracle.run(data, 5, stages=1)
         a = run_pack(emul, data, "emul_pack")
-        b = run_pack(emul, data, "emul_pack2")
-        assert (a[3] - a[3][0]).tolist() == ref["seq_off"].tolist(), data[:80]      # bases before the first header stay in the stream
-        assert a[3].tolist() == b[3].tolist() and a[2].tolist() == b[2].tolist() and a[4][:3].tolist() == b[4][:3].tolist()
         nb = int(a[4][1])
-        assert np.array_equal(unpack_syms(a[0], a[1], nb), unpack_syms(b[0], b[1], nb))
+        assert (a[3] - a[3][0]).tolist() == ref["seq_off"].tolist(), data[:80]      # bases before the first header stay in the stream
+        for fn in ("emul_pack2", "emul_pack3"):      # the single-pass and the 32-byte-chunk / local-header formulations
+            b = run_pack(emul, data, fn)
+            assert a[3].tolist() == b[3].tolist() and a[2].tolist() == b[2].tolist() and a[4][:3].tolist() == b[4][:3].tolist(), (fn, data[:80])
+            assert np.array_equal(unpack_syms(a[0], a[1], nb), unpack_syms(b[0], b[1], nb)), (fn, data[:80])
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if (c["c"] >> 1) & 1 and "Ns" not in c], ids=lambda c: c["name"])
@@ -173,14 +176,15 @@ def test_emul_compact_records_match_golden(emul, case):
     assert rk.tolist() == case["rdbg"]
 
 
-@pytest.mark.parametrize("k", [4, 12, 21, 26, 27])
-def test_emul_compact_records_big(emul, k):
-    """1 Mbp x 4 with every k parity (even k: palindromes take the fold-and-count-twice bit)"""
+@pytest.mark.parametrize("k,form", [(4, 1), (12, 1), (21, 1), (26, 1), (27, 1), (17, 2), (21, 2), (26, 2), (27, 2)])
+def test_emul_compact_records_big(emul, k, form):
+    """1 Mbp x 4 with every k parity (even k: palindromes take the fold-and-count-twice bit); form 2 = the compile-time-k
+    extraction (pg_interior_visit_ck: funnel shifts of three digit words, no rolling state)"""
     data = survey_4x1m()[:600_000]
     data = data[:data.rfind(b"\n") + 1]
     pk2, amb, hdr, so, counts = run_pack(emul, data)
     emul.emul_compact_bad.restype = ctypes.c_int64
-    emul.emul_set_compact(1)
+    emul.emul_set_compact(form)
     try:
         (ks, vs, cs), rk = run_dbg(emul, pk2, amb, so, k, 2)
         assert emul.emul_compact_bad() == 0
