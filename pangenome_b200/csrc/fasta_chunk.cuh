@@ -279,8 +279,9 @@ PG_HD Cls32 classify32(const uint32_t w[8], int64_t left) {
     const int n_lo = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
     const int64_t left_hi = left - 16;
     const int n_hi = left_hi >= 16 ? 16 : (left_hi > 0 ? (int)left_hi : 0);
-    const ChunkCls a = LINES_ONLY ? classify16_lines(w, n_lo, left <= 16) : classify16(w, n_lo, left <= 16);
-    const ChunkCls b = LINES_ONLY ? classify16_lines(w + 4, n_hi, left_hi <= 16) : classify16(w + 4, n_hi, left_hi <= 16);
+    const uint32_t wl[4] = {w[0], w[1], w[2], w[3]}, wh[4] = {w[4], w[5], w[6], w[7]};
+    const ChunkCls a = LINES_ONLY ? classify16_lines(wl, n_lo, left <= 16) : classify16(wl, n_lo, left <= 16);
+    const ChunkCls b = LINES_ONLY ? classify16_lines(wh, n_hi, left_hi <= 16) : classify16(wh, n_hi, left_hi <= 16);
     Cls32 c;
     c.nl = (a.nl & 0xFFFFu) | (b.nl << 16); c.gt = (a.gt & 0xFFFFu) | (b.gt << 16); c.amb = (a.amb & 0xFFFFu) | (b.amb << 16);
     c.dig_lo = a.dig; c.dig_hi = b.dig; c.real_nl = a.real_nl + b.real_nl;

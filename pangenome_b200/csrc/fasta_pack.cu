@@ -537,6 +537,247 @@ k1_fused_pack(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles,
     }
 }
 
+
+// =================================================================================================
+// K1 in 32-byte chunks with LOCAL header detection (fasta_chunk.cuh, "K1 in 32-byte chunks"): the default.
+//   A  k1x_tile_aggs   16 KB tiles, one 32-byte chunk per thread: newline / '>' masks only; the in-header bit carried
+//                      across chunks by two ballots per warp and once more across the 16 warps; per tile ONE uint4:
+//                      bases if the tile is entered outside a header, how many of them precede its first line end (they
+//                      are header bytes if it is entered inside one), headers started, the state it hands on, real '\n's
+//   B  k1x_scan        one CTA composes the tiles as functions of their entry state (TileFn) with a shuffle scan
+//   C  k1x_pack        every tile again with the full classification: ranks from a plain sum scan, 2-bit / 1-bit pack
+//                      staged in shared memory, whole-word stores (the write-out of k1_tile_pack)
+// Against the three launches above: no 3-variant summary per chunk, no ordered scan over them (the per-chunk work of
+// passes A and C drops from ~70 to ~15 thread-instructions per input byte), half as many scan participants.
+constexpr int X_THREADS = 512;
+constexpr int X_TILE = X_THREADS * 32;
+constexpr int X_NW = X_THREADS / 32;
+static_assert(X_TILE == K1_TILE, "the staging arrays and the workspace are sized for 16 KB tiles");
+
+__device__ __forceinline__ void x_load32(const uint8_t *fasta, int64_t nbytes, int64_t off, uint4 &a, uint4 &b) {
+    const int64_t left = nbytes - off;
+    if (left >= 32) {
+        a = __ldg(reinterpret_cast<const uint4 *>(fasta + off)); b = __ldg(reinterpret_cast<const uint4 *>(fasta + off) + 1);
+    } else {
+        uint64_t q[4] = {0, 0, 0, 0};
+        for (int i = 0; i < (int)left; i++) {           // the ragged chunk(s) at the end of the file
+            const uint64_t v = (uint64_t)fasta[off + i] << (8 * (i & 7));
+            if (i < 8) q[0] |= v; else if (i < 16) q[1] |= v; else if (i < 24) q[2] |= v; else q[3] |= v;
+        }
+        a = make_uint4((uint32_t)q[0], (uint32_t)(q[0] >> 32), (uint32_t)q[1], (uint32_t)(q[1] >> 32));
+        b = make_uint4((uint32_t)q[2], (uint32_t)(q[2] >> 32), (uint32_t)q[3], (uint32_t)(q[3] >> 32));
+    }
+}
+template <bool LINES_ONLY>
+__device__ __forceinline__ Cls32 x_classify(const uint4 &a, const uint4 &b, int64_t left) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    return classify32<LINES_ONLY>(w, left);
+}
+// the byte before the chunk ends a line (or the chunk starts the file): lane 0 looks, the others take the neighbour's bit 31
+__device__ __forceinline__ uint32_t x_prev_nl(const uint8_t *fasta, int64_t nbytes, int64_t off, uint32_t nl) {
+    uint32_t p = __shfl_up_sync(0xffffffffu, nl >> 31, 1);
+    if ((threadIdx.x & 31) == 0) p = off == 0 ? 1u : (off - 1 < nbytes ? (uint32_t)(fasta[off - 1] == '\n') : 1u);
+    return p;
+}
+// entry state of this thread's chunk: two ballots inside the warp, the warps' kinds through shared memory.
+// Contains one __syncthreads.  tile_kind: what the whole tile hands on.
+__device__ __forceinline__ uint32_t x_chunk_entry(uint32_t kind, uint32_t tile_entry, uint32_t *s_wkind, uint32_t &tile_kind) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t fixed = __ballot_sync(0xffffffffu, kind != HK_PASS), set = __ballot_sync(0xffffffffu, kind == HK_SET);
+    if (lane == 0) s_wkind[warp] = fixed ? (set >> pg_msb(fixed)) & 1u : (uint32_t)HK_PASS;
+    __syncthreads();
+    const uint32_t k2 = lane < X_NW ? s_wkind[lane] : (uint32_t)HK_PASS;
+    const uint32_t tf = __ballot_sync(0xffffffffu, k2 != HK_PASS), ts = __ballot_sync(0xffffffffu, k2 == HK_SET);
+    tile_kind = tf ? (ts >> pg_msb(tf)) & 1u : (uint32_t)HK_PASS;
+    const uint32_t wentry = hdr_entry_from_masks(tf, ts, warp, tile_entry);
+    return hdr_entry_from_masks(fixed, set, lane, wentry);
+}
+
+__global__ void __launch_bounds__(X_THREADS)
+k1x_tile_aggs(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles, uint4 *__restrict__ aggs) {
+    __shared__ uint32_t s_wkind[X_NW];
+    __shared__ uint32_t s_seq, s_hdr, s_nl, s_first;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) { s_seq = 0; s_hdr = 0; s_nl = 0; s_first = X_TILE; }
+        const int64_t off = tile * X_TILE + (int64_t)threadIdx.x * 32;
+        uint4 wa, wb;
+        x_load32(fasta, nbytes, off, wa, wb);
+        const Cls32 c = x_classify<true>(wa, wb, nbytes - off);
+        const uint32_t hs = hdr_starts32(c.nl, c.gt, x_prev_nl(fasta, nbytes, off, c.nl));
+        uint32_t tile_kind;
+        const uint32_t entry = x_chunk_entry(hdr_kind32(c.nl, hs), 0u, s_wkind, tile_kind);      // barrier inside: the zeroed sums are visible
+        const uint32_t h = hdr_fill32(c.nl, hs, entry);
+        uint32_t seq = pg_popc(~c.nl & ~h), nh = pg_popc(hs), rnl = c.real_nl;
+        uint32_t first = c.nl ? (uint32_t)threadIdx.x * 32u + (uint32_t)pg_ctz(c.nl) : (uint32_t)X_TILE;
+        seq = __reduce_add_sync(0xffffffffu, seq); nh = __reduce_add_sync(0xffffffffu, nh); rnl = __reduce_add_sync(0xffffffffu, rnl);
+        first = __reduce_min_sync(0xffffffffu, first);
+        if ((threadIdx.x & 31) == 0) {
+            if (seq) atomicAdd(&s_seq, seq);
+            if (nh) atomicAdd(&s_hdr, nh);
+            if (rnl) atomicAdd(&s_nl, rnl);
+            if (first < (uint32_t)X_TILE) atomicMin(&s_first, first);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t pre = (hs & 1u) ? 0u : s_first;       // a tile entered inside a header loses the bases before its first line end
+            aggs[tile] = make_uint4(s_seq, pre, s_hdr | (tile_kind << 30), s_nl);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ TileFn x_fn_of(const uint4 a) { return tilefn_make(a.x, a.y, a.z & 0x3FFFFFFFu, a.z >> 30, a.w); }
+__device__ __forceinline__ TileFn x_fn_shfl_up(const TileFn &f, int d) {
+    TileFn g;
+    g.seq0 = __shfl_up_sync(0xffffffffu, f.seq0, d); g.seq1 = __shfl_up_sync(0xffffffffu, f.seq1, d);
+    g.hdr = __shfl_up_sync(0xffffffffu, f.hdr, d); g.nl = __shfl_up_sync(0xffffffffu, f.nl, d);
+    const uint32_t e = __shfl_up_sync(0xffffffffu, f.exit0 | (f.exit1 << 1), d);
+    g.exit0 = e & 1u; g.exit1 = e >> 1;
+    return g;
+}
+constexpr int XB_THREADS = 1024;
+
+__global__ void __launch_bounds__(XB_THREADS)
+k1x_scan(const uint4 *__restrict__ aggs, int64_t ntiles, TileEntry *__restrict__ entries, uint32_t *__restrict__ pk2,
+         uint32_t *__restrict__ amb, int64_t *__restrict__ seq_off, int64_t cap_records, int64_t *__restrict__ counts) {
+    __shared__ TileFn s_w[XB_THREADS / 32];
+    __shared__ TileFn s_total;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t per = (ntiles + XB_THREADS - 1) / XB_THREADS;
+    const int64_t lo = (int64_t)t * per < ntiles ? (int64_t)t * per : ntiles, hi = lo + per < ntiles ? lo + per : ntiles;
+    TileFn mine = tilefn_identity();
+    for (int64_t i = lo; i < hi; i++) mine = tilefn_compose(mine, x_fn_of(aggs[i]));
+    // inclusive scan of the (non-commutative) composition over the block: inside the warps, then over the warp totals
+    TileFn inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const TileFn y = x_fn_shfl_up(inc, d); if (lane >= d) inc = tilefn_compose(y, inc); }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        TileFn a = s_w[lane], ainc = a;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const TileFn y = x_fn_shfl_up(ainc, d); if (lane >= d) ainc = tilefn_compose(y, ainc); }
+        const TileFn ex = x_fn_shfl_up(ainc, 1);
+        __syncwarp();
+        s_w[lane] = lane == 0 ? tilefn_identity() : ex;           // exclusive over the warps
+        if (lane == 31) s_total = ainc;
+    }
+    __syncthreads();
+    TileFn before = x_fn_shfl_up(inc, 1);
+    if (lane == 0) before = tilefn_identity();
+    before = tilefn_compose(s_w[warp], before);                   // everything before this thread's first tile
+    const TileFn total = s_total;
+    // a file without any real '\n' yields no line at all (readline_jit_ :129-132: `end > start > 0`)
+    const bool dead = total.nl == 0;
+    if (t == 0) {
+        counts[0] = dead ? 0 : (int64_t)total.hdr;
+        counts[1] = dead ? 0 : (int64_t)total.seq0;
+        counts[2] = (int64_t)total.nl;
+        counts[3] = dead ? 1 : 0;
+        if (!dead && (int64_t)total.hdr <= cap_records) seq_off[total.hdr] = (int64_t)total.seq0;
+        if (dead) seq_off[0] = 0;
+        const uint64_t tot = dead ? 0 : total.seq0;               // zero the padding the k-mer kernels may read past the last base
+        for (int i = 0; i < 16; i++) { pk2[(tot >> 4) + i] = 0; amb[(tot >> 5) + i] = 0; }
+    }
+    // the file starts outside a header: only the entry-0 branch of `before` is ever taken
+    uint64_t seq = before.seq0, hdr = before.hdr; uint32_t st = before.exit0;
+    for (int64_t i = lo; i < hi; i++) {
+        TileEntry e; e.seq = seq; e.hdr = hdr; e.state = st; e.dead = dead ? 1u : 0u;
+        entries[i] = e;
+        if (!dead) { pk2[seq >> 4] = 0; amb[seq >> 5] = 0; }      // words shared between neighbouring tiles (the tiles OR into them)
+        const TileFn f = x_fn_of(aggs[i]);
+        seq += st ? f.seq1 : f.seq0; hdr += f.hdr; st = st ? f.exit1 : f.exit0;
+    }
+}
+
+__global__ void __launch_bounds__(X_THREADS)
+k1x_pack(const uint8_t *__restrict__ fasta, int64_t nbytes, int64_t ntiles, const TileEntry *__restrict__ entries,
+         uint32_t *__restrict__ pk2, uint32_t *__restrict__ amb, int64_t *__restrict__ hdr_off, int64_t *__restrict__ seq_off,
+         int64_t cap_records) {
+    __shared__ uint32_t s_wkind[X_NW];
+    __shared__ uint32_t s_wtot[X_NW + 1];
+    __shared__ uint32_t s_pk[K1_PKW];
+    __shared__ uint32_t s_am[K1_AMW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileEntry e = entries[tile];
+        if (e.dead) return;
+        const int64_t off = tile * X_TILE + (int64_t)threadIdx.x * 32;
+        uint4 wa, wb;
+        x_load32(fasta, nbytes, off, wa, wb);                     // loads in flight while the staging is cleared
+        for (int i = threadIdx.x; i < K1_PKW; i += X_THREADS) s_pk[i] = 0;
+        for (int i = threadIdx.x; i < K1_AMW; i += X_THREADS) s_am[i] = 0;
+        const Cls32 c = x_classify<false>(wa, wb, nbytes - off);
+        const uint32_t hs = hdr_starts32(c.nl, c.gt, x_prev_nl(fasta, nbytes, off, c.nl));
+        uint32_t tile_kind;
+        const uint32_t entry = x_chunk_entry(hdr_kind32(c.nl, hs), e.state, s_wkind, tile_kind);      // barrier inside: staging zeroed
+        const uint32_t seqmask = ~c.nl & ~hdr_fill32(c.nl, hs, entry);
+        // ranks: bases | headers << 16 before this chunk, plain sum scan
+        const uint32_t cnt = pg_popc(seqmask) | (pg_popc(hs) << 16);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+        if (lane == 31) s_wtot[warp] = inc;
+        __syncthreads();
+        uint32_t wt = lane < X_NW ? s_wtot[lane] : 0u, winc = wt;
+#pragma unroll
+        for (int d = 1; d < X_NW; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += y; }
+        const uint32_t wbase = __shfl_sync(0xffffffffu, winc - wt, warp);
+        const uint32_t total = __shfl_sync(0xffffffffu, winc, X_NW - 1);
+        const uint32_t excl = wbase + inc - cnt;
+        const uint32_t rank = excl & 0xFFFFu, hrank = excl >> 16;
+        const uint32_t a0 = (uint32_t)(e.seq & 31);
+        // ---- pack the two 16-byte halves into the shared-memory staging
+        uint32_t r2 = rank;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t sm = (seqmask >> (16 * half)) & 0xFFFFu, n = pg_popc(sm);
+            if (n) {
+                uint32_t d = pext16_2bit(half ? c.dig_hi : c.dig_lo, sm);
+                const uint32_t m = pext16_1bit((c.amb >> (16 * half)) & 0xFFFFu, sm);
+                if (n < 16) d &= (1u << (2 * n)) - 1u;
+                const uint32_t q = a0 + r2, sh = 2 * (q & 15);
+                atomicOr(&s_pk[q >> 4], d << sh);
+                if (sh && (d >> (32 - sh))) atomicOr(&s_pk[(q >> 4) + 1], d >> (32 - sh));
+                if (m) {
+                    const uint32_t sh1 = q & 31;
+                    atomicOr(&s_am[q >> 5], m << sh1);
+                    if (sh1 > 16 && (m >> (32 - sh1))) atomicOr(&s_am[(q >> 5) + 1], m >> (32 - sh1));
+                }
+            }
+            r2 += n;
+        }
+        if (hs) {   // rare: this chunk starts record(s)
+            uint32_t x = hs; uint64_t idx = e.hdr + hrank;
+            while (x) {
+                const int j = pg_ctz(x); x &= x - 1;
+                if ((int64_t)idx < cap_records) {
+                    hdr_off[idx] = off + j;
+                    seq_off[idx] = (int64_t)(e.seq + rank + pg_popc(seqmask & ((1u << j) - 1u)));
+                }
+                idx++;
+            }
+        }
+        __syncthreads();
+        // ---- write-out: words fully owned by this tile are stored, shared boundary words are OR-ed
+        const uint32_t end = a0 + (total & 0xFFFFu);
+        uint32_t *gpk = pk2 + ((e.seq >> 5) << 1);
+        uint32_t *gam = amb + (e.seq >> 5);
+        const uint32_t npk = (end + 15) >> 4, nam = (end + 31) >> 5;
+        for (uint32_t x = threadIdx.x; x < npk; x += X_THREADS) {
+            const uint32_t v = s_pk[x];
+            if (16 * x >= a0 && 16 * (x + 1) <= end) gpk[x] = v;
+            else if (v) atomicOr(&gpk[x], v);
+        }
+        for (uint32_t x = threadIdx.x; x < nam; x += X_THREADS) {
+            const uint32_t v = s_am[x];
+            if (32 * x >= a0 && 32 * (x + 1) <= end) gam[x] = v;
+            else if (v) atomicOr(&gam[x], v);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t pg_pack_words(int64_t cap_bases) { return (cap_bases < 0 ? 0 : cap_bases) / 16 + 32; }
@@ -592,6 +833,20 @@ extern "C" int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes, uint32
         int grid1 = (int)(ntiles < maxg ? ntiles : maxg);
         k1_fused_pack<<<grid1, K1_THREADS, 0, stream>>>(d_fasta, nbytes, ntiles, ticket, agg, tile_nl, pref, pflag, d_pk2, d_amb,
                                                         d_hdr_off, d_seq_off, cap_records, d_counts);
+        PG_CUDA(cudaGetLastError());
+        return PG_OK;
+    }
+    static int legacy = -1;
+    if (legacy < 0) { const char *e = getenv("PG_K1_LEGACY"); legacy = e ? atoi(e) : 0; }
+    if (!legacy) {
+        // 32-byte chunks, local header detection: aggregates (uint4 per tile), one-CTA scan, pack
+        uint4 *aggs = reinterpret_cast<uint4 *>(d_ws);
+        TileEntry *ent = reinterpret_cast<TileEntry *>(reinterpret_cast<char *>(d_ws) + (ntiles < 1 ? 1 : ntiles) * sizeof(uint4));
+        const int sms_ = pg_num_sms();
+        const int grid_x = (int)(ntiles < (int64_t)sms_ * 4 ? (ntiles < 1 ? 1 : ntiles) : (int64_t)sms_ * 4);
+        if (ntiles > 0) k1x_tile_aggs<<<grid_x, X_THREADS, 0, stream>>>(d_fasta, nbytes, ntiles, aggs);
+        k1x_scan<<<1, XB_THREADS, 0, stream>>>(aggs, ntiles, ent, d_pk2, d_amb, d_seq_off, cap_records, d_counts);
+        if (ntiles > 0) k1x_pack<<<grid_x, X_THREADS, 0, stream>>>(d_fasta, nbytes, ntiles, ent, d_pk2, d_amb, d_hdr_off, d_seq_off, cap_records);
         PG_CUDA(cudaGetLastError());
         return PG_OK;
     }
