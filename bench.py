@@ -447,9 +447,9 @@ def main():
                                                              % (rec_b, rec_b, max(1, len(bld.levels) - 1))}
     if world > 1:
         k2b_ms = allmax(sum(a.elapsed_time(b) for a, b in kev["k2b"]) / len(kev["k2b"]))
-        b2 = 32.0 * (n_ins / 2) / world / bld.n_rounds
+        b2 = 2 * rec_b * (n_ins / 2) / world / bld.n_rounds
         roof["other_kernels"]["k2b_split"] = {"ms_per_launch": k2b_ms, "algorithmic_bytes_per_launch": b2, "achieved": b2 / (k2b_ms * 1e-3) / 1e9,
-                                              "frac": b2 / (k2b_ms * 1e-3) / 1e9 / peak, "convention": "16 B/record read + 16 B/record written"}
+                                              "frac": b2 / (k2b_ms * 1e-3) / 1e9 / peak, "convention": "%d B/record read + %d B/record written" % (rec_b, rec_b)}
     if world == 1 and not args.no_stages and len(data) <= 2e8:
         # the other kernels the north star names, and the random-slot ceiling K3 runs against (outside the timed region)
         try:
@@ -492,7 +492,17 @@ def main():
                             "(CUDA IPC peer memory); the only collective on the data path is the all-to-all of %d counts per round" % world)
         sent = bld.sent_total.cpu().tolist()                  # records this rank really stored into every owner's buffer (timed steps)
         away = sum(v for r_, v in enumerate(sent) if r_ != rank)
-        line["exchange_bytes_per_gpu_per_step"] = int(allmax(16.0 * away / n_stage_steps))
+        line["exchange_bytes_per_gpu_per_step"] = int(allmax(rec_b * away / n_stage_steps))
+        # the driver's scaling run mixes workloads (BASELINE quotes the metric on configs[1] at one GPU and configs[3] "hash-sharded at
+        # 2/4/8 GPUs"): the strong-scaling base of THIS workload on one GPU is kept in profiles/
+        if args.workload == "cfg4":
+            try:
+                with open(os.path.join(ROOT, "profiles", "r2r_bench_cfg4_n1.json")) as f:
+                    b1 = json.load(f)
+                line["strong_scaling_base"] = {"n_gpus": 1, "value": b1["value"], "ms_per_step": b1["ms_per_step"], "workload": "cfg4",
+                                               "source": "profiles/r2r_bench_cfg4_n1.json (same workload on one GPU, 16-byte records, L2-atomic K3)"}
+            except Exception:
+                pass
     if world == 1 and not args.no_cpu_baseline:
         r, kind, cores, text = cpu_reference_rate(data, k, 5_000_000)
         line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": text,

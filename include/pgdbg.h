@@ -272,8 +272,16 @@ typedef struct pg_cbuckets {
     int64_t part_cap;
     int32_t bits, reserved;
     uint64_t *d_wide;        /* wide_cap 16-byte records */
-    int64_t *d_wide_count;   /* one counter: records offered to the wide spill */
+    int64_t *d_wide_count;   /* one counter: records offered to the wide spill (peer sets: one per owner rank) */
     int64_t wide_cap;
+    /* fused exchange (pg_kmer_partition_c across GPUs; all NULL / 0 otherwise): bucket = owner rank = the LOW bits of
+     * mix64(2-bit code), bits = log2(ranks); bucket o is stored straight into rank o's receive buffers over NVLink at the
+     * slice of source rank my_rank - compact records at d_peer_bases[o] + my_rank * part_cap, wide ones at
+     * d_wide_peer_bases[o] + my_rank * wide_cap (records).  d_records / d_wide stay NULL.  What arrived is split into
+     * hash-prefix buckets by pg_records_split_c and the wide segments are upserted by pg_wide_insert. */
+    uint64_t *const *d_peer_bases;
+    uint64_t *const *d_wide_peer_bases;
+    int32_t my_rank, reserved2;
 } pg_cbuckets;
 int pg_kmer_partition_c(const pg_table *t, const uint32_t *d_pk2, const uint32_t *d_amb, const int64_t *d_seq_off,
                         int64_t n_rec, int64_t g_begin, int64_t g_end, const int64_t *d_counts, int64_t cap_records,
@@ -281,6 +289,8 @@ int pg_kmer_partition_c(const pg_table *t, const uint32_t *d_pk2, const uint32_t
                         int64_t *d_sample_count, pg_stream_t stream);
 int pg_records_resplit_c(const pg_cbuckets *in, int bits, const pg_cbuckets *out, int k, int64_t *d_table_stats, pg_stream_t stream);
 int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int first_round, pg_stream_t stream);
+int pg_records_split_c(const pg_cbuckets *in, const pg_cbuckets *out, int k, int64_t *d_table_stats, pg_stream_t stream);
+int pg_wide_insert(const pg_table *t, const uint64_t *d_wide, const int64_t *d_count, int64_t cap, pg_stream_t stream);
 
 /* ---- table read-out ---------------------------------------------------------
  * pg_table_count   : fills PG_STAT_USED / PG_STAT_ENTRIES in t->d_stats.

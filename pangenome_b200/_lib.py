@@ -41,7 +41,8 @@ BT = ctypes.POINTER(PgBucketSet)
 class PgCBuckets(ctypes.Structure):
     """Compact (8-byte) update records: include/pgdbg.h pg_cbuckets."""
     _fields_ = [("d_records", c_vp), ("d_counts", c_vp), ("part_cap", c_i64), ("bits", ctypes.c_int32), ("reserved", ctypes.c_int32),
-                ("d_wide", c_vp), ("d_wide_count", c_vp), ("wide_cap", c_i64)]
+                ("d_wide", c_vp), ("d_wide_count", c_vp), ("wide_cap", c_i64), ("d_peer_bases", c_vp), ("d_wide_peer_bases", c_vp),
+                ("my_rank", ctypes.c_int32), ("reserved2", ctypes.c_int32)]
 
 
 CT = ctypes.POINTER(PgCBuckets)
@@ -76,6 +77,8 @@ SIGNATURES = {
     "pg_kmer_partition_c": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, CT, c_vp, c_i64, c_vp, c_vp]),
     "pg_records_resplit_c": (c_int, [CT, c_int, CT, c_int, c_vp, c_vp]),
     "pg_region_build_c": (c_int, [PT, CT, c_int, c_vp]),
+    "pg_records_split_c": (c_int, [CT, CT, c_int, c_vp, c_vp]),
+    "pg_wide_insert": (c_int, [PT, c_vp, c_vp, c_i64, c_vp]),
     "pg_microbench_slots": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "pg_table_count": (c_int, [PT, c_vp]),
     "pg_table_export": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -177,7 +177,7 @@ class RoundBuilder:
         # or long ambiguity runs: positions the compact form cannot hold).
         if compact is None:
             compact = os.environ.get("PG_COMPACT", "1") != "0"
-        self._compact_pref = bool(compact) and self.world == 1 and self.mode == _lib.PG_MODE_CANONICAL and self._region_pref == 12
+        self._compact_pref = bool(compact) and self.mode == _lib.PG_MODE_CANONICAL and self._region_pref == 12
         self.compact = False
         cap_log = cap.bit_length() - 1
         region_now = bool(self._region_pref) and 0 <= cap_log - self._region_pref <= self.MAX_REGION_LOG
@@ -207,7 +207,7 @@ class RoundBuilder:
             self._arriving = R * per_pos
             self.wire = None
         else:
-            self.cap_wire = cw = int(R / W * slack) + 8192
+            self.cap_wire = cw = (int(R / W * slack) + 8192) & ~1
             self.wire_bytes = W * cw * 16
             self.own, self._opened, self.peer_tables, self.wire_sets = [], [], [], []
             for _ in range(2):
@@ -235,6 +235,15 @@ class RoundBuilder:
             self.wire_seg_off = torch.arange(W, dtype=torch.int64, device=dev) * cw
             self.sent_total = torch.zeros(W, dtype=torch.int64, device=dev)
             self._arriving = W * cw
+            # the same receive buffers under compact records: W segments of cw 8-byte records, then W segments of cw / 2
+            # wide (16-byte) records; counters [W compact | W wide]
+            self.cap_wide_wire = cw // 2
+            self.wide_peer_tables = [pt + W * cw * 8 for pt in self.peer_tables]
+            self.csend_counts = [torch.zeros(2 * W, dtype=torch.int64, device=dev) for _ in range(2)]
+            self.crecv = [torch.zeros((W, 2), dtype=torch.int64, device=dev) for _ in range(2)]
+            self.cwire_sets = [PgCBuckets(None, self.csend_counts[i].data_ptr(), cw, self.owner_bits, 0, None,
+                                          self.csend_counts[i].data_ptr() + 8 * W, self.cap_wide_wire, self.peer_tables[i].data_ptr(),
+                                          self.wide_peer_tables[i].data_ptr(), rank, 0) for i in range(2)]
         self._configure(cap)
         if self.region_bits and W == 1 and sample and self.n_rounds == 1 and not capacity:
             self.sampler = engine.KeySampler(n_max * per_pos, dev)
@@ -253,6 +262,8 @@ class RoundBuilder:
     def launches_per_round(self):
         """Kernels of this library per round: K2a, (K2b,) then plan + K3, or K2c + K3s + spill upserts."""
         n = 1 + (1 if self.world > 1 else 0)
+        if self.compact and self.world > 1:
+            n += self.world                      # one wide-record upsert per source rank
         return n + ((len(self.levels) - 1 + 2) if self.region_bits else 2)
 
     @property
@@ -291,7 +302,7 @@ class RoundBuilder:
         spill_cap = max(1 << 16, int(self._arriving * self._spill_frac))
         if self.compact:
             if self.sets is None or sub_bits != self.sub_bits or not isinstance(self.sets[0], CompactBuckets):
-                n_sets = 2 if self.n_rounds > 1 else 1
+                n_sets = 2 if (self.world == 1 and self.n_rounds > 1) else 1
                 self.sets = None
                 self.sets = [CompactBuckets(sub_bits, part_cap, spill_cap, dev) for _ in range(n_sets)]
                 self._ev_free = [None, None]
@@ -397,7 +408,7 @@ class RoundBuilder:
                 else:
                     if self._ev_a2a is not None:
                         A.wait_event(self._ev_a2a)          # every peer has drained buffer i (its K2b of two rounds ago)
-                    out = self.wire_sets[i]
+                    out = self.cwire_sets[i] if self.compact else self.wire_sets[i]
                 e0 = stamp(A)
                 smp = self.sampler if (self.sampler is not None and r == 0) else None
                 if smp is not None:
@@ -413,14 +424,30 @@ class RoundBuilder:
                     self.last_estimate = smp.estimate()
                     want = engine.capacity_for(self.last_estimate, t.slots.numel() // 2, load=0.5, margin=1.02)
                     t.set_capacity(max(self.min_capacity, want))
-                if ev is not None and W > 1:
-                    self.sent_total += self.send_counts[i][:W]       # measurement only: records really sent to every owner
+                if ev is not None and W > 1:     # measurement only: records really sent to every owner
+                    self.sent_total += self.csend_counts[i][:W] if self.compact else self.send_counts[i][:W]
                 done = torch.cuda.Event()
                 done.record(A)
             # ---- stream B: (exchange barrier, split,) plan, table sweep
             with torch.cuda.stream(B):
                 B.wait_event(done)
-                if W > 1:
+                if W > 1 and self.compact:
+                    bs = self.sets[0]
+                    x0 = stamp(B)
+                    # one all-to-all for both counters: [owner][compact, wide] -> [source][compact, wide]
+                    dist.all_to_all_single(self.crecv[i], self.csend_counts[i].view(2, W).t().contiguous())
+                    self._ev_a2a = torch.cuda.Event()
+                    self._ev_a2a.record(B)
+                    x1 = stamp(B)
+                    recv_c, recv_w = self.crecv[i][:, 0].contiguous(), self.crecv[i][:, 1].contiguous()
+                    own = self.own[i].value
+                    arrived = PgCBuckets(own, recv_c.data_ptr(), self.cap_wire, self.owner_bits, 0, bs.wide.data_ptr(), bs.wide_count.data_ptr(),
+                                         bs.wide_cap, None, None, 0, 0)
+                    bs.wide_count.zero_()               # K2b-c / K2c-c bucket surplus of this round
+                    check(L.pg_records_split_c(byref(arrived), byref(bs.c), self.k, P(t.stats), engine._stream()), "pg_records_split_c")
+                    self._wide_segments = (own + W * self.cap_wire * 8, recv_w)
+                    x2 = stamp(B)
+                elif W > 1:
                     bs = self.sets[0]
                     x0 = stamp(B)
                     dist.all_to_all_single(self.recv_counts[i], self.send_counts[i][:W])
@@ -450,6 +477,11 @@ class RoundBuilder:
                         cur_c, bits = nxt_c, bits + lb
                     x2c = stamp(B)
                     check(L.pg_region_build_c(byref(t.c), byref(cur_c), 1 if r == 0 else 0, engine._stream()), "pg_region_build_c")
+                    if W > 1:       # the wide records the other ranks sent for keys this rank owns: one segment per source
+                        base, recv_w = self._wide_segments
+                        for src in range(W):
+                            check(L.pg_wide_insert(byref(t.c), ctypes.c_void_p(base + src * self.cap_wide_wire * 16),
+                                                   ctypes.c_void_p(recv_w.data_ptr() + 8 * src), self.cap_wide_wire, engine._stream()), "pg_wide_insert")
                     if ev is not None:
                         ev.setdefault("k2c", []).append((x2, x2c))
                         x2 = x2c

@@ -33,6 +33,10 @@ namespace {
 struct CBuckets {
     uint2 *records; unsigned long long *counts; int64_t part_cap; int bits;
     uint4 *wide; unsigned long long *wide_count; int64_t wide_cap;
+    // fused exchange (K2a-c across GPUs): bucket = OWNER rank; bucket o is written straight into rank o's receive buffers
+    // over NVLink, at the slice reserved for source rank my_rank - compact records at peers[o] + my_rank * part_cap, wide
+    // ones at wide_peers[o] + my_rank * wide_cap, counted in counts[o] / wide_count[o]
+    uint2 *const *peers; uint4 *const *wide_peers; int my_rank;
 };
 
 constexpr uint32_t C_NONE = 0xFFFFFFFFu;
@@ -40,6 +44,19 @@ constexpr uint32_t C_NONE = 0xFFFFFFFFu;
 __device__ __forceinline__ void wide_emit(const CBuckets &b, uint64_t key5, uint32_t masks, uint32_t inc) {
     const unsigned long long at = atomicAdd(b.wide_count, 1ull);
     if ((int64_t)at < b.wide_cap) b.wide[at] = make_uint4((uint32_t)key5, (uint32_t)(key5 >> 32), masks, inc);
+}
+// the same towards the owner rank of the key (fused exchange)
+__device__ __noinline__ void wide_emit_owner(uint4 *const *wide_peers, unsigned long long *wide_counts, int64_t wide_cap, int my_rank,
+                                             uint32_t owner, uint64_t key5, uint32_t masks, uint32_t inc) {
+    const unsigned long long at = atomicAdd(wide_counts + owner, 1ull);
+    if ((int64_t)at < wide_cap) wide_peers[owner][(int64_t)my_rank * wide_cap + (int64_t)at] = make_uint4((uint32_t)key5, (uint32_t)(key5 >> 32), masks, inc);
+}
+__device__ __noinline__ void wide_emit_compact_owner(uint4 *const *wide_peers, unsigned long long *wide_counts, int64_t wide_cap, int my_rank,
+                                                     uint32_t owner, uint64_t rec, int k) {
+    const uint32_t ctx = (uint32_t)(rec >> PG_C_KEYBITS);
+    uint32_t masks, inc;
+    pg_crec_vals(ctx, pg_vlut_entry(ctx & 15u), masks, inc);
+    wide_emit_owner(wide_peers, wide_counts, wide_cap, my_rank, owner, pg_code5_of2_loop(rec & PG_C_KEYMASK, k), masks, inc);
 }
 // a compact record whose bucket is full travels on as a wide one (rare: hash skew)
 __device__ __noinline__ void wide_emit_compact(uint4 *wide, unsigned long long *wide_count, int64_t wide_cap, uint64_t rec, int k) {
@@ -67,7 +84,7 @@ __device__ __forceinline__ void st_stream8_l2first(uint2 *p, uint64_t v, uint64_
 template <int T>
 __device__ __forceinline__ void tile_offsets(int fan, uint32_t *s_hist, uint32_t *s_off, uint32_t *s_end, unsigned long long *s_base,
                                              uint2 **s_dst, uint32_t *s_chunk, uint32_t *s_nrec, unsigned long long *counts,
-                                             uint2 *obase, int64_t part_cap) {
+                                             uint2 *obase, int64_t part_cap, uint2 *const *peers = nullptr, int my_rank = 0) {
     const int lane = threadIdx.x & 31;
     for (int base = 0; base < fan; base += T) {
         const int i = base + threadIdx.x;
@@ -96,7 +113,7 @@ __device__ __forceinline__ void tile_offsets(int fan, uint32_t *s_hist, uint32_t
         if (room < 0) room = 0;
         s_off[i] = off;
         s_end[i] = off + (room < (int64_t)h ? (uint32_t)room : h);
-        s_dst[i] = obase + (int64_t)i * part_cap + (b - (int64_t)off);
+        s_dst[i] = (peers ? peers[i] + (int64_t)my_rank * part_cap : obase + (int64_t)i * part_cap) + (b - (int64_t)off);
     }
     __syncthreads();
 }
@@ -147,7 +164,9 @@ __device__ __noinline__ void sample_key_c(uint64_t *sample_keys, uint64_t sample
 // registers across the barriers: with a compile-time k a window costs two funnel shifts, and the kernel is bound by the
 // latency of its dependent chains at 24 warps per SM, not by its instruction count (holding the records measured 0.349 ms
 // against 0.332 ms; ranks from ballots / MATCH.ANY + per-warp counters instead of the histogram atomic: 0.72 / 0.76 ms).
-template <int T, bool SAMPLE, int KT, int MINB>
+// PEER: the fused exchange - bucket = owner rank = LOW bits of the full mix (disjoint from the slot bits, which are the top
+// ones), runs stored into the owners' receive buffers over NVLink.
+template <int T, bool SAMPLE, int KT, int MINB, bool PEER>
 __global__ void __launch_bounds__(T, MINB)
 k2a_partition_c(CPartArgs a) {
     constexpr int TILE = T * KP_G;
@@ -205,13 +224,13 @@ k2a_partition_c(CPartArgs a) {
                 auto rank = [&](int q, uint64_t F2, uint64_t R2, uint32_t) {
                     const uint64_t key = F2 < R2 ? F2 : R2;
                     uint64_t h;
-                    if (SAMPLE) {
+                    if (SAMPLE || PEER) {
                         h = pg_mix64(key);
-                        if (((h >> 8) & 0xFFu) == 0) sample_key_c(a.sample_keys, a.sample_mask, a.sample_count, key, h);
+                        if (SAMPLE) { if (((h >> 8) & 0xFFu) == 0) sample_key_c(a.sample_keys, a.sample_mask, a.sample_count, key, h); }
                     } else {
                         h = pg_mix64_top(key);
                     }
-                    const uint32_t pid = a.out.bits ? (uint32_t)(h >> shift) : 0u;
+                    const uint32_t pid = PEER ? (uint32_t)h & (uint32_t)(fan - 1) : (a.out.bits ? (uint32_t)(h >> shift) : 0u);
                     pr[q] = pid | (atomicAdd(&s_hist[pid], 1u) << 10);
                 };
                 if (KT) pg_interior_visit_ck<(KT ? KT : 27)>(w, j0, rank);
@@ -233,7 +252,9 @@ k2a_partition_c(CPartArgs a) {
                         uint32_t vf, vr;
                         pg_occ_vals(w, j, g - rs, re - rs, k, vf, vr);
                         const PgUpdate u = pg_canonical_update_w(F, R, vf | (vr << 16));
-                        wide_emit(a.out, u.key, u.masks, u.inc);
+                        if (PEER) wide_emit_owner(a.out.wide_peers, a.out.wide_count, a.out.wide_cap, a.out.my_rank,
+                                                  (uint32_t)pg_hash_kind1(u.key, k) & (uint32_t)(fan - 1), u.key, u.masks, u.inc);
+                        else wide_emit(a.out, u.key, u.masks, u.inc);
                     }
                     pg_codes_roll(w, j, k, a.pow5km1, F, R);
                 }
@@ -241,7 +262,8 @@ k2a_partition_c(CPartArgs a) {
         }
         __syncthreads();
         // ---- 2. offsets in the tile, room in the output buckets
-        tile_offsets<T>(fan, s_hist, s_off, s_end, s_base, s_dst, s_chunk, &s_nrec, a.out.counts, a.out.records, a.out.part_cap);
+        tile_offsets<T>(fan, s_hist, s_off, s_end, s_base, s_dst, s_chunk, &s_nrec, a.out.counts, a.out.records, a.out.part_cap,
+                        PEER ? a.out.peers : nullptr, a.out.my_rank);
         // ---- 3. every record to its sorted position
         if (interior) {
             uint32_t ovf = 0;       // records past their bucket's room (rare: hash skew) are handled after the loop, off the common path
@@ -256,7 +278,10 @@ k2a_partition_c(CPartArgs a) {
             else pg_interior_visit_c<KP_G>(w, j0, k, place);
             if (ovf) {
                 auto spill = [&](int q, uint64_t F2, uint64_t R2, uint32_t ctx4) {
-                    if (ovf & (1u << q)) wide_emit_compact(a.out.wide, a.out.wide_count, a.out.wide_cap, pg_crec_pack(F2, R2, ctx4), k);
+                    if (!(ovf & (1u << q))) return;
+                    if (PEER) wide_emit_compact_owner(a.out.wide_peers, a.out.wide_count, a.out.wide_cap, a.out.my_rank, pr[q] & 1023u,
+                                                      pg_crec_pack(F2, R2, ctx4), k);
+                    else wide_emit_compact(a.out.wide, a.out.wide_count, a.out.wide_cap, pg_crec_pack(F2, R2, ctx4), k);
                 };
                 pg_interior_visit_c<KP_G>(w, j0, k, spill);
             }
@@ -268,7 +293,9 @@ k2a_partition_c(CPartArgs a) {
 }
 
 // ---- K2c-c ---------------------------------------------------------------------------------------------------------
-struct CSplitArgs { CBuckets in, out; int bits; int k; int64_t *stats; };
+// sliced: segment s of `in` writes buckets [s << bits, ...) of `out` by hash bits [skip_bits, skip_bits + bits) (K2c-c);
+// else every segment writes the same 2^bits buckets (K2b-c: what arrived from the other ranks, skip_bits 0)
+struct CSplitArgs { CBuckets in, out; int bits; int k; int64_t *stats; int sliced, skip_bits; };
 
 constexpr int MSC_LOADS = 8;                 // 16-byte loads per thread = 16 records
 
@@ -311,7 +338,7 @@ k2c_multisplit_c(CSplitArgs a) {
     }
     __syncthreads();
     const uint32_t n_tiles = s_tile0[n_seg];
-    const int shift = 64 - a.in.bits - a.bits;
+    const int shift = 64 - a.skip_bits - a.bits;
 
     int seg = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -345,8 +372,9 @@ k2c_multisplit_c(CSplitArgs a) {
         }
         __syncthreads();
         // ---- 2. offsets in the tile, room in this segment's slice of the output buckets
-        tile_offsets<T>(fan, s_hist, s_off, s_end, s_base, s_dst, s_chunk, &s_nrec, a.out.counts + ((int64_t)seg << a.bits),
-                        a.out.records + ((int64_t)seg << a.bits) * a.out.part_cap, a.out.part_cap);
+        const int64_t slice = a.sliced ? ((int64_t)seg << a.bits) : 0;
+        tile_offsets<T>(fan, s_hist, s_off, s_end, s_base, s_dst, s_chunk, &s_nrec, a.out.counts + slice,
+                        a.out.records + slice * a.out.part_cap, a.out.part_cap);
         // ---- 3. every record to its sorted position (one past its bucket's room: remembered, handled off the common path)
         uint32_t ovf = 0;
 #pragma unroll
@@ -412,7 +440,7 @@ __device__ __forceinline__ uint4 lds128c(const void *p) {      // re-issued ever
 // key for a key that has no 2-bit form, met only when a later round reloads a region the wide spill wrote into), the value
 // word comes from the 16-entry table, and the write-out converts to the base-5 key the table holds in HBM.
 template <bool FIRST, int THREADS, int RPT>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 2 : 3)
 k3s_region_build_c(CRegionArgs a) {
     constexpr int NS = 1 << 12;
     constexpr uint32_t CNT_MAX = (1u << 22) - 1u;
@@ -534,12 +562,20 @@ k3s_wide_insert(TableView t, const uint4 *__restrict__ wide, const unsigned long
 }
 
 int make_cbuckets(const pg_cbuckets *b, const char *who, CBuckets &o) {
-    if (!b || !b->d_records || !b->d_counts || !b->d_wide || !b->d_wide_count || b->part_cap < 2 || (b->part_cap & 1) || b->wide_cap < 1 ||
-        b->bits < 0 || ((reinterpret_cast<uintptr_t>(b->d_records) | reinterpret_cast<uintptr_t>(b->d_wide)) & 15))
-        return pg_fail(PG_ERR_INVALID, "%s: bad compact bucket set (even part_cap, wide_cap >= 1, 16-byte aligned buffers)", who);
+    const bool peer = b && b->d_peer_bases != nullptr;
+    if (!b || !b->d_counts || !b->d_wide_count || b->part_cap < 2 || (b->part_cap & 1) || b->wide_cap < 1 || b->bits < 0)
+        return pg_fail(PG_ERR_INVALID, "%s: bad compact bucket set (even part_cap, wide_cap >= 1)", who);
+    if (peer) {
+        if (b->d_records || b->d_wide || !b->d_wide_peer_bases || b->bits > 6 || b->my_rank < 0 || b->my_rank >= (1 << b->bits))
+            return pg_fail(PG_ERR_INVALID, "%s: a peer bucket set has d_peer_bases AND d_wide_peer_bases, no local buffers, bits = log2(ranks) <= 6", who);
+    } else if (!b->d_records || !b->d_wide || ((reinterpret_cast<uintptr_t>(b->d_records) | reinterpret_cast<uintptr_t>(b->d_wide)) & 15)) {
+        return pg_fail(PG_ERR_INVALID, "%s: bad compact bucket set (16-byte aligned buffers)", who);
+    }
     o.records = reinterpret_cast<uint2 *>(b->d_records); o.counts = reinterpret_cast<unsigned long long *>(b->d_counts);
     o.part_cap = b->part_cap; o.bits = b->bits;
     o.wide = reinterpret_cast<uint4 *>(b->d_wide); o.wide_count = reinterpret_cast<unsigned long long *>(b->d_wide_count); o.wide_cap = b->wide_cap;
+    o.peers = reinterpret_cast<uint2 *const *>(b->d_peer_bases); o.wide_peers = reinterpret_cast<uint4 *const *>(b->d_wide_peer_bases);
+    o.my_rank = b->my_rank;
     return PG_OK;
 }
 
@@ -560,19 +596,21 @@ extern "C" int pg_kmer_partition_c(const pg_table *t, const uint32_t *d_pk2, con
     if (out->bits > 10) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_c: at most 2^10 buckets");
     cudaStream_t st = (cudaStream_t)stream_;
     const int fan = 1 << out->bits;
+    const bool peer = a.out.peers != nullptr;
     PG_CUDA(cudaMemsetAsync(out->d_counts, 0, (size_t)fan * 8, st));
-    PG_CUDA(cudaMemsetAsync(out->d_wide_count, 0, 8, st));
+    PG_CUDA(cudaMemsetAsync(out->d_wide_count, 0, (size_t)(peer ? fan : 1) * 8, st));
     int64_t span = g_end - g_begin;                                     // grid sizing only in device-argument mode
     if (d_counts) { n_rec = 1; span = (g_end < 0 || g_end - g_begin > max_bases) ? max_bases - (g_begin < max_bases ? g_begin : max_bases) : g_end - g_begin; }
     if (n_rec == 0 || span <= 0) return PG_OK;
     a.pk2 = reinterpret_cast<const uint64_t *>(d_pk2); a.amb = d_amb; a.n_words = ((g_end + 31) >> 5) + 4;
     a.seq_off = d_seq_off; a.n_rec = n_rec; a.g_begin = g_begin; a.g_end = g_end; a.k = t->k; a.pow5km1 = pg_pow5(t->k - 1);
-    constexpr int T = 256;
+    const int T = peer ? 512 : 256;       // across GPUs 8192-position tiles: twice the run length per owner on NVLink
     const int tile = T * KP_G;
     a.t_first = g_begin / tile; a.n_tiles = (g_begin + span + tile - 1) / tile - a.t_first;
     a.d_counts = d_counts; a.cap_records = cap_records;
     a.sample_keys = nullptr; a.sample_mask = 0; a.sample_count = nullptr;
     if (d_sample_keys) {
+        if (peer) return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_c: no key sampling on the fused exchange");
         if (!d_sample_count || sample_cap < 2 || (sample_cap & (sample_cap - 1)))
             return pg_fail(PG_ERR_INVALID, "pg_kmer_partition_c: sample set needs a power-of-two capacity and a counter");
         a.sample_keys = d_sample_keys; a.sample_mask = (uint64_t)sample_cap - 1;
@@ -583,26 +621,28 @@ extern "C" int pg_kmer_partition_c(const pg_table *t, const uint32_t *d_pk2, con
     if (per_sm_env < 0) { const char *e = getenv("PG_K2AC_CTAS"); per_sm_env = e ? atoi(e) : 0; }
     // 3 CTAs (80 registers) per SM measured 0.278 ms on config 2, 4 CTAs (64 registers, PG_K2AC_CTAS=4) 0.291 ms
     int per_sm = ctas_per_sm(smem, 512);
-    const int want = per_sm_env > 0 ? per_sm_env : 3;
+    const int want = per_sm_env > 0 ? per_sm_env : (peer ? 2 : 3);
     if (per_sm > want) per_sm = want;
     if (per_sm > 4) per_sm = 4;
     const int64_t maxg = (int64_t)pg_num_sms() * per_sm;
     int grid = (int)(a.n_tiles < maxg ? a.n_tiles : maxg);
     if (grid < 1) grid = 1;
-#define K2AC_LAUNCH(S, KT, MB)                                                                                              \
+#define K2AC_LAUNCH(TT, S, KT, MB, P)                                                                                       \
     do {                                                                                                                    \
-        PG_CUDA(cudaFuncSetAttribute(k2a_partition_c<T, S, KT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
-        k2a_partition_c<T, S, KT, MB><<<grid, T, smem, st>>>(a);                                                            \
+        PG_CUDA(cudaFuncSetAttribute(k2a_partition_c<TT, S, KT, MB, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        k2a_partition_c<TT, S, KT, MB, P><<<grid, TT, smem, st>>>(a);                                                       \
     } while (0)
     static int kt_env = -1;
     if (kt_env < 0) { const char *e = getenv("PG_K2AC_GENERIC"); kt_env = e ? atoi(e) : 0; }      // 1: always the runtime-k kernel
     const int kt = kt_env ? 0 : t->k;
-    if (a.sample_keys) {
-        if (kt == 27) K2AC_LAUNCH(true, 27, 3); else if (kt == 21) K2AC_LAUNCH(true, 21, 3); else K2AC_LAUNCH(true, 0, 3);
+    if (peer) {
+        if (kt == 27) K2AC_LAUNCH(512, false, 27, 2, true); else if (kt == 21) K2AC_LAUNCH(512, false, 21, 2, true); else K2AC_LAUNCH(512, false, 0, 2, true);
+    } else if (a.sample_keys) {
+        if (kt == 27) K2AC_LAUNCH(256, true, 27, 3, false); else if (kt == 21) K2AC_LAUNCH(256, true, 21, 3, false); else K2AC_LAUNCH(256, true, 0, 3, false);
     } else if (per_sm >= 4) {
-        if (kt == 27) K2AC_LAUNCH(false, 27, 4); else if (kt == 21) K2AC_LAUNCH(false, 21, 4); else K2AC_LAUNCH(false, 0, 3);
+        if (kt == 27) K2AC_LAUNCH(256, false, 27, 4, false); else if (kt == 21) K2AC_LAUNCH(256, false, 21, 4, false); else K2AC_LAUNCH(256, false, 0, 3, false);
     } else {
-        if (kt == 27) K2AC_LAUNCH(false, 27, 3); else if (kt == 21) K2AC_LAUNCH(false, 21, 3); else K2AC_LAUNCH(false, 0, 3);
+        if (kt == 27) K2AC_LAUNCH(256, false, 27, 3, false); else if (kt == 21) K2AC_LAUNCH(256, false, 21, 3, false); else K2AC_LAUNCH(256, false, 0, 3, false);
     }
 #undef K2AC_LAUNCH
     PG_CUDA(cudaGetLastError());
@@ -617,7 +657,7 @@ extern "C" int pg_records_resplit_c(const pg_cbuckets *in, int bits, const pg_cb
         return pg_fail(PG_ERR_INVALID, "pg_records_resplit_c: bad geometry (bits 1..8, in->bits <= 13, out->bits == in->bits + bits, distinct buffers)");
     cudaStream_t st = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(out->d_counts, 0, (size_t)(1ll << out->bits) * 8, st));
-    a.bits = bits; a.k = k; a.stats = d_table_stats;
+    a.bits = bits; a.k = k; a.stats = d_table_stats; a.sliced = 1; a.skip_bits = in->bits;
     static int thr_env = -1;
     if (thr_env < 0) { const char *e = getenv("PG_SPLITC_THREADS"); thr_env = e ? atoi(e) : 0; }
     const int fan = 1 << bits;
@@ -626,6 +666,34 @@ extern "C" int pg_records_resplit_c(const pg_cbuckets *in, int bits, const pg_cb
     if (threads == 256) return launch_split_c<256>(a, st);
     if (threads == 512) return launch_split_c<512>(a, st);
     return launch_split_c<1024>(a, st);
+}
+
+// K2b-c: what arrived from the other ranks - the 2^in->bits segments of `in`, one per source rank, each of in->part_cap
+// records - into the 2^out->bits hash-prefix buckets of `out` (TOP bits of the mix)
+extern "C" int pg_records_split_c(const pg_cbuckets *in, const pg_cbuckets *out, int k, int64_t *d_table_stats, pg_stream_t stream_) {
+    CSplitArgs a;
+    int rc = make_cbuckets(in, "pg_records_split_c", a.in); if (rc) return rc;
+    rc = make_cbuckets(out, "pg_records_split_c", a.out); if (rc) return rc;
+    if (a.in.peers || a.out.peers || in->bits > 6 || out->bits < 1 || out->bits > 10 || k < 1 || k > 27 || in->d_records == out->d_records)
+        return pg_fail(PG_ERR_INVALID, "pg_records_split_c: bad geometry (local sets, <= 64 segments, 2..1024 buckets, distinct buffers)");
+    cudaStream_t st = (cudaStream_t)stream_;
+    PG_CUDA(cudaMemsetAsync(out->d_counts, 0, (size_t)(1ll << out->bits) * 8, st));
+    a.bits = out->bits; a.k = k; a.stats = d_table_stats; a.sliced = 0; a.skip_bits = 0;
+    const int fan = 1 << a.bits;
+    if (fan <= 64) return launch_split_c<256>(a, st);
+    if (fan <= 256) return launch_split_c<512>(a, st);
+    return launch_split_c<1024>(a, st);
+}
+
+// upsert one segment of wide records (what another rank's K2a-c sent for the keys this rank owns) with L2 atomics
+extern "C" int pg_wide_insert(const pg_table *t, const uint64_t *d_wide, const int64_t *d_count, int64_t cap, pg_stream_t stream_) {
+    if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)) || t->epoch < 1 || t->epoch > PG_EPOCH_MAX)
+        return pg_fail(PG_ERR_INVALID, "pg_wide_insert: bad table");
+    if (!d_wide || !d_count || cap < 1 || (reinterpret_cast<uintptr_t>(d_wide) & 15)) return pg_fail(PG_ERR_INVALID, "pg_wide_insert: bad arguments");
+    k3s_wide_insert<<<pg_num_sms(), 256, 0, (cudaStream_t)stream_>>>(make_view(t), reinterpret_cast<const uint4 *>(d_wide),
+                                                                     reinterpret_cast<const unsigned long long *>(d_count), cap);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
 }
 
 extern "C" int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int first_round, pg_stream_t stream_) {
@@ -640,17 +708,21 @@ extern "C" int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int fi
         return pg_fail(PG_ERR_INVALID, "pg_region_build_c: the bucket set must hold one bucket per 4096-slot region (bits %d, table 2^%d slots)", b->bits, bits);
     cudaStream_t st = (cudaStream_t)stream_;
     ra.t = make_view(t); ra.n_regions = 1 << b->bits;
-    constexpr int THREADS = 512, RPT = 4;
     constexpr int smem = (1 << 12) * 16;
-    const int64_t maxg = (int64_t)pg_num_sms() * 3;
-    const int grid = (int)(ra.n_regions < maxg ? ra.n_regions : maxg);
-    if (first_round) {
-        PG_CUDA(cudaFuncSetAttribute(k3s_region_build_c<true, THREADS, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k3s_region_build_c<true, THREADS, RPT><<<grid, THREADS, smem, st>>>(ra);
-    } else {
-        PG_CUDA(cudaFuncSetAttribute(k3s_region_build_c<false, THREADS, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k3s_region_build_c<false, THREADS, RPT><<<grid, THREADS, smem, st>>>(ra);
-    }
+    static int cfg = -1;
+    if (cfg < 0) { const char *e = getenv("PG_K3SC_CFG"); cfg = e ? atoi(e) : 0; }
+#define K3SC_LAUNCH(F, T, R, PER)                                                                                          \
+    do {                                                                                                                    \
+        const int64_t maxg = (int64_t)pg_num_sms() * (PER);                                                                 \
+        const int grid = (int)(ra.n_regions < maxg ? ra.n_regions : maxg);                                                  \
+        PG_CUDA(cudaFuncSetAttribute(k3s_region_build_c<F, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+        k3s_region_build_c<F, T, R><<<grid, T, smem, st>>>(ra);                                                             \
+    } while (0)
+    if (cfg == 1) { if (first_round) K3SC_LAUNCH(true, 512, 2, 3); else K3SC_LAUNCH(false, 512, 2, 3); }
+    else if (cfg == 2) { if (first_round) K3SC_LAUNCH(true, 1024, 2, 2); else K3SC_LAUNCH(false, 1024, 2, 2); }
+    else if (cfg == 3) { if (first_round) K3SC_LAUNCH(true, 1024, 1, 2); else K3SC_LAUNCH(false, 1024, 1, 2); }
+    else { if (first_round) K3SC_LAUNCH(true, 512, 4, 3); else K3SC_LAUNCH(false, 512, 4, 3); }
+#undef K3SC_LAUNCH
     PG_CUDA(cudaGetLastError());
     k3s_wide_insert<<<pg_num_sms(), 256, 0, st>>>(ra.t, ra.b.wide, ra.b.wide_count, ra.b.wide_cap);
     PG_CUDA(cudaGetLastError());

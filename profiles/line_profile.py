@@ -63,18 +63,20 @@ def main():
     cands = [c for c in cands if len(c[1]) == len(rows)] or cands
     sect, ins = cands[0]
     print("# kernel %s\n# section %s: %d SASS instructions (ncu lists %d)" % (blk["name"], sect, len(ins), len(rows)))
-    agg = collections.defaultdict(lambda: [0.0, 0.0, 0])
-    tot_i = tot_s = 0.0
+    agg = collections.defaultdict(lambda: [0.0, 0.0, 0, 0.0])
+    tot_i = tot_s = tot_w = 0.0
     for (f, l, txt), r in zip(ins, rows):
         n = float(r.get("Instructions Executed") or 0)
         s = float(r.get("# Samples") or 0)
+        wv = float(r.get("L1 Wavefronts Shared") or 0)
         a = agg[(f, l)]
-        a[0] += n; a[1] += s; a[2] += 1
-        tot_i += n; tot_s += s
-    print("# total warp instructions %.0f, stall samples %.0f" % (tot_i, tot_s))
-    print("# inst%%  samples%%  sass  file:line")
-    for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-        print("%6.2f  %6.2f  %4d  %s:%s" % (100 * a[0] / max(tot_i, 1), 100 * a[1] / max(tot_s, 1), a[2], f, l))
+        a[0] += n; a[1] += s; a[2] += 1; a[3] += wv
+        tot_i += n; tot_s += s; tot_w += wv
+    print("# total warp instructions %.0f, stall samples %.0f, shared-memory wavefronts %.0f" % (tot_i, tot_s, tot_w))
+    key = 3 if (len(sys.argv) > 5 and sys.argv[5] == "smem") else 0
+    print("# inst%%  samples%%  smem_wavefronts%%  sass  file:line")
+    for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
+        print("%6.2f  %6.2f  %6.2f  %4d  %s:%s" % (100 * a[0] / max(tot_i, 1), 100 * a[1] / max(tot_s, 1), 100 * a[3] / max(tot_w, 1), a[2], f, l))
 
 
 if __name__ == "__main__":

@@ -90,5 +90,5 @@ def test_cli_stage1_runs_the_benchmarked_kernels(tmp_path):
         pytest.skip("kernel tracing returned no events")
     assert any("k2a_partition" in n for n in names), sorted(names)
     assert any("k3s_region_build" in n for n in names), sorted(names)
-    assert any("k1_tile_pack" in n for n in names), sorted(names)
+    assert any("k1x_pack" in n for n in names), sorted(names)
     assert not any("k2_kmer_insert" in n for n in names), sorted(names)
