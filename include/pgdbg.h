@@ -264,7 +264,10 @@ int pg_region_build(const pg_table *t, const uint64_t *d_records, const int64_t 
  * pg_records_resplit_c (K2c-c): bucket s of `in` is split 2^bits ways (1..8) by hash bits [in->bits, in->bits + bits)
  *   into buckets [s << bits, ...) of `out` (out->bits == in->bits + bits; zeroes out->d_counts).
  * pg_region_build_c (K3s-c): bucket b of `b` (b->bits == log2(capacity) - 12) becomes region b of the table, then the
- *   wide spill is upserted with L2 atomics.  first_round as pg_region_build.  PG_STAT_OVERFLOW: a region filled up;
+ *   wide spill is upserted with L2 atomics.  first_round as pg_region_build.  last_round = 0: more rounds follow - the
+ *   table is left in an INTERMEDIATE form (ACGT-only keys as 2-bit codes under bit 63) that only the next
+ *   pg_region_build_c / pg_wide_insert calls of the same build may read; last_round != 0 writes the base-5 keys.
+ *   A single-round build passes 1, 1.  PG_STAT_OVERFLOW: a region filled up;
  *   PG_STAT_LOST: the wide spill exceeded wide_cap (or K1's record index was truncated) - rebuild on the 16-byte path. */
 typedef struct pg_cbuckets {
     uint64_t *d_records;     /* 2^bits buckets of part_cap (even) 8-byte records, 16-byte aligned */
@@ -288,9 +291,9 @@ int pg_kmer_partition_c(const pg_table *t, const uint32_t *d_pk2, const uint32_t
                         int64_t max_bases, const pg_cbuckets *out, uint64_t *d_sample_keys, int64_t sample_cap,
                         int64_t *d_sample_count, pg_stream_t stream);
 int pg_records_resplit_c(const pg_cbuckets *in, int bits, const pg_cbuckets *out, int k, int64_t *d_table_stats, pg_stream_t stream);
-int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int first_round, pg_stream_t stream);
+int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int first_round, int last_round, pg_stream_t stream);
 int pg_records_split_c(const pg_cbuckets *in, const pg_cbuckets *out, int k, int64_t *d_table_stats, pg_stream_t stream);
-int pg_wide_insert(const pg_table *t, const uint64_t *d_wide, const int64_t *d_count, int64_t cap, pg_stream_t stream);
+int pg_wide_insert(const pg_table *t, const uint64_t *d_wide, const int64_t *d_count, int64_t cap, int last_round, pg_stream_t stream);
 
 /* ---- table read-out ---------------------------------------------------------
  * pg_table_count   : fills PG_STAT_USED / PG_STAT_ENTRIES in t->d_stats.

@@ -76,9 +76,9 @@ SIGNATURES = {
     "pg_buckets_plan": (c_int, [BT, c_vp, c_vp, c_vp]),
     "pg_kmer_partition_c": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, CT, c_vp, c_i64, c_vp, c_vp]),
     "pg_records_resplit_c": (c_int, [CT, c_int, CT, c_int, c_vp, c_vp]),
-    "pg_region_build_c": (c_int, [PT, CT, c_int, c_vp]),
+    "pg_region_build_c": (c_int, [PT, CT, c_int, c_int, c_vp]),
     "pg_records_split_c": (c_int, [CT, CT, c_int, c_vp, c_vp]),
-    "pg_wide_insert": (c_int, [PT, c_vp, c_vp, c_i64, c_vp]),
+    "pg_wide_insert": (c_int, [PT, c_vp, c_vp, c_i64, c_int, c_vp]),
     "pg_microbench_slots": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "pg_table_count": (c_int, [PT, c_vp]),
     "pg_table_export": (c_int, [PT, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -103,6 +103,14 @@ def plan_levels(region_log, world):
     levels as the fan-out limits allow: on BASELINE config 4 at 2 GPUs (2^18 regions per rank) [10, 8], [5, 6, 7] and the
     older tile sort measured 104 / 107 / 101 ms per step - a pass costs its 32 B per record whatever its fan-out, so the
     third pass eats what the longer runs of the first two win."""
+    env = os.environ.get("PG_LEVELS")
+    if env:                                  # experiment switch: "6,6,6"
+        try:
+            lv = [int(x) for x in env.split(",")]
+            if sum(lv) == region_log and all(1 <= x <= (10 if i == 0 else 8) for i, x in enumerate(lv)):
+                return lv
+        except ValueError:
+            pass
     if region_log <= 8:
         return [region_log]
     first = 8 if world == 1 else min(10, max(6, region_log - 8))
@@ -476,12 +484,13 @@ class RoundBuilder:
                         check(L.pg_records_resplit_c(byref(cur_c), lb, byref(nxt_c), self.k, P(t.stats), engine._stream()), "pg_records_resplit_c")
                         cur_c, bits = nxt_c, bits + lb
                     x2c = stamp(B)
-                    check(L.pg_region_build_c(byref(t.c), byref(cur_c), 1 if r == 0 else 0, engine._stream()), "pg_region_build_c")
+                    last = 1 if r == self.n_rounds - 1 else 0
+                    check(L.pg_region_build_c(byref(t.c), byref(cur_c), 1 if r == 0 else 0, last, engine._stream()), "pg_region_build_c")
                     if W > 1:       # the wide records the other ranks sent for keys this rank owns: one segment per source
                         base, recv_w = self._wide_segments
                         for src in range(W):
                             check(L.pg_wide_insert(byref(t.c), ctypes.c_void_p(base + src * self.cap_wide_wire * 16),
-                                                   ctypes.c_void_p(recv_w.data_ptr() + 8 * src), self.cap_wide_wire, engine._stream()), "pg_wide_insert")
+                                                   ctypes.c_void_p(recv_w.data_ptr() + 8 * src), self.cap_wide_wire, last, engine._stream()), "pg_wide_insert")
                     if ev is not None:
                         ev.setdefault("k2c", []).append((x2, x2c))
                         x2 = x2c

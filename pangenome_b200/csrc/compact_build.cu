@@ -439,7 +439,12 @@ __device__ __forceinline__ uint4 lds128c(const void *p) {      // re-issued ever
 // tricks, one CAS site.  Differences: records are 8 bytes, the shared-memory key is the 2-bit code (or PG_WIDE_FLAG | base-5
 // key for a key that has no 2-bit form, met only when a later round reloads a region the wide spill wrote into), the value
 // word comes from the 16-entry table, and the write-out converts to the base-5 key the table holds in HBM.
-template <bool FIRST, int THREADS, int RPT>
+// Between the rounds of a multi-round build the table holds ACGT-only keys in their 2-bit form under PG_C_HBM_FLAG (bit 63;
+// base-5 codes stay below 2^63): a later round then reloads a region without converting 2^RB keys back (27 divisions by 5
+// each - on BASELINE config 4 at 2 GPUs that doubled K3s-c), and only the LAST round writes the base-5 keys the
+// reference's table holds.  The wide upserts between rounds follow the same convention (k3s_wide_insert, compact_mode).
+#define PG_C_HBM_FLAG 0x8000000000000000ull
+template <bool FIRST, bool LAST, int THREADS, int RPT>
 __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 2 : 3)
 k3s_region_build_c(CRegionArgs a) {
     constexpr int NS = 1 << 12;
@@ -462,9 +467,10 @@ k3s_region_build_c(CRegionArgs a) {
             const uint4 g = slots[r * NS + s];
             const uint64_t hi = (uint64_t)g.z | ((uint64_t)g.w << 32);
             if ((hi & ~PG_VAL_MASK) == t.tag) {
-                const uint64_t key5 = (uint64_t)g.x | ((uint64_t)g.y << 32);
-                uint64_t x2;
-                key = pg_code2_of5(key5, t.k, x2) ? x2 : (key5 | PG_WIDE_FLAG);
+                // what an earlier round left: a 2-bit key under PG_C_HBM_FLAG, or the base-5 key of a k-mer with an
+                // ambiguity digit (it has no 2-bit form: PG_WIDE_FLAG in shared memory)
+                const uint64_t kh = (uint64_t)g.x | ((uint64_t)g.y << 32);
+                key = (kh & PG_C_HBM_FLAG) ? (kh & ~PG_C_HBM_FLAG) : (kh | PG_WIDE_FLAG);
                 m = g.z; c = g.w & CNT_MAX;
             }
         }
@@ -533,7 +539,7 @@ k3s_region_build_c(CRegionArgs a) {
             const uint64_t key = s_key[s];
             uint4 g = make_uint4(0u, 0u, 0u, 0u);
             if (key != PG_EMPTY) {
-                const uint64_t key5 = (key & PG_WIDE_FLAG) ? (key & ~PG_WIDE_FLAG) : pg_code5_of2(key, s_lut5);
+                const uint64_t key5 = (key & PG_WIDE_FLAG) ? (key & ~PG_WIDE_FLAG) : (LAST ? pg_code5_of2(key, s_lut5) : (key | PG_C_HBM_FLAG));
                 const uint32_t cnt = s_cnt[s];
                 g = make_uint4((uint32_t)key5, (uint32_t)(key5 >> 32), s_mask[s], (cnt < CNT_MAX ? cnt : CNT_MAX) | (uint32_t)(t.tag >> 32));
             }
@@ -547,7 +553,7 @@ k3s_region_build_c(CRegionArgs a) {
 
 // the wide spill: upserts with L2 atomics, probing confined to the regions (the same kernel region_build.cu runs on its spill)
 __global__ void __launch_bounds__(256)
-k3s_wide_insert(TableView t, const uint4 *__restrict__ wide, const unsigned long long *__restrict__ count, int64_t cap) {
+k3s_wide_insert(TableView t, const uint4 *__restrict__ wide, const unsigned long long *__restrict__ count, int64_t cap, int compact_mode) {
     unsigned long long c = *count;
     if (c > (unsigned long long)cap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_LOST), 1ull);
@@ -556,7 +562,16 @@ k3s_wide_insert(TableView t, const uint4 *__restrict__ wide, const unsigned long
     uint32_t n_claimed = 0;
     for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < c; i += gridDim.x * 256ull) {
         const uint4 r = pg_ld_stream(wide + i);
-        table_upsert(t, (uint64_t)r.x | ((uint64_t)r.y << 32), r.z, r.w, n_claimed);
+        const uint64_t key5 = (uint64_t)r.x | ((uint64_t)r.y << 32);
+        uint64_t x2;
+        const bool pure = pg_code2_of5(key5, t.k, x2);
+        // compact_mode: more rounds follow, ACGT-only keys live in the table in their flagged 2-bit form
+        const uint64_t key = (compact_mode && pure) ? (x2 | PG_C_HBM_FLAG) : key5;
+        const uint64_t h = pure ? pg_mix64(x2) : pg_mix64(~key5);           // == pg_hash_kind1(key5)
+        const uint64_t s = (h >> t.shift) & t.hmask;
+        uint64_t lo, hi;
+        pg_ld_slot_raw(t.slots + 2 * s, lo, hi);
+        table_upsert_from(t, s, lo, hi, key, r.z, r.w, n_claimed);
     }
     publish_claims(t, n_claimed);
 }
@@ -686,17 +701,18 @@ extern "C" int pg_records_split_c(const pg_cbuckets *in, const pg_cbuckets *out,
 }
 
 // upsert one segment of wide records (what another rank's K2a-c sent for the keys this rank owns) with L2 atomics
-extern "C" int pg_wide_insert(const pg_table *t, const uint64_t *d_wide, const int64_t *d_count, int64_t cap, pg_stream_t stream_) {
+extern "C" int pg_wide_insert(const pg_table *t, const uint64_t *d_wide, const int64_t *d_count, int64_t cap, int last_round, pg_stream_t stream_) {
     if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)) || t->epoch < 1 || t->epoch > PG_EPOCH_MAX)
         return pg_fail(PG_ERR_INVALID, "pg_wide_insert: bad table");
-    if (!d_wide || !d_count || cap < 1 || (reinterpret_cast<uintptr_t>(d_wide) & 15)) return pg_fail(PG_ERR_INVALID, "pg_wide_insert: bad arguments");
+    if (!d_wide || !d_count || cap < 1 || (reinterpret_cast<uintptr_t>(d_wide) & 15) || t->hash_kind != 1)
+        return pg_fail(PG_ERR_INVALID, "pg_wide_insert: bad arguments (hash_kind 1 table, 16-byte aligned records)");
     k3s_wide_insert<<<pg_num_sms(), 256, 0, (cudaStream_t)stream_>>>(make_view(t), reinterpret_cast<const uint4 *>(d_wide),
-                                                                     reinterpret_cast<const unsigned long long *>(d_count), cap);
+                                                                     reinterpret_cast<const unsigned long long *>(d_count), cap, last_round ? 0 : 1);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
 
-extern "C" int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int first_round, pg_stream_t stream_) {
+extern "C" int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int first_round, int last_round, pg_stream_t stream_) {
     if (!t || !t->d_slots || !t->d_stats || t->capacity < 2 || (t->capacity & (t->capacity - 1)) || t->epoch < 1 || t->epoch > PG_EPOCH_MAX)
         return pg_fail(PG_ERR_INVALID, "pg_region_build_c: bad table");
     if (t->region_bits != 12 || t->hash_kind != 1 || t->mode != PG_MODE_CANONICAL)
@@ -711,20 +727,24 @@ extern "C" int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int fi
     constexpr int smem = (1 << 12) * 16;
     static int cfg = -1;
     if (cfg < 0) { const char *e = getenv("PG_K3SC_CFG"); cfg = e ? atoi(e) : 0; }
-#define K3SC_LAUNCH(F, T, R, PER)                                                                                          \
+#define K3SC_LAUNCH2(F, LA, T, R, PER)                                                                                     \
     do {                                                                                                                    \
         const int64_t maxg = (int64_t)pg_num_sms() * (PER);                                                                 \
         const int grid = (int)(ra.n_regions < maxg ? ra.n_regions : maxg);                                                  \
-        PG_CUDA(cudaFuncSetAttribute(k3s_region_build_c<F, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-        k3s_region_build_c<F, T, R><<<grid, T, smem, st>>>(ra);                                                             \
+        PG_CUDA(cudaFuncSetAttribute(k3s_region_build_c<F, LA, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+        k3s_region_build_c<F, LA, T, R><<<grid, T, smem, st>>>(ra);                                                         \
     } while (0)
-    if (cfg == 1) { if (first_round) K3SC_LAUNCH(true, 512, 2, 3); else K3SC_LAUNCH(false, 512, 2, 3); }
-    else if (cfg == 2) { if (first_round) K3SC_LAUNCH(true, 1024, 2, 2); else K3SC_LAUNCH(false, 1024, 2, 2); }
-    else if (cfg == 3) { if (first_round) K3SC_LAUNCH(true, 1024, 1, 2); else K3SC_LAUNCH(false, 1024, 1, 2); }
-    else { if (first_round) K3SC_LAUNCH(true, 512, 4, 3); else K3SC_LAUNCH(false, 512, 4, 3); }
+#define K3SC_LAUNCH(T, R, PER)                                                                                              \
+    do {                                                                                                                    \
+        if (first_round) { if (last_round) K3SC_LAUNCH2(true, true, T, R, PER); else K3SC_LAUNCH2(true, false, T, R, PER); } \
+        else { if (last_round) K3SC_LAUNCH2(false, true, T, R, PER); else K3SC_LAUNCH2(false, false, T, R, PER); }          \
+    } while (0)
+    if (cfg == 2) K3SC_LAUNCH(1024, 2, 2);
+    else K3SC_LAUNCH(512, 4, 3);
+#undef K3SC_LAUNCH2
 #undef K3SC_LAUNCH
     PG_CUDA(cudaGetLastError());
-    k3s_wide_insert<<<pg_num_sms(), 256, 0, st>>>(ra.t, ra.b.wide, ra.b.wide_count, ra.b.wide_cap);
+    k3s_wide_insert<<<pg_num_sms(), 256, 0, st>>>(ra.t, ra.b.wide, ra.b.wide_count, ra.b.wide_cap, last_round ? 0 : 1);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

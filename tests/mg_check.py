@@ -59,8 +59,8 @@ def main():
                 assert np.array_equal(ks, ref["dbg"][0]), "keys differ"
                 assert np.array_equal(vs, ref["dbg"][1]), "masks differ"
                 assert np.array_equal(cs_, ref["dbg"][2]), "counts differ"
-                print("mg_check ok: dBG %s, world %d, rounds %d (%d planned), %d entries, max count %d" %
-                      (name, world, rounds, b.n_rounds, ks.size, int(cs_.max())), flush=True)
+                print("mg_check ok: dBG %s, world %d, rounds %d (%d planned), %d entries, max count %d, records: %s" %
+                      (name, world, rounds, b.n_rounds, ks.size, int(cs_.max()), b.describe().get("records")), flush=True)
             if rounds == 1:
                 # stages 2-5 distributed: rdBG all-gather, hits gathered to rank 0, K6-K8 there
                 for c_flag in (2, 3):
