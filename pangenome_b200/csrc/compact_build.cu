@@ -444,7 +444,19 @@ __device__ __forceinline__ uint4 lds128c(const void *p) {      // re-issued ever
 // each - on BASELINE config 4 at 2 GPUs that doubled K3s-c), and only the LAST round writes the base-5 keys the
 // reference's table holds.  The wide upserts between rounds follow the same convention (k3s_wide_insert, compact_mode).
 #define PG_C_HBM_FLAG 0x8000000000000000ull
-template <bool FIRST, bool LAST, int THREADS, int RPT>
+// FP: probe on 16-bit FINGERPRINTS.  The kernel is bound by shared-memory wavefronts, almost half of them the two 16-byte
+// loads (four 8-byte keys) of a probe step, which random addresses stretch to ~10 wavefronts each.  With FP a probe step
+// loads the group's four 16-bit tags (one 8-byte load), compares them in SWAR form and reads a key (8 bytes) only where a
+// tag matches; tag 0 = free.  The 64-bit CAS on the key stays the one source of truth: a claim writes the key first and the
+// tag after it, so a reader can meet a slot whose tag is still 0 although its key is set - its CAS then fails and tells
+// it the key (its own: found; another: that slot is taken, on to the next free one).
+__device__ __forceinline__ uint32_t haszero16(uint32_t x) { return (x - 0x00010001u) & ~x & 0x80008000u; }
+__device__ __forceinline__ uint2 lds64c(const void *p) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return r;
+}
+template <bool FIRST, bool LAST, int THREADS, int RPT, bool FP>
 __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 2 : 3)
 k3s_region_build_c(CRegionArgs a) {
     constexpr int NS = 1 << 12;
@@ -453,6 +465,8 @@ k3s_region_build_c(CRegionArgs a) {
     uint64_t *s_key = reinterpret_cast<uint64_t *>(smem);
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_key + NS);
     uint32_t *s_cnt = s_mask + NS;
+    uint16_t *s_fp = reinterpret_cast<uint16_t *>(s_cnt + NS);          // FP only: NS tags
+    const int tag_shift = a.t.shift - 16;                               // the 16 hash bits below the slot index
     __shared__ uint16_t s_lut5[PG_LUT5_SIZE];
     __shared__ uint32_t s_vlut[16];
     const TableView &t = a.t;
@@ -475,6 +489,11 @@ k3s_region_build_c(CRegionArgs a) {
             }
         }
         s_key[s] = key; s_mask[s] = m; s_cnt[s] = c;
+        if (FP) {       // a key without a 2-bit form never equals a compact record's: any non-zero tag will do
+            uint32_t tg = 0;
+            if (!FIRST && key != PG_EMPTY) tg = (key & PG_WIDE_FLAG) ? 1u : (((uint32_t)(pg_mix64_top(key) >> tag_shift) & 0xFFFFu) | 1u);
+            s_fp[s] = (uint16_t)tg;
+        }
     };
 
     int64_t r = blockIdx.x;
@@ -499,9 +518,42 @@ k3s_region_build_c(CRegionArgs a) {
                 const uint32_t klo = rec[j].x, khi = rec[j].y & (uint32_t)(PG_C_KEYMASK >> 32);
                 const uint32_t ctx = rec[j].y >> (PG_C_KEYBITS - 32);
                 const uint64_t key = (uint64_t)klo | ((uint64_t)khi << 32);
-                uint32_t g = (uint32_t)(pg_mix64_top(key) >> t.shift) & (NS - 1) & ~(uint32_t)(PG_REGION_GROUP - 1);
+                const uint64_t h = pg_mix64_top(key);
+                uint32_t g = (uint32_t)(h >> t.shift) & (NS - 1) & ~(uint32_t)(PG_REGION_GROUP - 1);
                 int s = -1;
-                if (act) {
+                if (act && FP) {
+                    const uint32_t tag = ((uint32_t)(h >> tag_shift) & 0xFFFFu) | 1u, tt = tag * 0x00010001u;
+                    for (int probe = 0; probe < NS / PG_REGION_GROUP;) {
+                        const uint2 tg = lds64c(s_fp + g);
+                        // tags equal to mine (bit 15 / 31 of a word per slot; a flag above a true one may be spurious - every
+                        // candidate is confirmed on its key)
+                        uint32_t cm = (haszero16(tg.x ^ tt) >> 15 & 0x10001u) | ((haszero16(tg.y ^ tt) >> 15 & 0x10001u) << 2);
+                        cm = (cm & 0xFu) | (cm >> 15 & 0xAu);              // slots 0..3 -> bits 0..3
+                        bool found = false;
+                        while (cm) {
+                            const int j = __ffs(cm) - 1; cm &= cm - 1;
+                            const uint2 kk = lds64c(s_key + g + j);
+                            if (kk.x == klo && kk.y == khi) { s = (int)g + j; found = true; break; }
+                        }
+                        if (found) break;
+                        uint32_t em = (haszero16(tg.x) >> 15 & 0x10001u) | ((haszero16(tg.y) >> 15 & 0x10001u) << 2);
+                        em = (em & 0xFu) | (em >> 15 & 0xAu);              // the LOWEST flagged slot is always a true zero
+                        // free slots of the group in ascending order.  A failed CAS says which key holds the slot: mine (found)
+                        // or another one, whose tag is simply not out yet - skip it.  No re-reading, so no lane ever waits
+                        // for another lane's tag store (two lanes of ONE warp racing for a slot would otherwise spin on each other).
+                        while (em) {
+                            const int e = (int)g + __ffs(em) - 1; em &= em - 1;
+                            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(s_key + e), (unsigned long long)PG_EMPTY,
+                                                                     (unsigned long long)key);
+                            if (old == PG_EMPTY) { *reinterpret_cast<volatile uint16_t *>(s_fp + e) = (uint16_t)tag; n_claimed++; s = e; found = true; break; }
+                            if (old == key) { s = e; found = true; break; }
+                        }
+                        if (found) break;
+                        g = (g + PG_REGION_GROUP) & (NS - 1); probe++;
+                    }
+                    if (s < 0) atomicExch(reinterpret_cast<unsigned long long *>(t.stats + PG_STAT_OVERFLOW), 1ull);
+                }
+                if (act && !FP) {
                     for (int probe = 0; probe < NS / PG_REGION_GROUP;) {
                         const uint4 a4 = lds128c(s_key + g), b4 = lds128c(s_key + g + 2);
                         const uint32_t mm = (uint32_t)(a4.x == klo && a4.y == khi) | ((uint32_t)(a4.z == klo && a4.w == khi) << 1) |
@@ -727,13 +779,17 @@ extern "C" int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int fi
     constexpr int smem = (1 << 12) * 16;
     static int cfg = -1;
     if (cfg < 0) { const char *e = getenv("PG_K3SC_CFG"); cfg = e ? atoi(e) : 0; }
-#define K3SC_LAUNCH2(F, LA, T, R, PER)                                                                                     \
+    static int fp = -1;
+    if (fp < 0) { const char *e = getenv("PG_K3SC_FP"); fp = e ? atoi(e) : 0; }      // measured 0.502 ms against 0.480 ms: off
+#define K3SC_LAUNCH3(F, LA, T, R, PER, FPV)                                                                                 \
     do {                                                                                                                    \
+        const int smem_ = smem + ((FPV) ? (1 << 12) * 2 : 0);                                                               \
         const int64_t maxg = (int64_t)pg_num_sms() * (PER);                                                                 \
         const int grid = (int)(ra.n_regions < maxg ? ra.n_regions : maxg);                                                  \
-        PG_CUDA(cudaFuncSetAttribute(k3s_region_build_c<F, LA, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
-        k3s_region_build_c<F, LA, T, R><<<grid, T, smem, st>>>(ra);                                                         \
+        PG_CUDA(cudaFuncSetAttribute(k3s_region_build_c<F, LA, T, R, FPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_)); \
+        k3s_region_build_c<F, LA, T, R, FPV><<<grid, T, smem_, st>>>(ra);                                                   \
     } while (0)
+#define K3SC_LAUNCH2(F, LA, T, R, PER) do { if (fp) K3SC_LAUNCH3(F, LA, T, R, PER, true); else K3SC_LAUNCH3(F, LA, T, R, PER, false); } while (0)
 #define K3SC_LAUNCH(T, R, PER)                                                                                              \
     do {                                                                                                                    \
         if (first_round) { if (last_round) K3SC_LAUNCH2(true, true, T, R, PER); else K3SC_LAUNCH2(true, false, T, R, PER); } \
@@ -741,6 +797,7 @@ extern "C" int pg_region_build_c(const pg_table *t, const pg_cbuckets *b, int fi
     } while (0)
     if (cfg == 2) K3SC_LAUNCH(1024, 2, 2);
     else K3SC_LAUNCH(512, 4, 3);
+#undef K3SC_LAUNCH3
 #undef K3SC_LAUNCH2
 #undef K3SC_LAUNCH
     PG_CUDA(cudaGetLastError());
