@@ -299,7 +299,7 @@ struct CSplitArgs { CBuckets in, out; int bits; int k; int64_t *stats; int slice
 
 constexpr int MSC_LOADS = 8;                 // 16-byte loads per thread = 16 records
 
-template <int T>
+template <int T, bool SLICED>
 __global__ void __launch_bounds__(T, T == 256 ? 3 : (T == 512 ? 2 : 1))
 k2c_multisplit_c(CSplitArgs a) {
     constexpr int TILE = T * MSC_LOADS * 2;
@@ -338,7 +338,7 @@ k2c_multisplit_c(CSplitArgs a) {
     }
     __syncthreads();
     const uint32_t n_tiles = s_tile0[n_seg];
-    const int shift = 64 - a.skip_bits - a.bits;
+    const int shift = 64 - (SLICED ? a.in.bits : 0) - a.bits;
 
     int seg = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -372,7 +372,7 @@ k2c_multisplit_c(CSplitArgs a) {
         }
         __syncthreads();
         // ---- 2. offsets in the tile, room in this segment's slice of the output buckets
-        const int64_t slice = a.sliced ? ((int64_t)seg << a.bits) : 0;
+        const int64_t slice = SLICED ? ((int64_t)seg << a.bits) : 0;
         tile_offsets<T>(fan, s_hist, s_off, s_end, s_base, s_dst, s_chunk, &s_nrec, a.out.counts + slice,
                         a.out.records + slice * a.out.part_cap, a.out.part_cap);
         // ---- 3. every record to its sorted position (one past its bucket's room: remembered, handled off the common path)
@@ -419,8 +419,13 @@ int launch_split_c(const CSplitArgs &a, cudaStream_t st) {
     const int64_t maxg = (int64_t)pg_num_sms() * per_sm;
     int grid = (int)(max_tiles < maxg ? max_tiles : maxg);
     if (grid < 1) grid = 1;
-    PG_CUDA(cudaFuncSetAttribute(k2c_multisplit_c<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k2c_multisplit_c<T><<<grid, T, smem, st>>>(a);
+    if (a.sliced) {
+        PG_CUDA(cudaFuncSetAttribute(k2c_multisplit_c<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k2c_multisplit_c<T, true><<<grid, T, smem, st>>>(a);
+    } else {
+        PG_CUDA(cudaFuncSetAttribute(k2c_multisplit_c<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k2c_multisplit_c<T, false><<<grid, T, smem, st>>>(a);
+    }
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
