@@ -2,24 +2,25 @@
 """bench.py - dBG build throughput (G k-mers/s) of the B200 path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload cfg2|cfg3|small] [--k 27]
+                    [--workload cfg2|cfg3|cfg4|cfg5|small|cfg4s] [--k 27]
 
-One JSON line on stdout (rank 0).  A *step* is one full dBG build of the
-workload: FASTA scan/pack (K1) + table reset + k-mer extraction into
-hash-partitioned update records (K2a) + record insertion (K3).  Metric = k-mer insertions / s, an insertion being
-one k-mer occurrence on one strand: 2 * sum max(n_r - k + 1, 1) over records
-(BASELINE.md section 3).
+One JSON line on stdout (rank 0).  A *step* is one full dBG build of the workload: FASTA scan/pack (K1) + table reset +
+k-mer extraction into hash-partitioned compact 8-byte update records (K2a-c; across GPUs fused with the exchange over
+NVLink) + partition level(s) (K2b-c / K2c-c) + the table regions built in shared memory (K3s-c) + the wide-record
+upserts.  Metric = k-mer insertions / s, an insertion being one k-mer occurrence on one strand:
+2 * sum max(n_r - k + 1, 1) over records.  Workload: BASELINE configs[1] at one GPU, configs[3]
+(strong scaling, ONE file split by byte range) at 2 / 4 / 8 GPUs.
 
- value   : device-resident input (the FASTA bytes already in HBM), CUDA events
-           around exactly K steps, max over ranks.
- e2e     : the same build through the public host API with HOST buffers: pinned
-           FASTA bytes -> H2D, build, D2H of the table statistics + checksum.
- roofline: the dominant kernel (k3_insert_records), timed live with CUDA events on
-           the launching stream; algorithmic bytes = 16 B per insertion
-           (SURVEY.md 8d).
- cpu_baseline: the reference's numba code (oracle/_ref, kind "reference") or,
-           if that is unavailable, the C port (oracle/, kind "port"), one core,
-           on a bounded sample of the same workload.
+ value   : device-resident input (the FASTA bytes already in HBM), CUDA events around exactly K steps, max over ranks.
+ e2e     : the same build through the public host API with HOST buffers: pinned FASTA bytes -> H2D, build, D2H of the
+           table statistics.
+ roofline: the dominant kernel (k3s_region_build_c; k3_insert_records on tables beyond 2^18 regions), timed live with
+           CUDA events on the launching stream; algorithmic bytes = 16 B per insertion; the other kernels
+           of the path in other_kernels with their own conventions.
+ cpu_baseline: the reference's numba code (oracle/_ref, kind "reference") or, if that is unavailable, the C port
+           (oracle/, kind "port"), one core, on a bounded sample of the same workload.
+ checksum: the built table's order-independent checksum, compared with the oracle's (configs 2 / 3) or the recorded one
+           (configs 4 / 5) BEFORE anything is timed: a line is only printed for a correct table.
 """
 import argparse
 import json

@@ -89,3 +89,38 @@ def test_record_ids_and_rows_vectorised():
     res.rows_raw = [(np.array([2, 0, 0]), np.array([0, 0, 2]), np.array([3, 2, 4]), 1, np.array([7, 5, 6])),
                     (np.array([0]), np.array([1]), np.array([3]), -1, np.array([9]))]
     assert res.rows(P, data) == [("a desc", 0, 2, "+", 5), ("a desc", 2, 4, "+", 6), ("a desc", 1, 3, "-", 9), ("c", 0, 3, "+", 7)]
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The ctypes structures in pangenome_b200/_lib.py must have the size and field offsets gcc gives the structs of
+    include/pgdbg.h (a silent mismatch would hand the kernels garbage)."""
+    import ctypes
+    import subprocess
+    from pangenome_b200 import _lib
+    structs = {"pg_table": _lib.PgTable, "pg_bucket_set": _lib.PgBucketSet, "pg_cbuckets": _lib.PgCBuckets, "pg_graph": _lib.PgGraph}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pgdbg.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_edge_stage_checkpoint_flag_is_rejected_loudly():
+    """-R (kmer_numba.py:1876-1890: resume the edge-weight stage from <qry>_rdb_brkpt.npz) is deliberately not built: the
+    reference only ever writes that file after 2^33 bases of one stage call, and its dump/reload cycle (Dict.popitem while
+    dumping, re-insertion on load) reorders every later line of the .xyz file, so a faithful resume would have to
+    replicate numba's typed-dict iteration order.  The CLI must say so instead of silently ignoring the flag."""
+    from pangenome_b200 import cli
+    with pytest.raises(SystemExit) as e:
+        cli.entry_point(["prog", "-i", "x.fa", "-k", "27", "-R", "x.fa_rdb_brkpt.npz"], out=io.StringIO())
+    assert "-R" in str(e.value) and "not supported" in str(e.value)
