@@ -10,18 +10,21 @@
 // the 2-bit domain; the base-5 key the reference's table holds is produced once per DISTINCT key, when K3s-c writes a
 // finished region to HBM).
 //
-//   K2a-c  thread = 16 positions.  Interior: 16 compact records held in REGISTERS, bucket = top bits of mix64(2-bit key),
-//          rank inside the tile's run from the histogram atomic, records stored at their sorted position of an 8-byte
-//          shared-memory staging, linear copy-out (the register-held multisplit of multisplit.cu - the tile sort's
-//          permutation and gather passes were half of K2a's instructions).  Everything else (record edges with '#', '$'
-//          and Q1, ambiguity codes): the generic per-position path of partition.cu, emitted as 16-byte WIDE records
-//          straight into the build's wide spill.
-//   K2c-c  register-held multisplit of 8-byte records, 16 per thread, one level of <= 2^8 ways per launch.
+//   K2a-c  thread = 16 positions.  Interior: bucket = top bits of mix64(2-bit key), rank inside the tile's run from the
+//          histogram atomic, scan, every record stored at its sorted position of an 8-byte shared-memory staging,
+//          linear copy-out (the multisplit of multisplit.cu without the tile sort's permutation and gather passes,
+//          which were half of K2a's instructions).  With a compile-time k the two windows of a position are constant
+//          funnel shifts of three digit words, so the records are derived twice (before and after the scan) rather
+//          than held.  Everything else (record edges with '#', '$' and Q1, ambiguity codes): the generic per-position
+//          path of partition.cu, emitted as 16-byte WIDE records straight into the build's wide spill.  Across GPUs
+//          (PEER) the bucket is the owner rank and the runs are stored into the owners' receive buffers over NVLink.
+//   K2c-c  register-held multisplit of 8-byte records, 16 per thread, one level of <= 2^8 ways per launch; K2b-c: the
+//          same kernel on what arrived from the other ranks (one segment per source -> hash-prefix buckets).
 //   K3s-c  one CTA per 4096-slot region: the region lives in shared memory keyed by the 2-bit code; the value words come
 //          from the 16-entry table by the record's context bits; the region is converted to base-5 keys (6 table
-//          look-ups per live slot) as it is written to HBM.  Later rounds start from what HBM holds (base-5 -> 2-bit on
-//          load; a key with an ambiguity digit keeps its base-5 form under PG_WIDE_FLAG).  The wide spill is upserted
-//          afterwards with L2 atomics.
+//          look-ups per live slot) as the LAST round writes it to HBM.  Between the rounds of a multi-round build the
+//          2-bit keys stay in HBM under PG_C_HBM_FLAG (a key with an ambiguity digit keeps its base-5 form and gets
+//          PG_WIDE_FLAG in shared memory).  The wide spill is upserted afterwards with L2 atomics.
 //
 // The table this produces is placed by the hash of the 2-bit code (pg_table.hash_kind = 1, table_dev.cuh tv_home), probes
 // inside 4096-slot regions like every region-built table, and holds exactly the slots the 16-byte path would: same keys,
@@ -293,9 +296,9 @@ k2a_partition_c(CPartArgs a) {
 }
 
 // ---- K2c-c ---------------------------------------------------------------------------------------------------------
-// sliced: segment s of `in` writes buckets [s << bits, ...) of `out` by hash bits [skip_bits, skip_bits + bits) (K2c-c);
-// else every segment writes the same 2^bits buckets (K2b-c: what arrived from the other ranks, skip_bits 0)
-struct CSplitArgs { CBuckets in, out; int bits; int k; int64_t *stats; int sliced, skip_bits; };
+// sliced (the kernel's SLICED): segment s of `in` writes buckets [s << bits, ...) of `out` by hash bits [in.bits, in.bits + bits)
+// (K2c-c); else every segment writes the same 2^bits buckets by the TOP bits (K2b-c: what arrived from the other ranks)
+struct CSplitArgs { CBuckets in, out; int bits; int k; int64_t *stats; int sliced; };
 
 constexpr int MSC_LOADS = 8;                 // 16-byte loads per thread = 16 records
 
@@ -729,7 +732,7 @@ extern "C" int pg_records_resplit_c(const pg_cbuckets *in, int bits, const pg_cb
         return pg_fail(PG_ERR_INVALID, "pg_records_resplit_c: bad geometry (bits 1..8, in->bits <= 13, out->bits == in->bits + bits, distinct buffers)");
     cudaStream_t st = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(out->d_counts, 0, (size_t)(1ll << out->bits) * 8, st));
-    a.bits = bits; a.k = k; a.stats = d_table_stats; a.sliced = 1; a.skip_bits = in->bits;
+    a.bits = bits; a.k = k; a.stats = d_table_stats; a.sliced = 1;
     static int thr_env = -1;
     if (thr_env < 0) { const char *e = getenv("PG_SPLITC_THREADS"); thr_env = e ? atoi(e) : 0; }
     const int fan = 1 << bits;
@@ -750,7 +753,7 @@ extern "C" int pg_records_split_c(const pg_cbuckets *in, const pg_cbuckets *out,
         return pg_fail(PG_ERR_INVALID, "pg_records_split_c: bad geometry (local sets, <= 64 segments, 2..1024 buckets, distinct buffers)");
     cudaStream_t st = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(out->d_counts, 0, (size_t)(1ll << out->bits) * 8, st));
-    a.bits = out->bits; a.k = k; a.stats = d_table_stats; a.sliced = 0; a.skip_bits = 0;
+    a.bits = out->bits; a.k = k; a.stats = d_table_stats; a.sliced = 0;
     const int fan = 1 << a.bits;
     if (fan <= 64) return launch_split_c<256>(a, st);
     if (fan <= 256) return launch_split_c<512>(a, st);
