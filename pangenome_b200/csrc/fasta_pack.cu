@@ -842,8 +842,12 @@ extern "C" int pg_fasta_scan_pack(const uint8_t *d_fasta, int64_t nbytes, uint32
         // 32-byte chunks, local header detection: aggregates (uint4 per tile), one-CTA scan, pack
         uint4 *aggs = reinterpret_cast<uint4 *>(d_ws);
         TileEntry *ent = reinterpret_cast<TileEntry *>(reinterpret_cast<char *>(d_ws) + (ntiles < 1 ? 1 : ntiles) * sizeof(uint4));
-        const int sms_ = pg_num_sms();
-        const int grid_x = (int)(ntiles < (int64_t)sms_ * 4 ? (ntiles < 1 ? 1 : ntiles) : (int64_t)sms_ * 4);
+        // one CTA per tile up to 2^20 CTAs (then a grid-stride loop): with a resident-size grid of 4 CTAs per SM the 3052
+        // tiles of the 50 MB config-2 file are 5.16 per CTA - a sixth, mostly empty wave; PG_K1_GRID=<CTAs per SM> restores that
+        static int k1_grid = -1;
+        if (k1_grid < 0) { const char *e = getenv("PG_K1_GRID"); k1_grid = e ? atoi(e) : 0; }
+        const int64_t cap_x = k1_grid > 0 ? (int64_t)pg_num_sms() * k1_grid : (1ll << 20);
+        const int grid_x = (int)(ntiles < cap_x ? (ntiles < 1 ? 1 : ntiles) : cap_x);
         if (ntiles > 0) k1x_tile_aggs<<<grid_x, X_THREADS, 0, stream>>>(d_fasta, nbytes, ntiles, aggs);
         k1x_scan<<<1, XB_THREADS, 0, stream>>>(aggs, ntiles, ent, d_pk2, d_amb, d_seq_off, cap_records, d_counts);
         if (ntiles > 0) k1x_pack<<<grid_x, X_THREADS, 0, stream>>>(d_fasta, nbytes, ntiles, ent, d_pk2, d_amb, d_hdr_off, d_seq_off, cap_records);
