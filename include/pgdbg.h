@@ -261,7 +261,7 @@ int pg_region_build(const pg_table *t, const uint64_t *d_records, const int64_t 
  * Buckets and slots are placed by mix64 of the 2-BIT code: the table must carry hash_kind = 1 (and region_bits = 12).
  * PG_MODE_CANONICAL only.  One pg_cbuckets per partition level; all levels of a round share the wide spill.
  * pg_kmer_partition_c (K2a-c): arguments as pg_kmer_partition_to; zeroes out->d_counts and *out->d_wide_count.
- * pg_records_resplit_c (K2c-c): bucket s of `in` is split 2^bits ways (1..8) by hash bits [in->bits, in->bits + bits)
+ * pg_records_resplit_c (K2c-c): bucket s of `in` is split 2^bits ways (1..10; the builder uses at most 8) by hash bits [in->bits, in->bits + bits)
  *   into buckets [s << bits, ...) of `out` (out->bits == in->bits + bits; zeroes out->d_counts).
  * pg_region_build_c (K3s-c): bucket b of `b` (b->bits == log2(capacity) - 12) becomes region b of the table, then the
  *   wide spill is upserted with L2 atomics.  first_round as pg_region_build.  last_round = 0: more rounds follow - the

@@ -86,6 +86,15 @@ class CompactBuckets:
         return self.records.numel() * 8 + self.wide.numel() * 8
 
 
+def exchange_record_counts(send_counts, recv, world):
+    """The one collective on the compact multi-GPU data path.  ``send_counts``: [compact count per owner rank | wide count
+    per owner rank] as K2a-c left them (2 * world int64); ``recv``: a (world, 2) int64 buffer that ends up holding, per
+    SOURCE rank, (compact records, wide records) that rank stored into this rank's receive buffers.  Also the barrier
+    that orders the peer stores before they are read.  Returns (compact counts, wide counts), contiguous."""
+    dist.all_to_all_single(recv, send_counts.view(2, world).t().contiguous())
+    return recv[:, 0].contiguous(), recv[:, 1].contiguous()
+
+
 def plan_rounds(n_bases_max, rounds=None, round_len=None, tile=_TILE):
     """(n_rounds, round_len): the stream [0, n_bases_max) in equal rounds, a whole number of K2a tiles each."""
     n_bases_max = max(1, int(n_bases_max))
@@ -107,7 +116,7 @@ def plan_levels(region_log, world):
     if env:                                  # experiment switch: "6,6,6"
         try:
             lv = [int(x) for x in env.split(",")]
-            if sum(lv) == region_log and all(1 <= x <= (10 if i == 0 else 8) for i, x in enumerate(lv)):
+            if sum(lv) == region_log and all(1 <= x <= 10 for x in lv):
                 return lv
         except ValueError:
             pass
@@ -443,11 +452,10 @@ class RoundBuilder:
                     bs = self.sets[0]
                     x0 = stamp(B)
                     # one all-to-all for both counters: [owner][compact, wide] -> [source][compact, wide]
-                    dist.all_to_all_single(self.crecv[i], self.csend_counts[i].view(2, W).t().contiguous())
+                    recv_c, recv_w = exchange_record_counts(self.csend_counts[i], self.crecv[i], W)
                     self._ev_a2a = torch.cuda.Event()
                     self._ev_a2a.record(B)
                     x1 = stamp(B)
-                    recv_c, recv_w = self.crecv[i][:, 0].contiguous(), self.crecv[i][:, 1].contiguous()
                     own = self.own[i].value
                     arrived = PgCBuckets(own, recv_c.data_ptr(), self.cap_wire, self.owner_bits, 0, bs.wide.data_ptr(), bs.wide_count.data_ptr(),
                                          bs.wide_cap, None, None, 0, 0)

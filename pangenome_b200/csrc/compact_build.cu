@@ -728,8 +728,8 @@ extern "C" int pg_records_resplit_c(const pg_cbuckets *in, int bits, const pg_cb
     CSplitArgs a;
     int rc = make_cbuckets(in, "pg_records_resplit_c", a.in); if (rc) return rc;
     rc = make_cbuckets(out, "pg_records_resplit_c", a.out); if (rc) return rc;
-    if (bits < 1 || bits > 8 || in->bits > 13 || out->bits != in->bits + bits || k < 1 || k > 27 || in->d_records == out->d_records)
-        return pg_fail(PG_ERR_INVALID, "pg_records_resplit_c: bad geometry (bits 1..8, in->bits <= 13, out->bits == in->bits + bits, distinct buffers)");
+    if (bits < 1 || bits > 10 || in->bits > 13 || out->bits != in->bits + bits || k < 1 || k > 27 || in->d_records == out->d_records)
+        return pg_fail(PG_ERR_INVALID, "pg_records_resplit_c: bad geometry (bits 1..10, in->bits <= 13, out->bits == in->bits + bits, distinct buffers)");
     cudaStream_t st = (cudaStream_t)stream_;
     PG_CUDA(cudaMemsetAsync(out->d_counts, 0, (size_t)(1ll << out->bits) * 8, st));
     a.bits = bits; a.k = k; a.stats = d_table_stats; a.sliced = 1;

@@ -185,3 +185,32 @@ def test_round_planning():
     assert n * r >= 2_000_000_000 and r % 8192 == 0 and n == 15
     assert builder.table_capacity_for(50_000_000, 180e9) == 1 << 27
     assert builder.table_capacity_for(4_000_000_000, 170e9) == 1 << 32          # capped by the free HBM
+
+
+def _count_exchange_worker(rank, world, port, out):
+    _init(rank, world, port)
+    from pangenome_b200 import builder
+    # rank r "stored" 100 * r + o compact and 7000 + 10 * r + o wide records into owner o's receive buffers
+    send = torch.tensor([100 * rank + o for o in range(world)] + [7000 + 10 * rank + o for o in range(world)], dtype=torch.int64)
+    recv = torch.zeros((world, 2), dtype=torch.int64)
+    c, w = builder.exchange_record_counts(send, recv, world)
+    ok = c.tolist() == [100 * s + rank for s in range(world)] and w.tolist() == [7000 + 10 * s + rank for s in range(world)]
+    ok = ok and c.is_contiguous() and w.is_contiguous()
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_compact_count_exchange_gloo():
+    """the all-to-all of the compact build: per owner (compact, wide) counts in, per source (compact, wide) counts out"""
+    _spawn(_count_exchange_worker, 2, 29577)
+
+
+def test_plan_levels():
+    from pangenome_b200 import builder
+    for world in (1, 2, 8):
+        for region_log in range(0, 19):
+            lv = builder.plan_levels(region_log, world)
+            assert sum(lv) == region_log and len(lv) <= 3, (region_log, world, lv)
+            assert lv[0] <= 10 and all(1 <= x <= 8 for x in lv[1:]), (region_log, world, lv)
+    assert builder.plan_levels(13, 1) == [8, 5] and builder.plan_levels(18, 2) == [10, 8]
