@@ -105,7 +105,7 @@ def plan_rounds(n_bases_max, rounds=None, round_len=None, tile=_TILE):
     return (n_bases_max + round_len - 1) // round_len, round_len
 
 
-def plan_levels(region_log, world):
+def plan_levels(region_log, world, max_bits=8):
     """Fan-out bits of the partition levels that take a record down to one bucket per table region (2^region_log of
     them).  Level 0 is K2a's (one GPU) or K2b's (what arrived over the wire) and goes through the bucket-set API (<= 2^10
     buckets); every further level is a sliced re-split (pg_records_resplit, <= 2^8 ways, input <= 2^13 buckets).  As few
@@ -124,7 +124,7 @@ def plan_levels(region_log, world):
         return [region_log]
     first = 8 if world == 1 else min(10, max(6, region_log - 8))
     rest = region_log - first
-    if rest <= 8:
+    if rest <= max_bits:          # compact records take one 2^9-way pass (config 3: 11.7 ms against 13.3 ms for [4, 5])
         return [first, rest]
     a = rest // 2
     return [first, a, rest - a]
@@ -296,8 +296,9 @@ class RoundBuilder:
         cap = engine.next_pow2(cap)
         cap_log = cap.bit_length() - 1
         region = bool(rb) and 0 <= cap_log - rb <= self.MAX_REGION_LOG
+        self._level_bits = 9 if (region and self._compact_pref) else 8        # widest re-split level (K2c-c: 9, K2c: 8)
         if region:
-            self.levels = plan_levels(cap_log - rb, self.world)
+            self.levels = plan_levels(cap_log - rb, self.world, self._level_bits)
             sub_bits = self.levels[0]
         else:
             self.levels = None
@@ -478,10 +479,10 @@ class RoundBuilder:
                 if self.compact:
                     # K2c-c: 8-byte records level by level down to one bucket per region, then K3s-c (+ the wide spill)
                     region_log = (t.capacity >> self.region_bits).bit_length() - 1
-                    levels = [self.sub_bits] + plan_levels(region_log, W)[1:] if region_log > self.sub_bits else [self.sub_bits]
+                    levels = [self.sub_bits] + plan_levels(region_log, W, self._level_bits)[1:] if region_log > self.sub_bits else [self.sub_bits]
                     if sum(levels) != region_log:              # sampled capacity: one or two even levels below K2a's buckets
                         rest = region_log - self.sub_bits
-                        levels = [self.sub_bits] + ([rest] if rest <= 8 else [rest // 2, rest - rest // 2])
+                        levels = [self.sub_bits] + ([rest] if rest <= self._level_bits else [rest // 2, rest - rest // 2])
                     cur_c, bits = bs.c, self.sub_bits
                     bufs = [self.fine_records, bs.records]
                     for li, lb in enumerate(levels[1:]):

@@ -214,3 +214,4 @@ def test_plan_levels():
             assert sum(lv) == region_log and len(lv) <= 3, (region_log, world, lv)
             assert lv[0] <= 10 and all(1 <= x <= 8 for x in lv[1:]), (region_log, world, lv)
     assert builder.plan_levels(13, 1) == [8, 5] and builder.plan_levels(18, 2) == [10, 8]
+    assert builder.plan_levels(17, 1) == [8, 4, 5] and builder.plan_levels(17, 1, 9) == [8, 9] and builder.plan_levels(18, 1, 9) == [8, 5, 5]
