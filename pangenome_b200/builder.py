@@ -1,25 +1,29 @@
 """The streaming dBG builder: one code path for a single GPU and for the hash-partitioned multi-GPU build
 (replaces oakht + seq2dbg_jit_, kmer_numba.py:340-679, 1202-1230; the split is SURVEY.md 8e).
 
-A build is cut into ROUNDS of stream positions.  Per round and rank:
+A build is cut into ROUNDS of stream positions.  Per round and rank (default: COMPACT 8-byte update records,
+csrc/compact_build.cu - canonical mode, 4096-slot regions; the same pipeline runs on 16-byte records for the literal
+modes, 256-slot regions and inputs whose wide spill overflows):
 
-    stream A   K2a   k-mer extraction -> 16-byte update records
-                     world 1 : straight into the 2^sub_bits hash-prefix buckets (+ spill) of a local set
-                     world N : bucketed by OWNER only and stored into the owners' receive buffers over NVLink
-                               (CUDA IPC peer memory) - 8192-position tiles give 16 KB runs per peer
-    stream B   [N>1] all-to-all of the W record counts (NCCL) - also the barrier that orders the peer stores
-               [N>1] K2b  what arrived (one segment per source) -> hash-prefix buckets (+ spill)
-                     plan (clamped counts, PG_STAT_LOST), K3 region sweep into the table (L2 atomics)
-               or, on one GPU while the table has at most 2^18 regions of 4096 slots (``region_bits``):
-                     K2c  every hash-prefix bucket -> one bucket per table region,
-                     K3s  one CTA per region builds it in SHARED MEMORY and writes it to HBM once (csrc/region_build.cu)
+    stream A   K2a-c  k-mer extraction -> 8-byte records for interior positions, 16-byte wide records for the rest
+                      world 1 : straight into the 2^sub_bits hash-prefix buckets of a local set (+ its wide spill)
+                      world N : bucketed by OWNER only and stored into the owners' receive buffers over NVLink
+                                (CUDA IPC peer memory) - 8192-position tiles give 8 KB runs per peer at 8 GPUs
+    stream B   [N>1] all-to-all of the 2 W record counts (NCCL) - also the barrier that orders the peer stores
+               [N>1] K2b-c  what arrived (one segment per source) -> hash-prefix buckets
+                     K2c-c  every hash-prefix bucket -> one bucket per table region (one or two levels),
+                     K3s-c  one CTA per region builds it in SHARED MEMORY from the 2-bit codes and writes it to HBM once
+                            (base-5 keys in the last round), then the wide records are upserted with L2 atomics
+               or, for tables beyond 2^18 regions: plan (clamped counts, PG_STAT_LOST), K3 region sweep with L2 atomics
+               on 16-byte records
 
-Two record buffers alternate, so K2a of round r+1 runs while K2b/K3 of round r drain the other buffer: the
-issue-bound extraction (and its NVLink write-out) overlaps the table sweep, which is bound by L2 sector requests.
+Two record buffers alternate, so K2a of round r+1 runs while K2b/K2c/K3s of round r drain the other buffer: the
+extraction (and its NVLink write-out) overlaps the table build.
 Nothing is read back inside a build; verify() looks at the table's statistics block afterwards (overflow /
-lost-record flags) and the callers fall back to a safer configuration (more rounds, larger table) when it trips.
+lost-record flags) and the callers fall back to a safer configuration (16-byte records, more rounds, larger table)
+when it trips.
 
-Memory: a round holds round_len x 16 B x slack per buffer, the table 16 B per slot; both are sized for the
+Memory: a round holds round_len x 8 (or 16) B x slack per buffer, the table 16 B per slot; both are sized for the
 HBM that is actually free (180 GB on a B200), so inputs far larger than one round stream through.
 """
 import ctypes
