@@ -193,3 +193,41 @@ def test_emul_compact_records_big(emul, k, form):
     ref = oracle.run(data, k, stages=2)
     assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2])
     assert np.array_equal(rk, ref["rdbg"])
+
+
+def test_emul_compact_records_random_inputs(emul):
+    """seeded random multi-record inputs (N runs, lowercase, IUPAC, records shorter than k, poly-A, palindromic repeats)
+    through the compact-record logic, rolling and compile-time-k forms, against the oracle"""
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    emul.emul_compact_bad.restype = ctypes.c_int64
+    for it in range(24):
+        k = int(rng.choice([17, 20, 21, 26, 27, 11, 5]))
+        recs = []
+        for r in range(int(rng.integers(1, 6))):
+            n = int(rng.choice([0, k - 1, k, k + 2, int(rng.integers(200, 4000))]))
+            s = bytearray(acgt[rng.integers(0, 4, n)].tobytes())
+            if n > 300 and rng.random() < 0.5:
+                a = int(rng.integers(0, n - 100)); s[a:a + int(rng.integers(1, 60))] = b"N" * len(s[a:a + int(rng.integers(1, 60))])
+            if n > 300 and rng.random() < 0.4:
+                a = int(rng.integers(0, n - 100)); s[a:a + 50] = bytes(s[a:a + 50]).lower()
+            if n > 300 and rng.random() < 0.3:
+                a = int(rng.integers(0, n - 100)); s[a] = ord("R")
+            if n > 300 and rng.random() < 0.4:
+                a = int(rng.integers(0, n - 120)); s[a:a + 90] = b"A" * 90
+            if n > 300 and rng.random() < 0.4:
+                a = int(rng.integers(0, n - 120)); s[a:a + 64] = b"ACGT" * 16        # palindromic at every even k
+            recs.append(b">r%d\n" % r + bytes(s) + b"\n")
+        data = b"".join(recs)
+        ref = oracle.run(data, k, stages=1)
+        if ref["ub_count"]:
+            continue
+        pk2, amb, hdr, so, counts = run_pack(emul, data, "emul_pack3")
+        for form in (1, 2):
+            emul.emul_set_compact(form)
+            try:
+                (ks, vs, cs), _ = run_dbg(emul, pk2, amb, so, k, 2)
+                assert emul.emul_compact_bad() == 0
+            finally:
+                emul.emul_set_compact(0)
+            assert np.array_equal(ks, ref["dbg"][0]) and np.array_equal(vs, ref["dbg"][1]) and np.array_equal(cs, ref["dbg"][2]), (it, k, form)
